@@ -1,0 +1,53 @@
+"""ctypes binding of libpapr_b200.so (the C ABI declared in include/papr_b200.h).
+
+There is no fallback: if the library is missing or a call fails, a :class:`PaprError` is raised.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpapr_b200.so")
+
+_c = ctypes
+_ptr, _i64, _i32, _f32 = _c.c_void_p, _c.c_int64, _c.c_int, _c.c_float
+
+# name -> argtypes; must list every symbol declared in include/papr_b200.h (tests/test_abi.py checks that)
+SIGNATURES = {
+    "papr_abi_version": [],
+    "papr_status_string": [_i32],
+    "papr_last_cuda_error": [],
+    "papr_select_topk": [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i32, _f32, _ptr, _ptr],
+}
+_RESTYPE = {"papr_status_string": _c.c_char_p, "papr_last_cuda_error": _c.c_char_p}
+
+
+class PaprError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """The loaded library; raises PaprError if it has not been built (python -m papr_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise PaprError(f"{LIB_PATH} is missing: build it with `python -m papr_b200.build` "
+                            "(there is no CPU or PyTorch fallback for the CUDA path)")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.argtypes = argtypes
+            fn.restype = _RESTYPE.get(name, _i32)
+        _lib = handle
+    return _lib
+
+
+def check(status, what):
+    if status != 0:
+        l = lib()
+        msg = l.papr_status_string(status).decode()
+        if status == -2:
+            msg += ": " + l.papr_last_cuda_error().decode()
+        raise PaprError(f"{what} failed: {msg}")

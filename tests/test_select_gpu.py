@@ -1,0 +1,89 @@
+"""GPU parity of stage a1 (fused distance + top-K) against the CPU oracle and the reference's golden vectors."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import papr_oracle as O
+from papr_b200.config import make_config
+from tests.parity import load_golden, topk_sets_match
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(rays_o, rays_d, points, K, eps=1e-6):
+    from papr_b200 import ops
+    idx = ops.select_topk(rays_o.cuda(), rays_d.cuda(), points.cuda(), K, eps)
+    torch.cuda.synchronize()
+    return idx.cpu()
+
+
+def _compare(rays_o, rays_d, points, K, eps=1e-6):
+    got = _run(rays_o, rays_d, points, K, eps)
+    want, kth = O.select_topk(rays_o, rays_d, points, K, eps)
+    assert got.dtype == torch.int32 and got.shape == want.shape
+    if torch.equal(got.long(), want):      # same order too: (distance, index) ascending
+        return 0
+    dist = O.select_distances(rays_o, rays_d, points, eps)
+    ok, n = topk_sets_match(got, want, lambda i: torch.gather(dist, -1, i), kth)
+    assert ok, "top-K sets differ beyond ties at the K-th distance"
+    return n
+
+
+def test_select_golden_reference_sets(golden_dir):
+    """Index sets equal the sets the real reference produced (fixture written by oracle/make_golden.py)."""
+    g = load_golden(golden_dir, "select_24x24x2_p3000")
+    cfg = make_config("chair")
+    params = O.init_params(cfg, int(g["P"]), seed=2, cloud="shell")
+    assert abs(O.params_checksum(params) - float(g["params_checksum"])) < 1e-6 * abs(float(g["params_checksum"]))
+    rays_o, rays_d = torch.from_numpy(g["rays_o"]), torch.from_numpy(g["rays_d"])
+    got = _run(rays_o, rays_d, params["points"], 20)
+    got_sorted = torch.sort(got, -1).values
+    ref_sorted = torch.from_numpy(g["idx_sorted"])
+    diff = (got_sorted != ref_sorted).any(-1)
+    if diff.any():
+        dist = O.select_distances(rays_o, rays_d, params["points"])
+        ok, _ = topk_sets_match(got, ref_sorted, lambda i: torch.gather(dist, -1, i), torch.from_numpy(g["kth"]))
+        assert ok
+
+
+@pytest.mark.parametrize("H,W,P,K,views,cloud", [
+    (16, 16, 3000, 20, 1, "cube"), (7, 5, 257, 20, 3, "shell"), (33, 31, 2049, 30, 2, "cube"),
+    (4, 4, 33, 32, 1, "cube"), (1, 1, 21, 20, 1, "cube"), (40, 40, 30000, 20, 1, "shell"), (3, 3, 4100, 1, 2, "cube"),
+])
+def test_select_matches_oracle(H, W, P, K, views, cloud):
+    cfg = make_config("chair")
+    params = O.init_params(cfg, P, seed=H * 131 + P, cloud=cloud)
+    rays_o, rays_d, _ = O.synthetic_rays(H * 4, W * 4, cfg.dataset.coord_scale, n_views=views, seed=P, h0=H, h1=2 * H, w0=W, w1=2 * W)
+    _compare(rays_o, rays_d, params["points"], K)
+
+
+def test_select_exact_ties_and_lattice():
+    """The reference's cube-lattice init (model.py:246-256) gives many exactly tied distances."""
+    cfg = make_config("chair")
+    xs = np.linspace(-12, 12, 12)
+    pts = torch.tensor(np.array([[i, j, k] for i in xs for j in xs for k in xs]), dtype=torch.float32)
+    rays_o, rays_d, _ = O.synthetic_rays(64, 64, 10.0, n_views=1, seed=5, h0=20, h1=44, w0=20, w1=44)
+    # axis-aligned rays through the lattice: plenty of exact ties
+    rays_d[0, 0, 0] = torch.tensor([0.0, 0.0, -1.0])
+    rays_d[0, 0, 1] = torch.tensor([1.0, 0.0, 0.0])
+    _compare(rays_o, rays_d, pts, 20)
+
+
+def test_select_unnormalised_directions_and_duplicates():
+    """rays_d is used as given (model.py:277: den = d.d + eps); duplicated points must tie-break by index."""
+    g = torch.Generator().manual_seed(0)
+    pts = torch.randn(500, 3, generator=g) * 5
+    pts = torch.cat([pts, pts[:100]])            # exact duplicates
+    rays_o = torch.randn(2, 3, generator=g) * 20
+    rays_d = torch.randn(2, 9, 9, 3, generator=g) * torch.rand(2, 9, 9, 1, generator=g) * 3
+    got = _run(rays_o, rays_d, pts, 20)
+    want, _ = O.select_topk(rays_o, rays_d, pts, 20)
+    assert torch.equal(got.long(), want)          # identical order: (key, index)
+
+
+def test_select_rejects_bad_arguments():
+    from papr_b200 import ops
+    with pytest.raises(ValueError):
+        ops.select_topk(torch.zeros(1, 3).cuda(), torch.zeros(1, 2, 2, 3).cuda(), torch.zeros(10, 3).cuda(), 20)
+    with pytest.raises(ValueError):
+        ops.select_topk(torch.zeros(1, 3).cuda(), torch.zeros(1, 2, 2, 3).cuda(), torch.zeros(100, 3).cuda(), 33)
