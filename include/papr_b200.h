@@ -46,6 +46,47 @@ int papr_select_topk(const float *rays_o, const float *rays_d, const float *poin
                      int64_t n_views, int64_t rays_per_view, int64_t P, int K, float eps,
                      int32_t *idx_out, void *stream);
 
+/*
+ * Tensor-core building blocks (stages a7/a8/a12).  Activations use the library's "tile-blocked" bf16 layout: a logical
+ * [rows, cols] matrix (rows % 128 == 0, cols % 64 == 0) stored as [rows/128][cols/64] blocks of 16 KB, each block
+ * 128 rows x 64 columns with the eight 16-byte chunks of a row XOR-swizzled by (row & 7) -- the shared-memory image
+ * tcgen05.mma consumes, moved by 1-D TMA bulk copies.
+ */
+
+/* fp32 row-major (src_rows x src_cols, leading dim ld) -> tile-blocked bf16 (rows_pad x cols_pad, zero padded). */
+int papr_blocked_from_f32(const float *src, int64_t src_rows, int src_cols, int64_t ld, void *dst,
+                          int64_t rows_pad, int cols_pad, void *stream);
+/* tile-blocked bf16 (cols_pad wide) -> fp32 row-major (dst_rows x dst_cols, leading dim ld). */
+int papr_blocked_to_f32(const void *src, int cols_pad, float *dst, int64_t dst_rows, int dst_cols, int64_t ld,
+                        void *stream);
+/*
+ * torch Linear weight (src_rows x src_cols fp32, leading dim ld; reference models/mlp.py:36, attn.py:204-205) -> bf16
+ * weight image for papr_linear_bf16: element (n,k) = scale * W[n][k] (transpose=0) or scale * W[k][n] (transpose=1),
+ * zero padded to N x K (N,K multiples of 16, <= 256).  Image size: ceil(K/64) * N * 128 bytes.
+ */
+int papr_pack_weight(const float *w, int64_t ld, int src_rows, int src_cols, int transpose, int N, int K,
+                     float scale, void *image, void *stream);
+/*
+ * One Linear layer, replaces nn.Linear + activation inside models/mlp.py:53-58 (and w_k/w_q of attn.py:217-218):
+ *   Y = act(X W^T + bias)    X: tile-blocked bf16 [rows, ceil(K/64)*64];  fp32 accumulation in TMEM.
+ * Outputs (any combination): y_blocked tile-blocked bf16 [rows, ceil(N/64)*64]; y_f32 fp32 row-major (ldy);
+ * sign_bits_out [rows, ceil(N/64)] u64, bit j of word g = (pre-activation column 64g+j > 0);
+ * colsum[N] += column sums of the bf16 output (bias gradients).
+ * Backward use (dgrad): X = dZ, weight image packed with transpose=1, sign_bits_in = the forward layer's sign bits:
+ * output column j is multiplied by 1 (bit set) or `slope` (bit clear), i.e. by act'(.) of relu/leakyrelu.
+ * act: 0 none, 1 relu/leakyrelu with negative slope `slope`.  rows % 128 == 0; N a multiple of 32, K a multiple of 16, both <= 256.
+ */
+int papr_linear_bf16(const void *x, const void *w_image, const float *bias, void *y_blocked, float *y_f32,
+                     int64_t ldy, uint64_t *sign_bits_out, const uint64_t *sign_bits_in, float *colsum,
+                     int64_t rows, int N, int K, int act, float slope, void *stream);
+/*
+ * Weight gradient of a Linear layer (autograd of models/mlp.py:53-58): C[a,b] += sum_rows A[row,a] * B[row,b] with
+ * A, B tile-blocked bf16 (a_cols, b_cols wide; a_cols >= 128*ceil(a_valid/128)); C fp32 (leading dim ldc), updated
+ * atomically; transpose_out stores C[b][a] instead.  dW = papr_wgrad(dZ, X).
+ */
+int papr_wgrad_bf16(const void *a_blocked, int a_cols, const void *b_blocked, int b_cols, float *c, int64_t ldc,
+                    int a_valid, int b_valid, int transpose_out, int64_t rows, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -17,6 +17,11 @@ SIGNATURES = {
     "papr_status_string": [_i32],
     "papr_last_cuda_error": [],
     "papr_select_topk": [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i32, _f32, _ptr, _ptr],
+    "papr_blocked_from_f32": [_ptr, _i64, _i32, _i64, _ptr, _i64, _i32, _ptr],
+    "papr_blocked_to_f32": [_ptr, _i32, _ptr, _i64, _i32, _i64, _ptr],
+    "papr_pack_weight": [_ptr, _i64, _i32, _i32, _i32, _i32, _i32, _f32, _ptr, _ptr],
+    "papr_linear_bf16": [_ptr, _ptr, _ptr, _ptr, _ptr, _i64, _ptr, _ptr, _ptr, _i64, _i32, _i32, _i32, _f32, _ptr],
+    "papr_wgrad_bf16": [_ptr, _i32, _ptr, _i32, _ptr, _i64, _i32, _i32, _i32, _i64, _ptr],
 }
 _RESTYPE = {"papr_status_string": _c.c_char_p, "papr_last_cuda_error": _c.c_char_p}
 

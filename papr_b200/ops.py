@@ -25,3 +25,79 @@ def select_topk(rays_o, rays_d, points, K, eps=1e-6):
     check(lib().papr_select_topk(ro.data_ptr(), rd.data_ptr(), pts.data_ptr(), N, H * W, P, K, float(eps),
                                  idx.data_ptr(), _stream()), "papr_select_topk")
     return idx
+
+
+# --------------------------------------------------------------------------- tensor-core building blocks
+def pad_rows(n):
+    return (n + 127) // 128 * 128
+
+
+def pad_cols(n):
+    return (n + 63) // 64 * 64
+
+
+class Blocked:
+    """A tile-blocked bf16 activation (see include/papr_b200.h): raw uint8 storage + logical shape."""
+
+    def __init__(self, rows, cols, device, zero=False):
+        self.rows, self.cols = rows, cols
+        self.rows_pad, self.cols_pad = pad_rows(rows), pad_cols(cols)
+        alloc = torch.zeros if zero else torch.empty
+        self.buf = alloc(self.rows_pad * self.cols_pad * 2, dtype=torch.uint8, device=device)
+
+    def data_ptr(self):
+        return self.buf.data_ptr()
+
+    @staticmethod
+    def from_f32(t, cols_pad=None):
+        t = _f32c(t)
+        out = Blocked(t.shape[0], t.shape[1], t.device)
+        if cols_pad:
+            out.cols_pad = cols_pad
+            out.buf = torch.empty(out.rows_pad * cols_pad * 2, dtype=torch.uint8, device=t.device)
+        check(lib().papr_blocked_from_f32(t.data_ptr(), t.shape[0], t.shape[1], t.stride(0), out.data_ptr(),
+                                          out.rows_pad, out.cols_pad, _stream()), "papr_blocked_from_f32")
+        return out
+
+    def to_f32(self, rows=None, cols=None):
+        rows = self.rows if rows is None else rows
+        cols = self.cols if cols is None else cols
+        out = torch.empty((rows, cols), dtype=torch.float32, device=self.buf.device)
+        check(lib().papr_blocked_to_f32(self.data_ptr(), self.cols_pad, out.data_ptr(), rows, cols, out.stride(0),
+                                        _stream()), "papr_blocked_to_f32")
+        return out
+
+
+def pack_weight(w, N, K, transpose=False, scale=1.0):
+    """bf16 weight image (uint8 tensor) for linear_bf16 from a torch Linear weight (out,in)."""
+    w = _f32c(w)
+    img = torch.empty(((K + 63) // 64) * N * 128, dtype=torch.uint8, device=w.device)
+    check(lib().papr_pack_weight(w.data_ptr(), w.stride(0), w.shape[0], w.shape[1], int(transpose), N, K, float(scale),
+                                 img.data_ptr(), _stream()), "papr_pack_weight")
+    return img
+
+
+def linear_bf16(x, w_image, N, K, bias=None, act=False, slope=0.0, out_blocked=True, out_f32=False,
+                sign_bits_out=False, sign_bits_in=None, colsum=None):
+    """Y = act(X W^T + b) on tcgen05 (see papr_linear_bf16).  Returns (Blocked|None, f32|None, bits|None)."""
+    dev = x.buf.device
+    rows_pad = x.rows_pad
+    assert x.cols_pad == pad_cols(K), (x.cols_pad, K)
+    yb = Blocked(x.rows, N, dev) if out_blocked else None
+    yf = torch.empty((rows_pad, N), dtype=torch.float32, device=dev) if out_f32 else None
+    bits = torch.empty((rows_pad, pad_cols(N) // 64), dtype=torch.int64, device=dev) if sign_bits_out else None
+    check(lib().papr_linear_bf16(
+        x.data_ptr(), w_image.data_ptr(), bias.data_ptr() if bias is not None else None,
+        yb.data_ptr() if yb is not None else None, yf.data_ptr() if yf is not None else None, N,
+        bits.data_ptr() if bits is not None else None, sign_bits_in.data_ptr() if sign_bits_in is not None else None,
+        colsum.data_ptr() if colsum is not None else None, rows_pad, N, K, int(act), float(slope), _stream()),
+        "papr_linear_bf16")
+    return yb, yf, bits
+
+
+def wgrad_bf16(a, b, out, a_valid, b_valid, transpose_out=False):
+    """out[a,b] += sum_rows A[row,a] B[row,b]  (out fp32, atomically accumulated)."""
+    assert a.rows_pad == b.rows_pad
+    check(lib().papr_wgrad_bf16(a.data_ptr(), a.cols_pad, b.data_ptr(), b.cols_pad, out.data_ptr(), out.stride(0),
+                                a_valid, b_valid, int(transpose_out), a.rows_pad, _stream()), "papr_wgrad_bf16")
+    return out
