@@ -87,6 +87,63 @@ int papr_linear_bf16(const void *x, const void *w_image, const float *bias, void
 int papr_wgrad_bf16(const void *a_blocked, int a_cols, const void *b_blocked, int b_cols, float *c, int64_t ldc,
                     int a_valid, int b_valid, int transpose_out, int64_t rows, void *stream);
 
+/*
+ * Per-ray CUDA-core stages.  Rows are (ray, candidate) pairs, row = ray*K + k; M = R*K rows, padded to 128.
+ * L = positional-encoding order (same for every feature; embed_type 1), S = 1+2L, dk = 9S, dv = 6S + F.
+ */
+
+/*
+ * Stages a2-a6 -- replaces the gathers of PAPR._get_points/_get_kqv, PAPR._calculate_distances, posenc and the key
+ * stack's input LayerNorm (reference models/model.py:285-310,330,396-437; models/utils.py:232-257; attn.py:39-42,172-191).
+ *   kin (M_pad, dk_pad) tile-blocked bf16 = LayerNorm([PE(point), PE(proj), PE(D)]) with affine ln_a, ln_b (dk)
+ *   vin (M_pad, dv_pad) tile-blocked bf16 = [PE(proj), PE(D), pc_feats[idx]]
+ * kin_f32 (M,dk) / vin_f32 (M,dv): optional fp32 copies of the same values (parity taps), may be null.
+ */
+int papr_attn_prologue_fwd(const float *rays_o, const float *rays_d, const float *points, const float *feats,
+                           const int32_t *idx, const float *ln_a, const float *ln_b, int64_t R,
+                           int64_t rays_per_view, int K, int L, int F, float eps, void *kin, int dk_pad,
+                           void *vin, int dv_pad, float *kin_f32, float *vin_f32, void *stream);
+/*
+ * Backward of the above (autograd of the same reference lines; the raw-position key features are detached,
+ * model.py:405).  Gradients are ACCUMULATED (atomically) into g_points (P,3), g_feats (P,F), g_ln_a/g_ln_b (dk).
+ * dkin/dvin: tile-blocked bf16 gradients, or fp32 row-major taps dkin_f32 (M,dk) / dvin_f32 (M,dv) if non-null.
+ */
+int papr_attn_prologue_bwd(const float *rays_o, const float *rays_d, const float *points, const int32_t *idx,
+                           const float *ln_a, int64_t R, int64_t rays_per_view, int K, int L, int F, float eps,
+                           const void *dkin, int dk_pad, const void *dvin, int dv_pad, const float *dkin_f32,
+                           const float *dvin_f32, float *g_points, float *g_feats, float *g_ln_a,
+                           float *g_ln_b, void *stream);
+/*
+ * Stages a6 (key output LayerNorm), a8 and a9 -- replaces FeedForward.outnorm + AttentionLayer + the blend of
+ * PAPR.forward/evaluate (reference attn.py:39-42,117,212-226,53-54; models/model.py:519-534).
+ * Uses score = (W_k^T q'/sqrt(d)) . LN(h5) + q'.b_k/sqrt(d): the caller passes ua (R,256) = (W_k^T q'/sqrt d) * a_2 and
+ * cprime (R) = (W_k^T q'/sqrt d) . b_2 + q'.b_k/sqrt d, with a_2,b_2 the key outnorm affine terms.
+ *   h5 (M_pad,256) tile-blocked bf16 key-stack output (or fp32 tap h5_f32 (M,256)); v (M_pad, ldv) fp32 value-stack output
+ *   fused (R,C); attn (R,K+1) softmax incl. background, un-renormalised (model.py:481/529);
+ *   sc (M) activated scores before influence; stats (M,2) = LayerNorm mean and 1/(std+eps) (saved for backward)
+ */
+int papr_score_blend_fwd(const void *h5, const float *h5_f32, const float *ua, const float *cprime,
+                         const float *influ, const int32_t *idx, const float *v, int64_t ldv, int64_t R, int K,
+                         int C, int score_relu, int normalize, float bkg_score, float eps, float *fused,
+                         float *attn, float *sc, float *stats, void *stream);
+/*
+ * Backward of the blend (model.py:524-534): from d_fused (R,C) and optional d_attn (R,K+1) to
+ *   dv_blocked (M_pad,64) tile-blocked bf16 (C <= 64), d_score (M) gradient of the pre-activation score,
+ *   g_influ (P) += , g_bias_v (C) += column sums of dv.
+ */
+int papr_blend_bwd(const float *d_fused, const float *d_attn, const float *attn, const float *sc,
+                   const float *influ, const int32_t *idx, const float *v, int64_t ldv, int64_t R, int K, int C,
+                   int score_relu, int normalize, void *dv_blocked, float *d_score, float *g_influ,
+                   float *g_bias_v, void *stream);
+/*
+ * Backward of the folded LayerNorm + scaled dot: d_score (M) -> dh5 (M_pad,256) tile-blocked bf16 (+ optional fp32 tap),
+ * zsum (R,256) = sum_k d_score * normalised h5 (= d ua), dssum (R) = sum_k d_score (= d cprime),
+ * g_bias5 (256) += column sums of dh5.
+ */
+int papr_key_score_bwd(const float *d_score, const void *h5, const float *h5_f32, const float *stats,
+                       const float *ua, int64_t R, int K, float eps, void *dh5_blocked, float *dh5_f32,
+                       float *zsum, float *dssum, float *g_bias5, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -71,21 +71,7 @@ def build_reference(models, cfg, params):
     return model
 
 
-def variant(name):
-    if name == "chair":
-        return make_config("chair", use_amp=False)
-    if name == "caterpillar_exposure":
-        return make_config("caterpillar_exposure", use_amp=False)
-    if name == "lego_like":     # configs/nerfsyn/lego.yml:10-15 style: leakyrelu + value skip layer
-        emb = dict(key=dict(ff_act="leakyrelu"), query=dict(ff_act="leakyrelu"),
-                   value=dict(ff_act="leakyrelu", skip_layers=[5]))
-        return make_config("chair", use_amp=False, models=dict(attn=dict(embed=emb)))
-    if name == "no_renderer":   # models.use_renderer false + value d_ff_out 3 (model.py:77-79)
-        return make_config("chair", use_amp=False,
-                           models=dict(use_renderer=False, attn=dict(embed=dict(value=dict(d_ff_out=3)))))
-    if name == "hotdog_like":   # select_k 30 (hotdog.yml), feature dim 128 (materials.yml)
-        return make_config("chair", use_amp=False, geoms=dict(points=dict(select_k=30), point_feats=dict(dim=128)))
-    raise KeyError(name)
+from tests.parity import golden_config as variant  # noqa: E402
 
 
 CASES = [

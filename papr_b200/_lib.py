@@ -21,6 +21,11 @@ SIGNATURES = {
     "papr_blocked_to_f32": [_ptr, _i32, _ptr, _i64, _i32, _i64, _ptr],
     "papr_pack_weight": [_ptr, _i64, _i32, _i32, _i32, _i32, _i32, _f32, _ptr, _ptr],
     "papr_linear_bf16": [_ptr, _ptr, _ptr, _ptr, _ptr, _i64, _ptr, _ptr, _ptr, _i64, _i32, _i32, _i32, _f32, _ptr],
+    "papr_attn_prologue_fwd": [_ptr] * 7 + [_i64, _i64, _i32, _i32, _i32, _f32, _ptr, _i32, _ptr, _i32, _ptr, _ptr, _ptr],
+    "papr_attn_prologue_bwd": [_ptr] * 5 + [_i64, _i64, _i32, _i32, _i32, _f32, _ptr, _i32, _ptr, _i32] + [_ptr] * 7,
+    "papr_score_blend_fwd": [_ptr] * 7 + [_i64, _i64, _i32, _i32, _i32, _i32, _f32, _f32] + [_ptr] * 5,
+    "papr_blend_bwd": [_ptr] * 7 + [_i64, _i64, _i32, _i32, _i32, _i32] + [_ptr] * 5,
+    "papr_key_score_bwd": [_ptr] * 5 + [_i64, _i32, _f32] + [_ptr] * 6,
     "papr_wgrad_bf16": [_ptr, _i32, _ptr, _i32, _ptr, _i64, _i32, _i32, _i32, _i64, _ptr],
 }
 _RESTYPE = {"papr_status_string": _c.c_char_p, "papr_last_cuda_error": _c.c_char_p}

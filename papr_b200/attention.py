@@ -1,0 +1,397 @@
+"""Proximity attention (reference models/attn.py ProximityAttention + the K/Q/V assembly and blend of
+models/model.py:396-437, 519-534) on the library's CUDA kernels.
+
+Data flow for one batch of rays (R rays, K candidates each, M = R*K rows):
+
+  select_topk (model.PAPR)            idx (R,K)
+  per ray, PyTorch + tcgen05 GEMMs    query stack -> q' ; ua = (q' W_k / sqrt d) * a2_k ; c' = ...      (5% of the work)
+  papr_attn_prologue_fwd              kin (M,128) , vin (M,192)    tile-blocked bf16
+  papr_linear_bf16 x5 / x8            key stack -> h5 ; value stack -> v (fp32)                          (tcgen05)
+  papr_score_blend_fwd                fused (R,C), attn (R,K+1)
+
+The backward of the per-row part is one torch.autograd.Function (RowAttentionFn) that calls the matching backward
+kernels (papr_blend_bwd, papr_key_score_bwd, papr_linear_bf16 as dgrad, papr_wgrad_bf16, papr_attn_prologue_bwd).
+The key stack's output LayerNorm, w_k and the dot with the query are folded algebraically:
+  score = q'.(W_k LN(h5) + b_k)/sqrt d = ua . z(h5) + c'   with z the normalised h5,
+which removes one 256x256 GEMM per row; its parameters therefore get their gradients through ua and c' (autograd).
+
+precision="fp32" keeps every CUDA-core kernel but routes the GEMMs through torch fp32 matmuls; it exists for the
+1e-5 parity tests, the bf16 tensor-core path is the product.
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from ._lib import check, lib
+from .nn import AttentionLayer, Embeddings, activation_slope
+
+
+def posenc(x, L, factor=2.0, mult=1.0):
+    """models/utils.py:232-242 (embed_type 1), used for the per-ray query features."""
+    parts = [x]
+    for i in range(L):
+        a = (factor ** i) * x * mult
+        parts += [torch.sin(a), torch.cos(a)]
+    return torch.flatten(torch.stack(parts, -1), start_dim=-2)
+
+
+def _ptr(t):
+    return t.data_ptr() if t is not None else None
+
+
+class _LinearBf16Fn(torch.autograd.Function):
+    """y = act(x W^T + b) for per-ray (fp32 in / fp32 out) tensors on the tcgen05 kernels."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, slope):
+        n_out, n_in = weight.shape
+        K = (n_in + 15) // 16 * 16
+        N = (n_out + 31) // 32 * 32
+        xb = ops.Blocked.from_f32(x)
+        img = ops.pack_weight(weight, N, K)
+        b = bias if n_out == N else F.pad(bias, (0, N - n_out))
+        _, y, _ = ops.linear_bf16(xb, img, N, K, bias=b.detach().contiguous(), act=slope is not None,
+                                  slope=slope or 0.0, out_blocked=False, out_f32=True)
+        y = y[: x.shape[0], :n_out]
+        ctx.save_for_backward(weight, y)
+        ctx.xb, ctx.slope, ctx.dims = xb, slope, (N, K, n_out, n_in)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        weight, y = ctx.saved_tensors
+        N, K, n_out, n_in = ctx.dims
+        g = gy
+        if ctx.slope is not None:
+            g = torch.where(y > 0, gy, gy * ctx.slope)
+        g = g.contiguous()
+        gb = ops.Blocked.from_f32(g, cols_pad=max(ops.pad_cols(n_out), 128))
+        Kd = (n_out + 15) // 16 * 16
+        Nd = ops.pad_cols(n_in)
+        img_t = ops.pack_weight(weight, Nd, Kd, transpose=True)
+        gb_lin = gb if gb.cols_pad == ops.pad_cols(Kd) else ops.Blocked.from_f32(g)
+        _, gx, _ = ops.linear_bf16(gb_lin, img_t, Nd, Kd, out_blocked=False, out_f32=True)
+        gw = torch.zeros(weight.shape, dtype=torch.float32, device=weight.device)
+        ops.wgrad_bf16(gb, ctx.xb, gw, n_out, n_in)
+        return gx[: g.shape[0], :n_in], gw, g.sum(0), None
+
+
+def _linear(x, lin, slope, precision):
+    if precision == "fp32":
+        y = F.linear(x, lin.weight, lin.bias)
+        if slope is not None:
+            y = F.leaky_relu(y, slope) if slope else F.relu(y)
+        return y
+    return _LinearBf16Fn.apply(x, lin.weight, lin.bias, slope)
+
+
+class _Shape:
+    """Static description of one call (sizes + flags) shared by forward and backward."""
+
+    def __init__(self, attn, R, rays_per_view, K):
+        self.R, self.rays_per_view, self.K = R, rays_per_view, K
+        self.M = R * K
+        self.L, self.F, self.C = attn.L, attn.F, attn.C
+        self.dk, self.dv = attn.dk, attn.dv
+        self.dk_pad, self.dv_pad = ops.pad_cols(attn.dk), ops.pad_cols(attn.dv)
+        self.eps = attn.eps
+        self.k_slope, self.v_slope = attn.k_slope, attn.v_slope
+        self.score_relu, self.normalize, self.bkg_score = attn.score_relu, attn.normalize, attn.bkg_score
+
+
+def _prologue_fwd(sh, rays_o, rays_d, points, feats, idx, ln_a, ln_b, taps=False):
+    dev = rays_d.device
+    kin = ops.Blocked(sh.M, sh.dk, dev)
+    vin = ops.Blocked(sh.M, sh.dv, dev)
+    kin32 = torch.empty((sh.M, sh.dk), device=dev) if taps else None
+    vin32 = torch.empty((sh.M, sh.dv), device=dev) if taps else None
+    check(lib().papr_attn_prologue_fwd(
+        rays_o.data_ptr(), rays_d.data_ptr(), points.data_ptr(), _ptr(feats), idx.data_ptr(), ln_a.data_ptr(),
+        ln_b.data_ptr(), sh.R, sh.rays_per_view, sh.K, sh.L, sh.F, sh.eps, kin.data_ptr(), sh.dk_pad, vin.data_ptr(),
+        sh.dv_pad, _ptr(kin32), _ptr(vin32), ops._stream()), "papr_attn_prologue_fwd")
+    return kin, vin, kin32, vin32
+
+
+def _prologue_bwd(sh, rays_o, rays_d, points, idx, ln_a, dkin, dvin, dkin32, dvin32, n_points):
+    dev = rays_d.device
+    g_points = torch.zeros((n_points, 3), device=dev)
+    g_feats = torch.zeros((n_points, sh.F), device=dev) if sh.F else None
+    g_a = torch.zeros(sh.dk, device=dev)
+    g_b = torch.zeros(sh.dk, device=dev)
+    check(lib().papr_attn_prologue_bwd(
+        rays_o.data_ptr(), rays_d.data_ptr(), points.data_ptr(), idx.data_ptr(), ln_a.data_ptr(), sh.R,
+        sh.rays_per_view, sh.K, sh.L, sh.F, sh.eps, _ptr(dkin), sh.dk_pad, _ptr(dvin), sh.dv_pad, _ptr(dkin32),
+        _ptr(dvin32), g_points.data_ptr(), _ptr(g_feats), g_a.data_ptr(), g_b.data_ptr(), ops._stream()),
+        "papr_attn_prologue_bwd")
+    return g_points, g_feats, g_a, g_b
+
+
+def _score_blend_fwd(sh, h5, h5_32, ua, cprime, influ, idx, v):
+    dev = ua.device
+    fused = torch.empty((sh.R, sh.C), device=dev)
+    attn = torch.empty((sh.R, sh.K + 1), device=dev)
+    sc = torch.empty((sh.M,), device=dev)
+    stats = torch.empty((sh.M, 2), device=dev)
+    check(lib().papr_score_blend_fwd(
+        _ptr(h5), _ptr(h5_32), ua.data_ptr(), cprime.data_ptr(), influ.data_ptr(), idx.data_ptr(), v.data_ptr(),
+        v.stride(0), sh.R, sh.K, sh.C, int(sh.score_relu), int(sh.normalize), sh.bkg_score, sh.eps, fused.data_ptr(),
+        attn.data_ptr(), sc.data_ptr(), stats.data_ptr(), ops._stream()), "papr_score_blend_fwd")
+    return fused, attn, sc, stats
+
+
+def _blend_bwd(sh, d_fused, d_attn, attn, sc, influ, idx, v, n_points):
+    dev = d_fused.device
+    dv = ops.Blocked(sh.M, sh.C, dev)
+    d_score = torch.empty((sh.M,), device=dev)
+    g_influ = torch.zeros((n_points,), device=dev)
+    g_bv = torch.zeros((sh.C,), device=dev)
+    check(lib().papr_blend_bwd(
+        d_fused.data_ptr(), _ptr(d_attn), attn.data_ptr(), sc.data_ptr(), influ.data_ptr(), idx.data_ptr(),
+        v.data_ptr(), v.stride(0), sh.R, sh.K, sh.C, int(sh.score_relu), int(sh.normalize), dv.data_ptr(),
+        d_score.data_ptr(), g_influ.data_ptr(), g_bv.data_ptr(), ops._stream()), "papr_blend_bwd")
+    return dv, d_score, g_influ, g_bv
+
+
+def _key_score_bwd(sh, d_score, h5, h5_32, stats, ua, tap=False):
+    dev = ua.device
+    dh5 = ops.Blocked(sh.M, 256, dev)
+    dh5_32 = torch.empty((sh.M, 256), device=dev) if tap else None
+    zsum = torch.empty((sh.R, 256), device=dev)
+    dssum = torch.empty((sh.R,), device=dev)
+    g_b5 = torch.zeros((256,), device=dev)
+    check(lib().papr_key_score_bwd(
+        d_score.data_ptr(), _ptr(h5), _ptr(h5_32), stats.data_ptr(), ua.data_ptr(), sh.R, sh.K, sh.eps,
+        dh5.data_ptr(), _ptr(dh5_32), zsum.data_ptr(), dssum.data_ptr(), g_b5.data_ptr(), ops._stream()),
+        "papr_key_score_bwd")
+    return dh5, dh5_32, zsum, dssum, g_b5
+
+
+def _pad_bias(b, N):
+    b = b.detach().float().contiguous()
+    return b if b.numel() == N else F.pad(b, (0, N - b.numel()))
+
+
+def _stack_forward(x, weights, biases, slope, n_in0, save, last_f32=False):
+    """Run one MLP stack on the tensor cores.  Returns (layer inputs, sign bits, last output: Blocked or fp32)."""
+    inputs, bits_list = [], []
+    h = x
+    n_layers = len(weights)
+    out = None
+    for i, (w, b) in enumerate(zip(weights, biases)):
+        n_out, n_in = w.shape
+        K = (n_in + 15) // 16 * 16
+        N = (n_out + 31) // 32 * 32
+        last = i == n_layers - 1
+        img = ops.pack_weight(w, N, K)
+        inputs.append(h)
+        f32 = last and last_f32
+        yb, yf, bits = ops.linear_bf16(h, img, N, K, bias=_pad_bias(b, N), act=(not last) and slope is not None,
+                                       slope=slope or 0.0, out_blocked=not f32, out_f32=f32,
+                                       sign_bits_out=save and not last and slope is not None)
+        bits_list.append(bits)
+        h = yb
+        out = yf if f32 else yb
+    return inputs, bits_list, out
+
+
+def _stack_backward(dz, inputs, bits_list, weights, slope, g_bias_last, in_valid, in_pad):
+    """Backward of _stack_forward.  dz: Blocked gradient of the last layer's output.  Returns (d_input Blocked,
+    [gW], [gb])."""
+    n_layers = len(weights)
+    gWs, gbs = [None] * n_layers, [None] * n_layers
+    gbs[-1] = g_bias_last
+    for i in range(n_layers - 1, -1, -1):
+        w = weights[i]
+        n_out, n_in = w.shape
+        gW = torch.zeros_like(w, dtype=torch.float32)
+        x = inputs[i]
+        if n_out < 128:     # narrow output (value head): swap operands so that M = n_in
+            ops.wgrad_bf16(x, dz, gW, n_in, n_out, transpose_out=True)
+        else:
+            ops.wgrad_bf16(dz, x, gW, n_out, n_in)
+        gWs[i] = gW
+        Kd = (n_out + 15) // 16 * 16
+        if i > 0:
+            Nd = n_in
+            img_t = ops.pack_weight(w, Nd, Kd, transpose=True)
+            gb_prev = torch.zeros((weights[i - 1].shape[0],), device=w.device)
+            dz, _, _ = ops.linear_bf16(dz, img_t, Nd, Kd, sign_bits_in=bits_list[i - 1] if slope is not None else None,
+                                       slope=slope or 0.0, colsum=gb_prev)
+            gbs[i - 1] = gb_prev
+        else:
+            img_t = ops.pack_weight(w, in_pad, Kd, transpose=True)
+            dz, _, _ = ops.linear_bf16(dz, img_t, in_pad, Kd)
+    return dz, gWs, gbs
+
+
+class RowAttentionFn(torch.autograd.Function):
+    """(points, pc_feats, influ, ua, c', key-in LayerNorm, key/value stack weights) -> (fused, attn)."""
+
+    @staticmethod
+    def forward(ctx, sh, rays_o, rays_d, idx, points, feats, influ, ua, cprime, ln_a, ln_b, nk, *wb):
+        kw, kb = wb[:nk], wb[nk:2 * nk]
+        nv = (len(wb) - 2 * nk) // 2
+        vw, vb = wb[2 * nk:2 * nk + nv], wb[2 * nk + nv:]
+        save = any(ctx.needs_input_grad)
+        pts = points.detach().contiguous()
+        fts = feats.detach().contiguous() if feats is not None else None
+        kin, vin, _, _ = _prologue_fwd(sh, rays_o, rays_d, pts, fts, idx, ln_a.detach(), ln_b.detach())
+        k_in, k_bits, h5 = _stack_forward(kin, [w.detach() for w in kw], kb, sh.k_slope, sh.dk, save)
+        v_in, v_bits, v = _stack_forward(vin, [w.detach() for w in vw], vb, sh.v_slope, sh.dv, save, last_f32=True)
+        infl = influ.detach().reshape(-1).contiguous()
+        fused, attn, sc, stats = _score_blend_fwd(sh, h5, None, ua.detach().contiguous(), cprime.detach().contiguous(),
+                                                  infl, idx, v)
+        if save:
+            ctx.sh, ctx.nk, ctx.nv = sh, nk, nv
+            ctx.blocked = (k_in, k_bits, h5, v_in, v_bits)
+            ctx.save_for_backward(rays_o, rays_d, idx, pts, infl, ua.detach(), ln_a.detach(), v, attn, sc, stats, *wb)
+        return fused, attn
+
+    @staticmethod
+    def backward(ctx, d_fused, d_attn):
+        sh, nk, nv = ctx.sh, ctx.nk, ctx.nv
+        rays_o, rays_d, idx, pts, infl, ua, ln_a, v, attn, sc, stats = ctx.saved_tensors[:11]
+        wb = ctx.saved_tensors[11:]
+        kw, vw = wb[:nk], wb[2 * nk:2 * nk + nv]
+        k_in, k_bits, h5, v_in, v_bits = ctx.blocked
+        P = pts.shape[0]
+        d_attn_c = d_attn.contiguous() if d_attn is not None else None
+        dv, d_score, g_influ, g_bv = _blend_bwd(sh, d_fused.contiguous(), d_attn_c, attn, sc, infl, idx, v, P)
+        d_vin, gvW, gvb = _stack_backward(dv, v_in, v_bits, vw, sh.v_slope, g_bv, sh.dv, sh.dv_pad)
+        dh5, _, zsum, dssum, g_b5 = _key_score_bwd(sh, d_score, h5, None, stats, ua)
+        d_kin, gkW, gkb = _stack_backward(dh5, k_in, k_bits, kw, sh.k_slope, g_b5, sh.dk, sh.dk_pad)
+        g_points, g_feats, g_a, g_b = _prologue_bwd(sh, rays_o, rays_d, pts, idx, ln_a, d_kin, d_vin, None, None, P)
+        ctx.blocked = None
+        return (None, None, None, None, g_points, g_feats, g_influ.reshape(-1, 1), zsum, dssum, g_a, g_b, None,
+                *gkW, *gkb, *gvW, *gvb)
+
+
+class _PrologueFp32Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, sh, rays_o, rays_d, idx, points, feats, ln_a, ln_b):
+        pts = points.detach().contiguous()
+        _, _, kin32, vin32 = _prologue_fwd(sh, rays_o, rays_d, pts, feats.detach().contiguous(), idx, ln_a.detach(),
+                                           ln_b.detach(), taps=True)
+        ctx.sh = sh
+        ctx.save_for_backward(rays_o, rays_d, idx, pts, ln_a.detach())
+        return kin32, vin32
+
+    @staticmethod
+    def backward(ctx, dkin, dvin):
+        rays_o, rays_d, idx, pts, ln_a = ctx.saved_tensors
+        g_points, g_feats, g_a, g_b = _prologue_bwd(ctx.sh, rays_o, rays_d, pts, idx, ln_a, None, None,
+                                                    dkin.contiguous(), dvin.contiguous(), pts.shape[0])
+        return None, None, None, None, g_points, g_feats, g_a, g_b
+
+
+class _ScoreBlendFp32Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, sh, idx, h5, v, ua, cprime, influ):
+        infl = influ.detach().reshape(-1).contiguous()
+        h5c, vc, uac = h5.detach().contiguous(), v.detach().contiguous(), ua.detach().contiguous()
+        fused, attn, sc, stats = _score_blend_fwd(sh, None, h5c, uac, cprime.detach().contiguous(), infl, idx, vc)
+        ctx.sh, ctx.P = sh, infl.shape[0]
+        ctx.save_for_backward(idx, h5c, vc, uac, infl, attn, sc, stats)
+        return fused, attn
+
+    @staticmethod
+    def backward(ctx, d_fused, d_attn):
+        sh = ctx.sh
+        idx, h5, v, ua, infl, attn, sc, stats = ctx.saved_tensors
+        _, d_score, g_influ, _ = _blend_bwd(sh, d_fused.contiguous(), d_attn.contiguous(), attn, sc, infl, idx, v, ctx.P)
+        _, dh5, zsum, dssum, _ = _key_score_bwd(sh, d_score, None, h5, stats, ua, tap=True)
+        w = attn[:, :sh.K]
+        if sh.normalize:
+            w = w / w.sum(-1, keepdim=True)
+        d_v = (w.unsqueeze(-1) * d_fused.unsqueeze(1)).reshape(sh.M, sh.C)
+        return None, None, dh5, d_v, zsum, dssum, g_influ.reshape(-1, 1)
+
+
+class ProximityAttention(nn.Module):
+    """Owns the reference's attention parameters (same state_dict keys) and runs the B200 path."""
+
+    def __init__(self, args, point_feat_dim, eps=1e-6, bkg_score=5.0, normalize=True, precision="bf16"):
+        super().__init__()
+        A, E = args, args.embed
+        if A.k_type != 1 or A.q_type != 1 or A.v_type != 1:
+            raise ValueError("Invalid key/query/value type")
+        if E.embed_type != 1:
+            raise NotImplementedError("embed_type 2 (PE without the input itself) is not used by any shipped config")
+        Ls = set(E.k_L) | set(E.q_L) | set(E.v_L)
+        if len(Ls) != 1:
+            raise NotImplementedError("the B200 path needs one positional-encoding order for all features")
+        self.L = int(next(iter(Ls)))
+        self.F = int(point_feat_dim)
+        S = 1 + 2 * self.L
+        self.dk, self.dq, self.dv = 9 * S, 3 * S, 6 * S + self.F
+        self.C = E.value.d_ff_out
+        self.eps = eps
+        self.bkg_score, self.normalize = float(bkg_score), bool(normalize)
+        self.pe_factor, self.pe_mult = E.pe_factor, E.pe_mult_factor
+        if E.pe_factor != 2.0 or E.pe_mult_factor != 1.0:
+            raise NotImplementedError("pe_factor/pe_mult_factor other than 2/1 are not used by any shipped config")
+        if E.key.d_ff_out != 256 or A.d_model != 256 or E.query.d_ff_out != 256:
+            raise NotImplementedError("the B200 score kernel is specialised to d_model = key/query width = 256")
+        if E.key.norm != "layernorm" or E.query.norm != "layernorm" or E.value.norm != "none":
+            raise NotImplementedError("only key/query layernorm + value none (the shipped setting) is supported")
+        self.k_slope = activation_slope(E.key.ff_act)
+        self.v_slope = activation_slope(E.value.ff_act)
+        self.q_slope = activation_slope(E.query.ff_act)
+        if A.score_act not in ("relu", "none"):
+            raise NotImplementedError("score_act must be relu or none")
+        self.score_relu = A.score_act == "relu"
+        self.d_model = A.d_model
+        self.precision = precision
+        self.embed = Embeddings(self.dk, self.dq, self.dv, E, eps)
+        self.attention_layer = AttentionLayer(E, A.d_model, A.score_act)
+
+    # ------------------------------------------------------------------ per-ray query side (5% of the work)
+    def query_terms(self, rays_d_flat, precision):
+        """(R,3) -> ua (R,256), c' (R): the query stack, w_q and the fold of w_k / key outnorm (see module doc)."""
+        q = posenc(rays_d_flat, self.L)
+        fq = self.embed.embed_q
+        q = fq.innorm(q)
+        lins = fq.mlp.linears()
+        for i, lin in enumerate(lins):
+            q = _linear(q, lin, self.q_slope if i < len(lins) - 1 else None, precision)
+        q = fq.outnorm(q)
+        al = self.attention_layer
+        qp = _linear(q, al.w_q, None, precision)                               # q' (R,256)
+        scale = 1.0 / math.sqrt(self.d_model)
+        if precision == "fp32":
+            u = (qp @ al.w_k.weight) * scale
+        else:
+            u = _LinearBf16Fn.apply(qp, al.w_k.weight.t(), torch.zeros_like(al.w_k.bias), None) * scale
+        on = self.embed.embed_k.outnorm
+        ua = u * on.a_2
+        cprime = (u * on.b_2).sum(-1) + (qp @ al.w_k.bias) * scale
+        return ua, cprime
+
+    def forward(self, rays_o, rays_d, idx, points, feats, influ, precision=None):
+        """rays_o (N,3), rays_d (N,H,W,3), idx int32 (N,H,W,K) -> fused (R,C), attn (R,K+1); differentiable."""
+        precision = precision or self.precision
+        N, H, W, _ = rays_d.shape
+        K = idx.shape[-1]
+        if K > 31:
+            raise NotImplementedError("the blend kernel holds the K candidates + background in one warp: K <= 31")
+        sh = _Shape(self, N * H * W, H * W, K)
+        rays_o = rays_o.detach().float().contiguous()
+        rd = rays_d.detach().float().contiguous().reshape(-1, 3)
+        idx = idx.reshape(-1, K).contiguous()
+        ua, cprime = self.query_terms(rd, precision)
+        fk, fv = self.embed.embed_k, self.embed.embed_v
+        if fv.mlp.skip_layers or fk.mlp.skip_layers:
+            if precision != "fp32":
+                raise NotImplementedError("skip_layers are only supported by the fp32 parity path so far")
+        if precision == "fp32":
+            kin, vin = _PrologueFp32Fn.apply(sh, rays_o, rd, idx, points, feats, fk.innorm.a_2, fk.innorm.b_2)
+            h5 = fk.mlp(kin)
+            v = fv.mlp(vin)
+            return _ScoreBlendFp32Fn.apply(sh, idx, h5, v, ua, cprime, influ)
+        klin, vlin = fk.mlp.linears(), fv.mlp.linears()
+        wb = [l.weight for l in klin] + [l.bias for l in klin] + [l.weight for l in vlin] + [l.bias for l in vlin]
+        return RowAttentionFn.apply(sh, rays_o, rd, idx, points, feats, influ, ua, cprime, fk.innorm.a_2, fk.innorm.b_2,
+                                    len(klin), *wb)

@@ -1,0 +1,625 @@
+// Per-ray CUDA-core stages of the proximity-attention path (everything that is not a dense contraction):
+//   attn_prologue_fwd / _bwd : gather + ray/point geometry + positional encoding + key input LayerNorm
+//                              (reference models/model.py:285-310,396-437; models/utils.py:232-257; attn.py:30-42,172-191)
+//   score_blend_fwd          : key output LayerNorm folded with w_k and the query (scaled dot), ReLU, influence scores,
+//                              background token, softmax, top-K renormalisation, value aggregation
+//                              (attn.py:30-42,217-226; model.py:519-534)
+//   blend_bwd, key_score_bwd : their backward passes (autograd of the same lines)
+// One warp owns one ray (its K candidate rows); lanes sweep columns, so tile-blocked rows are read and written as
+// whole 16-byte chunks and LayerNorm reductions are warp shuffles.  All math is fp32; bf16 only at the tensor-core
+// operand boundary.  Row index = ray * K + k everywhere.
+#include "tc_common.cuh"
+
+namespace papr {
+
+constexpr int kRowThreads = 256;
+constexpr int kRowWarps = kRowThreads / 32;
+constexpr int kMaxDk = 128;    // 9*(1+2L) <= 117 for L <= 6
+constexpr int kMaxDv = 256;
+
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+struct Geometry { float g[9]; };   // selected point (3), along-ray vector proj (3), perpendicular vector D (3)
+
+// model.py:302-305 for one (ray, point): rays = d/(|d|+eps); t = (v.rays)/(rays.rays+eps); proj = rays*t; D = v-proj
+__device__ __forceinline__ Geometry ray_point_geometry(const float *p, const float *o, const float *d, float eps,
+                                                       float *u_out, float *den_out)
+{
+    const float nrm = sqrtf(fmaf(d[2], d[2], fmaf(d[1], d[1], d[0] * d[0]))) + eps;
+    const float ux = d[0] / nrm, uy = d[1] / nrm, uz = d[2] / nrm;
+    const float vx = p[0] - o[0], vy = p[1] - o[1], vz = p[2] - o[2];
+    const float den = (ux * ux + uy * uy) + uz * uz + eps;
+    const float t = ((vx * ux + vy * uy) + vz * uz) / den;
+    Geometry r;
+    r.g[0] = p[0]; r.g[1] = p[1]; r.g[2] = p[2];
+    r.g[3] = ux * t; r.g[4] = uy * t; r.g[5] = uz * t;
+    r.g[6] = vx - r.g[3]; r.g[7] = vy - r.g[4]; r.g[8] = vz - r.g[5];
+    u_out[0] = ux; u_out[1] = uy; u_out[2] = uz; *den_out = den;
+    return r;
+}
+
+// Column j of the key embedding input -> which geometry scalar, which PE slot (utils.py:232-242: per coordinate
+// [x, sin(2^0 x), cos(2^0 x), ..., sin(2^(L-1) x), cos(2^(L-1) x)])
+struct PeCol { int src; int slot; };
+__device__ __forceinline__ PeCol pe_col(int j, int S) { PeCol c; c.src = j / S; c.slot = j - c.src * S; return c; }
+
+__device__ __forceinline__ float pe_value(float x, int slot)
+{
+    if (slot == 0) return x;
+    const float a = ldexpf(x, (slot - 1) >> 1);
+    float s, c;
+    sincosf(a, &s, &c);
+    return (slot & 1) ? s : c;
+}
+// d pe_value / dx
+__device__ __forceinline__ float pe_deriv(float x, int slot)
+{
+    if (slot == 0) return 1.f;
+    const int oct = (slot - 1) >> 1;
+    const float a = ldexpf(x, oct);
+    float s, c;
+    sincosf(a, &s, &c);
+    return ldexpf((slot & 1) ? c : -s, oct);
+}
+
+struct PrologueParams {
+    const float *rays_o, *rays_d, *points, *feats, *a2, *b2;
+    const int32_t *idx;
+    int64_t R, rays_per_view;
+    int K, L, F, dk, dv, nblk_k, nblk_v;
+    float eps;
+    // forward outputs
+    uint8_t *kin, *vin;
+    float *kin_f32, *vin_f32;         // optional fp32 taps (row-major [M,dk], [M,dv])
+    // backward inputs / outputs
+    const uint8_t *dkin, *dvin;
+    const float *dkin_f32, *dvin_f32; // optional fp32 taps
+    float *g_points, *g_feats, *g_a2, *g_b2;
+};
+
+__global__ void __launch_bounds__(kRowThreads) attn_prologue_fwd_kernel(const PrologueParams p)
+{
+    __shared__ float pe_s[kRowWarps][kMaxDk];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int S = 1 + 2 * p.L;
+    const int64_t M = p.R * p.K;
+    float *pe = pe_s[warp];
+
+    PeCol cols[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) cols[m] = pe_col(min(lane + 32 * m, p.dk - 1), S);
+
+    for (int64_t ray = (int64_t)blockIdx.x * kRowWarps + warp; ray < p.R; ray += (int64_t)gridDim.x * kRowWarps) {
+        const int64_t view = ray / p.rays_per_view;
+        Geometry geo;
+        int pidx = 0;
+        {
+            float u[3], den;
+            const int k = min(lane, p.K - 1);
+            pidx = p.idx[ray * p.K + k];
+            geo = ray_point_geometry(p.points + (size_t)pidx * 3, p.rays_o + view * 3, p.rays_d + ray * 3, p.eps, u, &den);
+        }
+        for (int k = 0; k < p.K; ++k) {
+            const int64_t row = ray * p.K + k;
+            float g[9];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) g[i] = __shfl_sync(0xffffffffu, geo.g[i], k);
+            const int pk = __shfl_sync(0xffffffffu, pidx, k);
+            float val[4], sum = 0.f;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const int j = lane + 32 * m;
+                float x = g[0];
+#pragma unroll
+                for (int i = 1; i < 9; ++i) x = (cols[m].src == i) ? g[i] : x;
+                val[m] = (j < p.dk) ? pe_value(x, cols[m].slot) : 0.f;
+                sum += val[m];
+            }
+            const float mean = warp_sum(sum) / (float)p.dk;
+            float sq = 0.f;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const int j = lane + 32 * m;
+                if (j < p.dk) { const float c = val[m] - mean; sq += c * c; pe[j] = val[m]; }
+            }
+            const float stdv = sqrtf(warp_sum(sq) / (float)(p.dk - 1));
+            const float rstd = 1.f / (stdv + p.eps);
+            __syncwarp();
+            // key input: LayerNorm(pe) (attn.py:39-42), zero padded to nblk_k*64 columns
+            for (int c = lane; c < p.nblk_k * 8; c += 32) {
+                float f[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int j = c * 8 + e;
+                    f[e] = (j < p.dk) ? __ldg(p.a2 + j) * (pe[j] - mean) * rstd + __ldg(p.b2 + j) : 0.f;
+                    if (p.kin_f32 && j < p.dk) p.kin_f32[row * p.dk + j] = f[e];
+                }
+                *reinterpret_cast<uint4 *>(p.kin + blocked_chunk_offset(row, c, p.nblk_k)) =
+                    make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+            }
+            // value input: [PE(proj), PE(D), point features] (attn.py:175,187,191)
+            const int dpe = 6 * S;
+            for (int c = lane; c < p.nblk_v * 8; c += 32) {
+                float f[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int j = c * 8 + e;
+                    float t = 0.f;
+                    if (j < dpe) t = pe[j + 3 * S];
+                    else if (j < p.dv) t = __ldg(p.feats + (size_t)pk * p.F + (j - dpe));
+                    f[e] = t;
+                    if (p.vin_f32 && j < p.dv) p.vin_f32[row * p.dv + j] = t;
+                }
+                *reinterpret_cast<uint4 *>(p.vin + blocked_chunk_offset(row, c, p.nblk_v)) =
+                    make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+            }
+            __syncwarp();
+        }
+    }
+    // zero the padding rows [M, pad128(M)) so downstream GEMMs and column sums see zeros
+    const int64_t M_pad = (M + 127) / 128 * 128;
+    const int per_row = (p.nblk_k + p.nblk_v) * 8;
+    for (int64_t i = (int64_t)blockIdx.x * kRowThreads + threadIdx.x; i < (M_pad - M) * per_row; i += (int64_t)gridDim.x * kRowThreads) {
+        const int64_t row = M + i / per_row;
+        const int c = (int)(i % per_row);
+        if (c < p.nblk_k * 8) *reinterpret_cast<uint4 *>(p.kin + blocked_chunk_offset(row, c, p.nblk_k)) = make_uint4(0, 0, 0, 0);
+        else *reinterpret_cast<uint4 *>(p.vin + blocked_chunk_offset(row, c - p.nblk_k * 8, p.nblk_v)) = make_uint4(0, 0, 0, 0);
+    }
+}
+
+__device__ __forceinline__ void unpack8(const uint4 q, float *f)
+{
+    f[0] = bf16_lo(q.x); f[1] = bf16_hi(q.x); f[2] = bf16_lo(q.y); f[3] = bf16_hi(q.y);
+    f[4] = bf16_lo(q.z); f[5] = bf16_hi(q.z); f[6] = bf16_lo(q.w); f[7] = bf16_hi(q.w);
+}
+
+__global__ void __launch_bounds__(kRowThreads) attn_prologue_bwd_kernel(const PrologueParams p)
+{
+    __shared__ float pe_s[kRowWarps][kMaxDk];      // pe values, then per-column contributions to d(geometry)
+    __shared__ float gk_s[kRowWarps][kMaxDk];      // d kin
+    __shared__ float gv_s[kRowWarps][kMaxDv];      // d vin
+    __shared__ float dx_s[kRowWarps][32][6];       // per candidate: d proj (3), d D (3)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int S = 1 + 2 * p.L;
+    float *pe = pe_s[warp], *gk = gk_s[warp], *gv = gv_s[warp];
+
+    PeCol cols[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) cols[m] = pe_col(min(lane + 32 * m, p.dk - 1), S);
+    float acc_a2[4] = {0, 0, 0, 0}, acc_b2[4] = {0, 0, 0, 0};
+
+    for (int64_t ray = (int64_t)blockIdx.x * kRowWarps + warp; ray < p.R; ray += (int64_t)gridDim.x * kRowWarps) {
+        const int64_t view = ray / p.rays_per_view;
+        Geometry geo;
+        float u[3], den;
+        int pidx;
+        {
+            const int k = min(lane, p.K - 1);
+            pidx = p.idx[ray * p.K + k];
+            geo = ray_point_geometry(p.points + (size_t)pidx * 3, p.rays_o + view * 3, p.rays_d + ray * 3, p.eps, u, &den);
+        }
+        for (int k = 0; k < p.K; ++k) {
+            const int64_t row = ray * p.K + k;
+            float g[9];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) g[i] = __shfl_sync(0xffffffffu, geo.g[i], k);
+            const int pk = __shfl_sync(0xffffffffu, pidx, k);
+            // stage the incoming gradients column-wise
+            for (int c = lane; c < p.nblk_k * 8; c += 32) {
+                float f[8];
+                if (p.dkin_f32) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) f[e] = (c * 8 + e < p.dk) ? p.dkin_f32[row * p.dk + c * 8 + e] : 0.f;
+                } else unpack8(*reinterpret_cast<const uint4 *>(p.dkin + blocked_chunk_offset(row, c, p.nblk_k)), f);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) if (c * 8 + e < kMaxDk) gk[c * 8 + e] = f[e];
+            }
+            for (int c = lane; c < p.nblk_v * 8; c += 32) {
+                float f[8];
+                if (p.dvin_f32) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) f[e] = (c * 8 + e < p.dv) ? p.dvin_f32[row * p.dv + c * 8 + e] : 0.f;
+                } else unpack8(*reinterpret_cast<const uint4 *>(p.dvin + blocked_chunk_offset(row, c, p.nblk_v)), f);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) gv[c * 8 + e] = f[e];
+            }
+            // recompute pe + LayerNorm statistics
+            float val[4], x4[4], sum = 0.f;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const int j = lane + 32 * m;
+                float x = g[0];
+#pragma unroll
+                for (int i = 1; i < 9; ++i) x = (cols[m].src == i) ? g[i] : x;
+                x4[m] = x;
+                val[m] = (j < p.dk) ? pe_value(x, cols[m].slot) : 0.f;
+                sum += val[m];
+            }
+            const float mean = warp_sum(sum) / (float)p.dk;
+            float sq = 0.f;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) { const float c = val[m] - mean; if (lane + 32 * m < p.dk) sq += c * c; }
+            const float stdv = sqrtf(warp_sum(sq) / (float)(p.dk - 1));
+            const float rstd = 1.f / (stdv + p.eps);
+            __syncwarp();
+            // LayerNorm backward: z = (pe-mean)*rstd, kin = a2*z+b2
+            float z[4], gz[4], s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const int j = lane + 32 * m;
+                z[m] = 0.f; gz[m] = 0.f;
+                if (j < p.dk) {
+                    z[m] = (val[m] - mean) * rstd;
+                    const float go = gk[j];
+                    acc_a2[m] += go * z[m]; acc_b2[m] += go;
+                    gz[m] = go * __ldg(p.a2 + j);
+                    s1 += gz[m]; s2 += gz[m] * z[m];
+                }
+            }
+            s1 = warp_sum(s1) / (float)p.dk;
+            s2 = warp_sum(s2) / ((float)(p.dk - 1) * stdv);
+            // per-column contribution to d(geometry scalar): (dLN + d vin) * dPE/dx; the raw-position key features
+            // are detached in the reference (model.py:405), so columns of source < 3 contribute nothing
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const int j = lane + 32 * m;
+                if (j < p.dk) {
+                    float d = rstd * (gz[m] - s1) - z[m] * s2;
+                    float contrib = 0.f;
+                    if (cols[m].src >= 3) {
+                        d += gv[j - 3 * S];
+                        contrib = d * pe_deriv(x4[m], cols[m].slot);
+                    }
+                    pe[j] = contrib;
+                }
+            }
+            __syncwarp();
+            if (lane < 6) {
+                float t = 0.f;
+                for (int s = 0; s < S; ++s) t += pe[(3 + lane) * S + s];
+                dx_s[warp][k][lane] = t;
+            }
+            // point-feature gradient (model.py:434-435 gather backward)
+            for (int c = lane; c < p.F; c += 32) atomicAdd(p.g_feats + (size_t)pk * p.F + c, gv[6 * S + c]);
+            __syncwarp();
+        }
+        if (lane < p.K) {
+            const float *dx = dx_s[warp][lane];
+            const float e0 = dx[0] - dx[3], e1 = dx[1] - dx[4], e2 = dx[2] - dx[5];
+            const float s = (e0 * u[0] + e1 * u[1] + e2 * u[2]) / den;
+            atomicAdd(p.g_points + (size_t)pidx * 3 + 0, dx[3] + u[0] * s);
+            atomicAdd(p.g_points + (size_t)pidx * 3 + 1, dx[4] + u[1] * s);
+            atomicAdd(p.g_points + (size_t)pidx * 3 + 2, dx[5] + u[2] * s);
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        const int j = lane + 32 * m;
+        if (j < p.dk) { atomicAdd(p.g_a2 + j, acc_a2[m]); atomicAdd(p.g_b2 + j, acc_b2[m]); }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ score + blend
+struct ScoreParams {
+    const uint8_t *h5;      // blocked bf16 [M_pad, 256] key stack output (before its LayerNorm)
+    const float *h5_f32;    // optional fp32 tap [M,256] used instead of h5
+    const float *ua;        // [R,256]  (W_k^T q' / sqrt(d)) * a2
+    const float *cprime;    // [R]
+    const float *influ;     // [P]
+    const int32_t *idx;     // [R,K]
+    const float *v;         // fp32 [M_pad, ldv]
+    int64_t R;
+    int K, C, ldv, score_relu, normalize;
+    float bkg_score, eps;
+    float *fused, *attn, *sc, *stats;       // [R,C], [R,K+1], [M], [M,2]
+    // backward
+    const float *d_fused, *d_attn;          // [R,C], [R,K+1] or null
+    uint8_t *dv;                            // blocked bf16 [M_pad, 64*ceil(C/64)]
+    float *d_score, *g_influ, *g_bv;        // [M], [P], [C]
+    const float *d_score_in;                // key_score_bwd input
+    uint8_t *dh5;                           // blocked bf16 [M_pad,256]
+    float *dh5_f32;                         // optional fp32 tap
+    float *zsum, *dssum, *g_b5;             // [R,256], [R], [256]
+};
+
+__device__ __forceinline__ void load_row8(const ScoreParams &p, int64_t row, int lane, float *h)
+{
+    if (p.h5_f32) {
+        const float4 a = *reinterpret_cast<const float4 *>(p.h5_f32 + row * 256 + lane * 8);
+        const float4 b = *reinterpret_cast<const float4 *>(p.h5_f32 + row * 256 + lane * 8 + 4);
+        h[0] = a.x; h[1] = a.y; h[2] = a.z; h[3] = a.w; h[4] = b.x; h[5] = b.y; h[6] = b.z; h[7] = b.w;
+    } else {
+        unpack8(*reinterpret_cast<const uint4 *>(p.h5 + blocked_chunk_offset(row, lane, 4)), h);
+    }
+}
+
+__global__ void __launch_bounds__(kRowThreads) score_blend_fwd_kernel(const ScoreParams p)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int64_t ray = (int64_t)blockIdx.x * kRowWarps + warp; ray < p.R; ray += (int64_t)gridDim.x * kRowWarps) {
+        float ua[8];
+        {
+            const float4 a = *reinterpret_cast<const float4 *>(p.ua + ray * 256 + lane * 8);
+            const float4 b = *reinterpret_cast<const float4 *>(p.ua + ray * 256 + lane * 8 + 4);
+            ua[0] = a.x; ua[1] = a.y; ua[2] = a.z; ua[3] = a.w; ua[4] = b.x; ua[5] = b.y; ua[6] = b.z; ua[7] = b.w;
+        }
+        const float cp = p.cprime[ray];
+        float my_sc = 0.f;
+        for (int k = 0; k < p.K; ++k) {
+            const int64_t row = ray * p.K + k;
+            float h[8], s = 0.f;
+            load_row8(p, row, lane, h);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) s += h[e];
+            const float mean = warp_sum(s) * (1.f / 256.f);
+            float sq = 0.f, dot = 0.f;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { const float c = h[e] - mean; sq += c * c; dot += c * ua[e]; }
+            sq = warp_sum(sq); dot = warp_sum(dot);
+            const float rstd = 1.f / (sqrtf(sq * (1.f / 255.f)) + p.eps);
+            float raw = dot * rstd + cp;
+            if (p.score_relu) raw = fmaxf(raw, 0.f);
+            if (lane == k) my_sc = raw;
+            if (lane == 0) { p.stats[row * 2] = mean; p.stats[row * 2 + 1] = rstd; }
+        }
+        // model.py:524-533: influence scores, background token, softmax, top-K renormalisation
+        float s = -INFINITY;
+        if (lane < p.K) {
+            p.sc[ray * p.K + lane] = my_sc;
+            s = my_sc * __ldg(p.influ + p.idx[ray * p.K + lane]);
+        } else if (lane == p.K) s = p.bkg_score;
+        const float mx = warp_max(s);
+        const float e = (lane <= p.K) ? expf(s - mx) : 0.f;
+        const float tot = warp_sum(e);
+        const float attn = e / tot;
+        if (lane <= p.K) p.attn[ray * (p.K + 1) + lane] = attn;
+        const float topk = warp_sum(lane < p.K ? attn : 0.f);
+        const float w = p.normalize ? attn / topk : attn;
+        for (int c0 = 0; c0 < p.C; c0 += 32) {
+            const int c = c0 + lane;
+            float acc = 0.f;
+            for (int k = 0; k < p.K; ++k) {
+                const float wk = __shfl_sync(0xffffffffu, w, k);
+                if (c < p.C) acc += wk * p.v[(ray * p.K + k) * p.ldv + c];
+            }
+            if (c < p.C) p.fused[ray * p.C + c] = acc;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kRowThreads) blend_bwd_kernel(const ScoreParams p)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nblk = (p.C + 63) / 64;
+    float acc_bv[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc_bv[e] = 0.f;
+    for (int64_t ray = (int64_t)blockIdx.x * kRowWarps + warp; ray < p.R; ray += (int64_t)gridDim.x * kRowWarps) {
+        const float attn = (lane <= p.K) ? p.attn[ray * (p.K + 1) + lane] : 0.f;
+        const float topk = warp_sum(lane < p.K ? attn : 0.f);
+        const float w = p.normalize ? attn / topk : attn;
+        // d w_k = d_fused . v_k   (lane k)
+        float dw = 0.f;
+        if (lane < p.K) {
+            const float *vr = p.v + (ray * p.K + lane) * p.ldv;
+            const float *df = p.d_fused + ray * p.C;
+            for (int c = 0; c < p.C; ++c) dw += __ldg(df + c) * vr[c];
+        }
+        float da;                                   // d attn
+        if (p.normalize) {
+            const float mix = warp_sum(lane < p.K ? dw * w : 0.f);
+            da = (lane < p.K) ? (dw - mix) / topk : 0.f;
+        } else da = (lane < p.K) ? dw : 0.f;
+        if (p.d_attn && lane <= p.K) da += p.d_attn[ray * (p.K + 1) + lane];
+        const float inner = warp_sum(lane <= p.K ? attn * da : 0.f);
+        const float ds = (lane <= p.K) ? attn * (da - inner) : 0.f;       // softmax backward
+        if (lane < p.K) {
+            const float sc = p.sc[ray * p.K + lane];
+            const int pi = p.idx[ray * p.K + lane];
+            const float influ = __ldg(p.influ + pi);
+            atomicAdd(p.g_influ + pi, ds * sc);
+            float dsc = ds * influ;
+            if (p.score_relu && !(sc > 0.f)) dsc = 0.f;
+            p.d_score[ray * p.K + lane] = dsc;
+        }
+        // d v_k = w_k * d_fused  -> tile-blocked bf16 operand of the value stack's backward (C <= 64: one block)
+        {
+            const int c = lane;
+            const bool writer = c < nblk * 8;
+            float df[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) df[e] = (writer && c * 8 + e < p.C) ? __ldg(p.d_fused + ray * p.C + c * 8 + e) : 0.f;
+            for (int k = 0; k < p.K; ++k) {
+                const float wk = __shfl_sync(0xffffffffu, w, k);
+                if (writer) {
+                    float f[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) f[e] = wk * df[e];
+                    const uint4 q = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+                    float r[8];
+                    unpack8(q, r);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) acc_bv[e] += r[e];
+                    *reinterpret_cast<uint4 *>(p.dv + blocked_chunk_offset(ray * p.K + k, c, nblk)) = q;
+                }
+            }
+        }
+    }
+    // bias gradient of the last value layer: column sums of d v (only the first 64 columns are tracked per lane)
+    if (lane < 8) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) if (lane * 8 + e < p.C) atomicAdd(p.g_bv + lane * 8 + e, acc_bv[e]);
+    }
+    const int64_t M = p.R * p.K, M_pad = (M + 127) / 128 * 128;
+    for (int64_t i = (int64_t)blockIdx.x * kRowThreads + threadIdx.x; i < (M_pad - M) * nblk * 8; i += (int64_t)gridDim.x * kRowThreads)
+        *reinterpret_cast<uint4 *>(p.dv + blocked_chunk_offset(M + i / (nblk * 8), (int)(i % (nblk * 8)), nblk)) = make_uint4(0, 0, 0, 0);
+}
+
+__global__ void __launch_bounds__(kRowThreads) key_score_bwd_kernel(const ScoreParams p)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float acc_b5[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc_b5[e] = 0.f;
+    for (int64_t ray = (int64_t)blockIdx.x * kRowWarps + warp; ray < p.R; ray += (int64_t)gridDim.x * kRowWarps) {
+        float ua[8], zs[8];
+        {
+            const float4 a = *reinterpret_cast<const float4 *>(p.ua + ray * 256 + lane * 8);
+            const float4 b = *reinterpret_cast<const float4 *>(p.ua + ray * 256 + lane * 8 + 4);
+            ua[0] = a.x; ua[1] = a.y; ua[2] = a.z; ua[3] = a.w; ua[4] = b.x; ua[5] = b.y; ua[6] = b.z; ua[7] = b.w;
+        }
+        float uas = 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { uas += ua[e]; zs[e] = 0.f; }
+        const float ua_mean = warp_sum(uas) * (1.f / 256.f);
+        float dss = 0.f;
+        for (int k = 0; k < p.K; ++k) {
+            const int64_t row = ray * p.K + k;
+            const float ds = p.d_score_in[row];
+            const float mean = p.stats[row * 2], rstd = p.stats[row * 2 + 1];
+            float h[8], y[8], dot = 0.f;
+            load_row8(p, row, lane, h);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { y[e] = (h[e] - mean) * rstd; dot += y[e] * ua[e]; }
+            dot = warp_sum(dot);
+            const float sigma = 1.f / rstd - p.eps;
+            const float coef = ds * dot / (255.f * sigma);
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                f[e] = rstd * ds * (ua[e] - ua_mean) - y[e] * coef;
+                zs[e] += ds * y[e];
+            }
+            dss += ds;
+            const uint4 q = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+            float r[8];
+            unpack8(q, r);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc_b5[e] += r[e];
+            *reinterpret_cast<uint4 *>(p.dh5 + blocked_chunk_offset(row, lane, 4)) = q;
+            if (p.dh5_f32) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) p.dh5_f32[row * 256 + lane * 8 + e] = f[e];
+            }
+        }
+        *reinterpret_cast<float4 *>(p.zsum + ray * 256 + lane * 8) = make_float4(zs[0], zs[1], zs[2], zs[3]);
+        *reinterpret_cast<float4 *>(p.zsum + ray * 256 + lane * 8 + 4) = make_float4(zs[4], zs[5], zs[6], zs[7]);
+        if (lane == 0) p.dssum[ray] = dss;
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) atomicAdd(p.g_b5 + lane * 8 + e, acc_b5[e]);
+    const int64_t M = p.R * p.K, M_pad = (M + 127) / 128 * 128;
+    for (int64_t i = (int64_t)blockIdx.x * kRowThreads + threadIdx.x; i < (M_pad - M) * 32; i += (int64_t)gridDim.x * kRowThreads)
+        *reinterpret_cast<uint4 *>(p.dh5 + blocked_chunk_offset(M + i / 32, (int)(i % 32), 4)) = make_uint4(0, 0, 0, 0);
+}
+
+static int row_grid(int64_t R)
+{
+    const int64_t blocks = (R + kRowWarps - 1) / kRowWarps;
+    const int64_t cap = (int64_t)kNumSMs * 8;
+    return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+}
+
+}  // namespace papr
+
+using namespace papr;
+
+static int prologue_check(int64_t R, int64_t rays_per_view, int K, int L, int F, int dk_pad, int dv_pad)
+{
+    if (R <= 0 || rays_per_view <= 0 || K < 1 || K > 32 || L < 0 || L > 6 || F < 0) return PAPR_ERR_INVALID_ARGUMENT;
+    const int S = 1 + 2 * L, dk = 9 * S, dv = 6 * S + F;
+    if (dk < 2 || dk > kMaxDk || dv > kMaxDv || dk_pad % 64 || dv_pad % 64 || dk_pad < dk || dv_pad < dv) return PAPR_ERR_INVALID_ARGUMENT;
+    return PAPR_OK;
+}
+
+extern "C" int papr_attn_prologue_fwd(const float *rays_o, const float *rays_d, const float *points, const float *feats,
+                                      const int32_t *idx, const float *ln_a, const float *ln_b, int64_t R,
+                                      int64_t rays_per_view, int K, int L, int F, float eps, void *kin, int dk_pad,
+                                      void *vin, int dv_pad, float *kin_f32, float *vin_f32, void *stream)
+{
+    if (!rays_o || !rays_d || !points || !idx || !ln_a || !ln_b || !kin || !vin || (F > 0 && !feats)) return PAPR_ERR_INVALID_ARGUMENT;
+    int st = prologue_check(R, rays_per_view, K, L, F, dk_pad, dv_pad);
+    if (st) return st;
+    PrologueParams p = {};
+    p.rays_o = rays_o; p.rays_d = rays_d; p.points = points; p.feats = feats; p.a2 = ln_a; p.b2 = ln_b; p.idx = idx;
+    p.R = R; p.rays_per_view = rays_per_view; p.K = K; p.L = L; p.F = F; p.dk = 9 * (1 + 2 * L); p.dv = 6 * (1 + 2 * L) + F;
+    p.nblk_k = dk_pad / 64; p.nblk_v = dv_pad / 64; p.eps = eps;
+    p.kin = (uint8_t *)kin; p.vin = (uint8_t *)vin; p.kin_f32 = kin_f32; p.vin_f32 = vin_f32;
+    attn_prologue_fwd_kernel<<<row_grid(R), kRowThreads, 0, (cudaStream_t)stream>>>(p);
+    return check_launch();
+}
+
+extern "C" int papr_attn_prologue_bwd(const float *rays_o, const float *rays_d, const float *points, const int32_t *idx,
+                                      const float *ln_a, int64_t R, int64_t rays_per_view, int K, int L, int F, float eps,
+                                      const void *dkin, int dk_pad, const void *dvin, int dv_pad, const float *dkin_f32,
+                                      const float *dvin_f32, float *g_points, float *g_feats, float *g_ln_a,
+                                      float *g_ln_b, void *stream)
+{
+    if (!rays_o || !rays_d || !points || !idx || !ln_a || !g_points || !g_ln_a || !g_ln_b || (F > 0 && !g_feats)) return PAPR_ERR_INVALID_ARGUMENT;
+    if ((!dkin && !dkin_f32) || (!dvin && !dvin_f32)) return PAPR_ERR_INVALID_ARGUMENT;
+    int st = prologue_check(R, rays_per_view, K, L, F, dk_pad, dv_pad);
+    if (st) return st;
+    PrologueParams p = {};
+    p.rays_o = rays_o; p.rays_d = rays_d; p.points = points; p.a2 = ln_a; p.idx = idx;
+    p.R = R; p.rays_per_view = rays_per_view; p.K = K; p.L = L; p.F = F; p.dk = 9 * (1 + 2 * L); p.dv = 6 * (1 + 2 * L) + F;
+    p.nblk_k = dk_pad / 64; p.nblk_v = dv_pad / 64; p.eps = eps;
+    p.dkin = (const uint8_t *)dkin; p.dvin = (const uint8_t *)dvin; p.dkin_f32 = dkin_f32; p.dvin_f32 = dvin_f32;
+    p.g_points = g_points; p.g_feats = g_feats; p.g_a2 = g_ln_a; p.g_b2 = g_ln_b;
+    attn_prologue_bwd_kernel<<<row_grid(R), kRowThreads, 0, (cudaStream_t)stream>>>(p);
+    return check_launch();
+}
+
+extern "C" int papr_score_blend_fwd(const void *h5, const float *h5_f32, const float *ua, const float *cprime,
+                                    const float *influ, const int32_t *idx, const float *v, int64_t ldv, int64_t R, int K,
+                                    int C, int score_relu, int normalize, float bkg_score, float eps, float *fused,
+                                    float *attn, float *sc, float *stats, void *stream)
+{
+    if ((!h5 && !h5_f32) || !ua || !cprime || !influ || !idx || !v || !fused || !attn || !sc || !stats) return PAPR_ERR_INVALID_ARGUMENT;
+    if (R <= 0 || K < 1 || K > 31 || C < 1 || ldv < C) return PAPR_ERR_INVALID_ARGUMENT;
+    ScoreParams p = {};
+    p.h5 = (const uint8_t *)h5; p.h5_f32 = h5_f32; p.ua = ua; p.cprime = cprime; p.influ = influ; p.idx = idx; p.v = v;
+    p.R = R; p.K = K; p.C = C; p.ldv = (int)ldv; p.score_relu = score_relu; p.normalize = normalize;
+    p.bkg_score = bkg_score; p.eps = eps; p.fused = fused; p.attn = attn; p.sc = sc; p.stats = stats;
+    score_blend_fwd_kernel<<<row_grid(R), kRowThreads, 0, (cudaStream_t)stream>>>(p);
+    return check_launch();
+}
+
+extern "C" int papr_blend_bwd(const float *d_fused, const float *d_attn, const float *attn, const float *sc,
+                              const float *influ, const int32_t *idx, const float *v, int64_t ldv, int64_t R, int K, int C,
+                              int score_relu, int normalize, void *dv_blocked, float *d_score, float *g_influ,
+                              float *g_bias_v, void *stream)
+{
+    if (!d_fused || !attn || !sc || !influ || !idx || !v || !dv_blocked || !d_score || !g_influ || !g_bias_v) return PAPR_ERR_INVALID_ARGUMENT;
+    if (R <= 0 || K < 1 || K > 31 || C < 1 || C > 64 || ldv < C) return PAPR_ERR_INVALID_ARGUMENT;
+    ScoreParams p = {};
+    p.d_fused = d_fused; p.d_attn = d_attn; p.attn = const_cast<float *>(attn); p.sc = const_cast<float *>(sc); p.influ = influ; p.idx = idx; p.v = v;
+    p.R = R; p.K = K; p.C = C; p.ldv = (int)ldv; p.score_relu = score_relu; p.normalize = normalize;
+    p.dv = (uint8_t *)dv_blocked; p.d_score = d_score; p.g_influ = g_influ; p.g_bv = g_bias_v;
+    blend_bwd_kernel<<<row_grid(R), kRowThreads, 0, (cudaStream_t)stream>>>(p);
+    return check_launch();
+}
+
+extern "C" int papr_key_score_bwd(const float *d_score, const void *h5, const float *h5_f32, const float *stats,
+                                  const float *ua, int64_t R, int K, float eps, void *dh5_blocked, float *dh5_f32,
+                                  float *zsum, float *dssum, float *g_bias5, void *stream)
+{
+    if (!d_score || (!h5 && !h5_f32) || !stats || !ua || !dh5_blocked || !zsum || !dssum || !g_bias5) return PAPR_ERR_INVALID_ARGUMENT;
+    if (R <= 0 || K < 1 || K > 31) return PAPR_ERR_INVALID_ARGUMENT;
+    ScoreParams p = {};
+    p.d_score_in = d_score; p.h5 = (const uint8_t *)h5; p.h5_f32 = h5_f32; p.stats = const_cast<float *>(stats); p.ua = ua; p.R = R; p.K = K;
+    p.eps = eps; p.dh5 = (uint8_t *)dh5_blocked; p.dh5_f32 = dh5_f32; p.zsum = zsum; p.dssum = dssum; p.g_b5 = g_bias5;
+    key_score_bwd_kernel<<<row_grid(R), kRowThreads, 0, (cudaStream_t)stream>>>(p);
+    return check_launch();
+}
