@@ -25,7 +25,6 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ops
-from ._lib import check, lib
 from .nn import AttentionLayer, Embeddings, activation_slope
 
 
@@ -108,10 +107,11 @@ def _prologue_fwd(sh, rays_o, rays_d, points, feats, idx, ln_a, ln_b, taps=False
     vin = ops.Blocked(sh.M, sh.dv, dev)
     kin32 = torch.empty((sh.M, sh.dk), device=dev) if taps else None
     vin32 = torch.empty((sh.M, sh.dv), device=dev) if taps else None
-    check(lib().papr_attn_prologue_fwd(
+    ops.call("papr_attn_prologue_fwd",
         rays_o.data_ptr(), rays_d.data_ptr(), points.data_ptr(), _ptr(feats), idx.data_ptr(), ln_a.data_ptr(),
         ln_b.data_ptr(), sh.R, sh.rays_per_view, sh.K, sh.L, sh.F, sh.eps, kin.data_ptr(), sh.dk_pad, vin.data_ptr(),
-        sh.dv_pad, _ptr(kin32), _ptr(vin32), ops._stream()), "papr_attn_prologue_fwd")
+        sh.dv_pad, _ptr(kin32), _ptr(vin32),
+        nbytes=sh.M * (2.0 * (sh.dk_pad + sh.dv_pad) + 12 + 4.0 * sh.F))
     return kin, vin, kin32, vin32
 
 
@@ -121,11 +121,11 @@ def _prologue_bwd(sh, rays_o, rays_d, points, idx, ln_a, dkin, dvin, dkin32, dvi
     g_feats = torch.zeros((n_points, sh.F), device=dev) if sh.F else None
     g_a = torch.zeros(sh.dk, device=dev)
     g_b = torch.zeros(sh.dk, device=dev)
-    check(lib().papr_attn_prologue_bwd(
+    ops.call("papr_attn_prologue_bwd",
         rays_o.data_ptr(), rays_d.data_ptr(), points.data_ptr(), idx.data_ptr(), ln_a.data_ptr(), sh.R,
         sh.rays_per_view, sh.K, sh.L, sh.F, sh.eps, _ptr(dkin), sh.dk_pad, _ptr(dvin), sh.dv_pad, _ptr(dkin32),
-        _ptr(dvin32), g_points.data_ptr(), _ptr(g_feats), g_a.data_ptr(), g_b.data_ptr(), ops._stream()),
-        "papr_attn_prologue_bwd")
+        _ptr(dvin32), g_points.data_ptr(), _ptr(g_feats), g_a.data_ptr(), g_b.data_ptr(),
+        nbytes=sh.M * (2.0 * (sh.dk_pad + sh.dv_pad) + 24 + 8.0 * sh.F))
     return g_points, g_feats, g_a, g_b
 
 
@@ -135,10 +135,11 @@ def _score_blend_fwd(sh, h5, h5_32, ua, cprime, influ, idx, v):
     attn = torch.empty((sh.R, sh.K + 1), device=dev)
     sc = torch.empty((sh.M,), device=dev)
     stats = torch.empty((sh.M, 2), device=dev)
-    check(lib().papr_score_blend_fwd(
+    ops.call("papr_score_blend_fwd",
         _ptr(h5), _ptr(h5_32), ua.data_ptr(), cprime.data_ptr(), influ.data_ptr(), idx.data_ptr(), v.data_ptr(),
         v.stride(0), sh.R, sh.K, sh.C, int(sh.score_relu), int(sh.normalize), sh.bkg_score, sh.eps, fused.data_ptr(),
-        attn.data_ptr(), sc.data_ptr(), stats.data_ptr(), ops._stream()), "papr_score_blend_fwd")
+        attn.data_ptr(), sc.data_ptr(), stats.data_ptr(),
+        nbytes=sh.M * (512.0 + 4 * sh.C + 16) + sh.R * (1024.0 + 4 * sh.C))
     return fused, attn, sc, stats
 
 
@@ -148,10 +149,11 @@ def _blend_bwd(sh, d_fused, d_attn, attn, sc, influ, idx, v, n_points):
     d_score = torch.empty((sh.M,), device=dev)
     g_influ = torch.zeros((n_points,), device=dev)
     g_bv = torch.zeros((sh.C,), device=dev)
-    check(lib().papr_blend_bwd(
+    ops.call("papr_blend_bwd",
         d_fused.data_ptr(), _ptr(d_attn), attn.data_ptr(), sc.data_ptr(), influ.data_ptr(), idx.data_ptr(),
         v.data_ptr(), v.stride(0), sh.R, sh.K, sh.C, int(sh.score_relu), int(sh.normalize), dv.data_ptr(),
-        d_score.data_ptr(), g_influ.data_ptr(), g_bv.data_ptr(), ops._stream()), "papr_blend_bwd")
+        d_score.data_ptr(), g_influ.data_ptr(), g_bv.data_ptr(),
+        nbytes=sh.M * (4.0 * sh.C + 128 + 16) + sh.R * 8.0 * sh.C)
     return dv, d_score, g_influ, g_bv
 
 
@@ -162,10 +164,10 @@ def _key_score_bwd(sh, d_score, h5, h5_32, stats, ua, tap=False):
     zsum = torch.empty((sh.R, 256), device=dev)
     dssum = torch.empty((sh.R,), device=dev)
     g_b5 = torch.zeros((256,), device=dev)
-    check(lib().papr_key_score_bwd(
+    ops.call("papr_key_score_bwd",
         d_score.data_ptr(), _ptr(h5), _ptr(h5_32), stats.data_ptr(), ua.data_ptr(), sh.R, sh.K, sh.eps,
-        dh5.data_ptr(), _ptr(dh5_32), zsum.data_ptr(), dssum.data_ptr(), g_b5.data_ptr(), ops._stream()),
-        "papr_key_score_bwd")
+        dh5.data_ptr(), _ptr(dh5_32), zsum.data_ptr(), dssum.data_ptr(), g_b5.data_ptr(),
+        nbytes=sh.M * (1024.0 + 12) + sh.R * 2048.0)
     return dh5, dh5_32, zsum, dssum, g_b5
 
 

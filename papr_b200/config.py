@@ -14,14 +14,24 @@ import copy
 class Config(dict):
     """dict with attribute access; nested dicts are wrapped lazily (ref utils.py:14-19)."""
 
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        for k, v in list(self.items()):     # wrap nested dicts once so attribute access returns the live object
+            if isinstance(v, dict) and not isinstance(v, Config):
+                super().__setitem__(k, Config(v))
+            elif isinstance(v, list):
+                super().__setitem__(k, [Config(i) if isinstance(i, dict) and not isinstance(i, Config) else i for i in v])
+
     def __getattr__(self, name):
         try:
-            value = self[name]
+            return self[name]
         except KeyError as e:
             raise AttributeError(name) from e
+
+    def __setitem__(self, key, value):
         if isinstance(value, dict) and not isinstance(value, Config):
             value = Config(value)
-        return value
+        super().__setitem__(key, value)
 
     def __setattr__(self, name, value):
         self[name] = value

@@ -8,6 +8,49 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+class LaunchStats:
+    """Counts the library's kernel launches; with timing on, brackets each launch with CUDA events on the launching
+    stream and records its algorithmic work (flops, bytes) so bench.py can report per-kernel roofline numbers."""
+
+    def __init__(self):
+        self.count = 0
+        self.timing = False
+        self.records = []      # (name, start_event, end_event, flops, bytes)
+
+    def reset(self):
+        self.count = 0
+        self.records = []
+
+    def summary(self):
+        """name -> dict(launches, ms, flops, bytes); call after torch.cuda.synchronize()."""
+        out = {}
+        for name, e0, e1, fl, by in self.records:
+            d = out.setdefault(name, dict(launches=0, ms=0.0, flops=0.0, bytes=0.0))
+            d["launches"] += 1
+            d["ms"] += e0.elapsed_time(e1)
+            d["flops"] += fl
+            d["bytes"] += by
+        return out
+
+
+STATS = LaunchStats()
+
+
+def call(name, *args, flops=0.0, nbytes=0.0):
+    """Invoke one C-ABI entry point on the current stream (the stream pointer is appended)."""
+    fn = getattr(lib(), name)
+    STATS.count += 1
+    if STATS.timing:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        status = fn(*args, _stream())
+        e1.record()
+        STATS.records.append((name, e0, e1, flops, nbytes))
+    else:
+        status = fn(*args, _stream())
+    check(status, name)
+
+
 def _f32c(t):
     assert t.is_cuda, "papr_b200 ops need CUDA tensors (there is no CPU path)"
     return t.detach().contiguous().float()
@@ -22,8 +65,9 @@ def select_topk(rays_o, rays_d, points, K, eps=1e-6):
         raise ValueError(f"select_topk needs 1 <= K <= 32 and K < P (K={K}, P={P})")
     ro, rd, pts = _f32c(rays_o), _f32c(rays_d), _f32c(points)
     idx = torch.empty((N, H, W, K), dtype=torch.int32, device=rd.device)
-    check(lib().papr_select_topk(ro.data_ptr(), rd.data_ptr(), pts.data_ptr(), N, H * W, P, K, float(eps),
-                                 idx.data_ptr(), _stream()), "papr_select_topk")
+    R = N * H * W
+    call("papr_select_topk", ro.data_ptr(), rd.data_ptr(), pts.data_ptr(), N, H * W, P, K, float(eps), idx.data_ptr(),
+         flops=17.0 * R * P, nbytes=12.0 * R + 12.0 * P + 4.0 * K * R)
     return idx
 
 
@@ -55,16 +99,16 @@ class Blocked:
         if cols_pad:
             out.cols_pad = cols_pad
             out.buf = torch.empty(out.rows_pad * cols_pad * 2, dtype=torch.uint8, device=t.device)
-        check(lib().papr_blocked_from_f32(t.data_ptr(), t.shape[0], t.shape[1], t.stride(0), out.data_ptr(),
-                                          out.rows_pad, out.cols_pad, _stream()), "papr_blocked_from_f32")
+        call("papr_blocked_from_f32", t.data_ptr(), t.shape[0], t.shape[1], t.stride(0), out.data_ptr(), out.rows_pad,
+             out.cols_pad, nbytes=4.0 * t.numel() + 2.0 * out.rows_pad * out.cols_pad)
         return out
 
     def to_f32(self, rows=None, cols=None):
         rows = self.rows if rows is None else rows
         cols = self.cols if cols is None else cols
         out = torch.empty((rows, cols), dtype=torch.float32, device=self.buf.device)
-        check(lib().papr_blocked_to_f32(self.data_ptr(), self.cols_pad, out.data_ptr(), rows, cols, out.stride(0),
-                                        _stream()), "papr_blocked_to_f32")
+        call("papr_blocked_to_f32", self.data_ptr(), self.cols_pad, out.data_ptr(), rows, cols, out.stride(0),
+             nbytes=6.0 * rows * cols)
         return out
 
 
@@ -72,8 +116,8 @@ def pack_weight(w, N, K, transpose=False, scale=1.0):
     """bf16 weight image (uint8 tensor) for linear_bf16 from a torch Linear weight (out,in)."""
     w = _f32c(w)
     img = torch.empty(((K + 63) // 64) * N * 128, dtype=torch.uint8, device=w.device)
-    check(lib().papr_pack_weight(w.data_ptr(), w.stride(0), w.shape[0], w.shape[1], int(transpose), N, K, float(scale),
-                                 img.data_ptr(), _stream()), "papr_pack_weight")
+    call("papr_pack_weight", w.data_ptr(), w.stride(0), w.shape[0], w.shape[1], int(transpose), N, K, float(scale),
+         img.data_ptr(), nbytes=6.0 * N * K)
     return img
 
 
@@ -86,18 +130,21 @@ def linear_bf16(x, w_image, N, K, bias=None, act=False, slope=0.0, out_blocked=T
     yb = Blocked(x.rows, N, dev) if out_blocked else None
     yf = torch.empty((rows_pad, N), dtype=torch.float32, device=dev) if out_f32 else None
     bits = torch.empty((rows_pad, pad_cols(N) // 64), dtype=torch.int64, device=dev) if sign_bits_out else None
-    check(lib().papr_linear_bf16(
-        x.data_ptr(), w_image.data_ptr(), bias.data_ptr() if bias is not None else None,
-        yb.data_ptr() if yb is not None else None, yf.data_ptr() if yf is not None else None, N,
-        bits.data_ptr() if bits is not None else None, sign_bits_in.data_ptr() if sign_bits_in is not None else None,
-        colsum.data_ptr() if colsum is not None else None, rows_pad, N, K, int(act), float(slope), _stream()),
-        "papr_linear_bf16")
+    nbytes = rows_pad * (2.0 * pad_cols(K) + (2.0 * pad_cols(N) if out_blocked else 0) + (4.0 * N if out_f32 else 0)
+                         + (8.0 * pad_cols(N) / 64 if sign_bits_out else 0) + (8.0 * pad_cols(N) / 64 if sign_bits_in is not None else 0))
+    call("papr_linear_bf16",
+         x.data_ptr(), w_image.data_ptr(), bias.data_ptr() if bias is not None else None,
+         yb.data_ptr() if yb is not None else None, yf.data_ptr() if yf is not None else None, N,
+         bits.data_ptr() if bits is not None else None, sign_bits_in.data_ptr() if sign_bits_in is not None else None,
+         colsum.data_ptr() if colsum is not None else None, rows_pad, N, K, int(act), float(slope),
+         flops=2.0 * x.rows * N * K, nbytes=nbytes)
     return yb, yf, bits
 
 
 def wgrad_bf16(a, b, out, a_valid, b_valid, transpose_out=False):
     """out[a,b] += sum_rows A[row,a] B[row,b]  (out fp32, atomically accumulated)."""
     assert a.rows_pad == b.rows_pad
-    check(lib().papr_wgrad_bf16(a.data_ptr(), a.cols_pad, b.data_ptr(), b.cols_pad, out.data_ptr(), out.stride(0),
-                                a_valid, b_valid, int(transpose_out), a.rows_pad, _stream()), "papr_wgrad_bf16")
+    call("papr_wgrad_bf16", a.data_ptr(), a.cols_pad, b.data_ptr(), b.cols_pad, out.data_ptr(), out.stride(0),
+         a_valid, b_valid, int(transpose_out), a.rows_pad, flops=2.0 * a.rows * a_valid * b_valid,
+         nbytes=2.0 * a.rows_pad * (128 * ((a_valid + 127) // 128) + pad_cols(b_valid)))
     return out

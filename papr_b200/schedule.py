@@ -14,18 +14,31 @@ class WarmupDecay:
     def __init__(self, kind, warmup, max_steps, gamma=1.0):
         self.kind, self.warmup, self.max_steps, self.gamma = kind, int(warmup), int(max_steps), gamma
 
+    def _cos(self, u):
+        T = max(self.max_steps - self.warmup, 1) * (2 if self.kind == "cosine-hlfperiod" else 1)
+        return 0.5 * (1.0 + math.cos(math.pi * u / T))
+
     def __call__(self, t):
         w = self.warmup
         if t < w:   # LinearLR(start_factor=1e-16, end_factor=1, total_iters=warmup)
             s = 1e-16
             return s + (1.0 - s) * t / w
         u = t - w
+        if w == 0:
+            # With milestone 0, SequentialLR never calls the decay scheduler's step(0): its __init__ leaves that
+            # scheduler at last_epoch = -1 and every step() then applies the *recursive* update.  For the cosine law
+            # this gives lr_t = base * c(t-1)/c(1) (slightly above base at t = 1); the other laws lag one step.
+            # The shipped configs hit this with lr.points (cosine, warmup 0); reproduced as is.
+            if t == 0:
+                return 1.0
+            if self.kind in ("cosine", "cosine-hlfperiod"):
+                return self._cos(t - 1) / self._cos(1)
+            u = t - 1
         if self.kind == "linear":
             total = self.max_steps - w
             return 1.0 - min(u, total) / total
         if self.kind in ("cosine", "cosine-hlfperiod"):
-            T = max(self.max_steps - w, 1) * (2 if self.kind == "cosine-hlfperiod" else 1)
-            return 0.5 * (1.0 + math.cos(math.pi * u / T))
+            return self._cos(u)
         if self.kind == "exp":
             return self.gamma ** u
         if self.kind == "stop":
