@@ -3,20 +3,21 @@
 //
 //   Y[M,N] = epilogue( X[M,K] * W[N,K]^T )            bf16 x bf16 -> fp32 in TMEM
 //
-// Persistent, warp-specialised, one CTA per SM:
-//   warp 0   TMA producer : the whole weight image once (it stays resident), then X blocks (128 rows x 64 cols,
-//                           16 KB, already in the UMMA shared-memory layout) through a ring of mbarrier stages
-//   warp 1   MMA issuer   : tcgen05.mma cta_group::1 kind::f16, M=128, N=N, K=16 per instruction, accumulating a
-//                           128 x N fp32 tile in TMEM; two accumulators so tile t+1 multiplies while t drains
-//   warp 2   TMEM allocator
-//   warps 4-7 epilogue    : tcgen05.ld -> bias / activation / activation-derivative mask -> bf16 -> swizzled staging
-//                           -> TMA bulk store of the next layer's operand block; optional fp32 row-major output,
-//                           activation sign bits (for backward) and per-column sums (bias gradients)
+// Persistent, warp-specialised, one CTA per SM (384 threads):
+//   warp 0    TMA producer : the whole weight image once (it stays resident), then X blocks (128 rows x 64 cols,
+//                            16 KB, already in the UMMA shared-memory layout) through a ring of mbarrier stages
+//   warp 1    MMA issuer   : tcgen05.mma cta_group::1 kind::f16, M=128, N=N, K=16 per instruction, accumulating a
+//                            128 x N fp32 tile in TMEM; two accumulators so tile t+1 multiplies while t drains
+//   warp 2    TMEM allocator
+//   warps 4-11 epilogue    : two sets of four warps (TMEM lane quadrant = warp % 4); set s drains the 64-column groups
+//                            g with (g & 1) == s: tcgen05.ld -> bias / activation / activation-derivative mask -> bf16
+//                            -> swizzled staging -> TMA bulk store of the next layer's operand block; optional fp32
+//                            row-major output, activation sign bits (for backward), per-column sums (bias gradients)
 #include "tc_common.cuh"
 
 namespace papr {
 
-constexpr int kLinThreads = 256;
+constexpr int kLinThreads = 384;
 constexpr int kMaxSmem = 232448;   // 227 KB
 
 struct LinearParams {
@@ -33,6 +34,25 @@ struct LinearParams {
     float slope;             // negative slope of the activation (0 relu, 0.2 leakyrelu) for act and for bits_in
 };
 
+// Epilogue flavours (compile-time so the per-element code carries no dead predicates)
+enum { EPI_PLAIN = 0, EPI_BIAS = 1, EPI_BIAS_ACT = 2, EPI_BIAS_ACT_BITS = 3, EPI_MASK = 4 };
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_math(uint32_t (&v)[32], const float *bias_s, int col0, float slope, uint32_t din,
+                                              uint32_t &dout)
+{
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        float t = __uint_as_float(v[j]);
+        if (EPI == EPI_BIAS || EPI == EPI_BIAS_ACT || EPI == EPI_BIAS_ACT_BITS) t += bias_s[col0 + j];
+        if (EPI == EPI_BIAS_ACT_BITS) dout |= (t > 0.f ? 1u : 0u) << j;
+        if (EPI == EPI_BIAS_ACT || EPI == EPI_BIAS_ACT_BITS) t = t > 0.f ? t : t * slope;
+        if (EPI == EPI_MASK) t = ((din >> j) & 1u) ? t : t * slope;
+        v[j] = __float_as_uint(t);
+    }
+}
+
+template <int EPI>
 __global__ void __launch_bounds__(kLinThreads, 1) linear_kernel(const LinearParams p)
 {
     extern __shared__ uint8_t smem_raw[];
@@ -40,22 +60,25 @@ __global__ void __launch_bounds__(kLinThreads, 1) linear_kernel(const LinearPara
     const int wbytes = p.kblk * p.N * 128;
     uint8_t *w_s = smem;
     uint8_t *ring = w_s + ((wbytes + 1023) & ~1023);
-    uint8_t *stage_out = ring + p.stages * kBlockBytes;
+    uint8_t *stage_out = ring + p.stages * kBlockBytes;            // one 16 KB staging buffer per epilogue set
     uint64_t *bars = (uint64_t *)(stage_out + 2 * kBlockBytes);
     uint64_t *full = bars, *empty = bars + 8, *tfull = bars + 16, *tempty = bars + 18, *wbar = bars + 20;
     uint32_t *tmem_slot = (uint32_t *)(bars + 21);
-    float *colsum_s = (float *)(bars + 24);   // 256 floats
+    float *colsum_s = (float *)(bars + 24);   // 256 floats: column sums (dgrad) ...
+    float *bias_s = colsum_s;                 // ... or the bias vector (forward); never both (checked by the caller)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 256); }
         mbar_init(wbar, 1);
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, 512);
-    for (int i = threadIdx.x; i < 256; i += kLinThreads) colsum_s[i] = 0.f;
+    for (int i = threadIdx.x; i < 256; i += kLinThreads) {
+        colsum_s[i] = (p.bias && i < p.N) ? p.bias[i] : 0.f;
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -102,100 +125,117 @@ __global__ void __launch_bounds__(kLinThreads, 1) linear_kernel(const LinearPara
         }
     } else if (warp >= 4) {
         const int ew = warp - 4;
-        const int row = ew * 32 + lane;
-        const int et = threadIdx.x - 128;
-        const uint32_t lane_base = (uint32_t)(ew * 32) << 16;
+        const int set = ew >> 2;                        // which 64-column groups this warp drains
+        const int quad = ew & 3;                        // TMEM lane quadrant (== warp % 4)
+        const int row = quad * 32 + lane;
+        const int st = (ew & 3) * 32 + lane;            // thread index within the set (0..127)
+        const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
         const int ngroups = (p.N + 63) >> 6;
+        uint8_t *sbuf = stage_out + set * kBlockBytes;
+        const int bar_id = 1 + set;
         int64_t it = 0;
-        int sb = 0;
         for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
             const int acc = (int)(it & 1);
+            const int64_t grow = tile * kTileRows + row;
+            uint64_t din[2] = {0, 0};
+            if (EPI == EPI_MASK) {
+                if (set < ngroups) din[0] = p.bits_in[grow * p.nblk_out + set];
+                if (set + 2 < ngroups) din[1] = p.bits_in[grow * p.nblk_out + set + 2];
+            }
             mbar_wait(&tfull[acc], (uint32_t)((it >> 1) & 1));
             tc_fence_after();
-            const int64_t grow = tile * kTileRows + row;
-            for (int g = 0; g < ngroups; ++g) {
-                uint8_t *sbuf = stage_out + sb * kBlockBytes;
-                if (p.y_blocked) {
-                    if (et == 0) bulk_wait_read<1>();      // the store that last used this staging buffer has been read
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int gi = 0; gi < 2; ++gi) {
+                const int g = set + 2 * gi;
+                if (g >= ngroups) break;
+                const int col0 = g * 64;
+                uint32_t v0[32], v1[32];
+                const bool second = col0 + 32 < p.N;
+                tmem_ld32(tmem_base + lane_base + acc * 256 + col0, v0);
+                if (second) tmem_ld32(tmem_base + lane_base + acc * 256 + col0 + 32, v1);
+                tmem_ld_wait();
+                if (!second) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v1[j] = 0;
                 }
-                uint64_t din = 0, dout = 0;
-                if (p.bits_in) din = p.bits_in[grow * p.nblk_out + g];
+                uint32_t blo = 0, bhi = 0;
+                epilogue_math<EPI>(v0, bias_s, col0, p.slope, (uint32_t)din[gi], blo);
+                if (second) epilogue_math<EPI>(v1, bias_s, col0 + 32, p.slope, (uint32_t)(din[gi] >> 32), bhi);
+                if (EPI == EPI_BIAS_ACT_BITS) p.bits_out[grow * p.nblk_out + g] = ((uint64_t)bhi << 32) | blo;
+                if (p.y_f32) {
+                    float4 *dst = reinterpret_cast<float4 *>(p.y_f32 + grow * p.ldy + col0);
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int col0 = g * 64 + h * 32;
-                    uint32_t v[32];
-                    if (col0 < p.N) {
-                        tmem_ld32(tmem_base + lane_base + acc * 256 + col0, v);
-                        tmem_ld_wait();
-                    } else {
+                    for (int j = 0; j < 8; ++j)
+                        dst[j] = make_float4(__uint_as_float(v0[4 * j]), __uint_as_float(v0[4 * j + 1]), __uint_as_float(v0[4 * j + 2]), __uint_as_float(v0[4 * j + 3]));
+                    if (second) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = 0;
-                    }
-                    float f[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        float t = __uint_as_float(v[j]);
-                        if (p.bias && col0 < p.N) t += __ldg(p.bias + col0 + j);
-                        if (t > 0.f) dout |= (uint64_t)1 << (h * 32 + j);
-                        if (p.act) t = t > 0.f ? t : t * p.slope;
-                        if (p.bits_in) t = ((din >> (h * 32 + j)) & 1) ? t : t * p.slope;
-                        f[j] = t;
-                    }
-                    if (p.y_f32 && col0 < p.N) {
-                        float4 *dst = reinterpret_cast<float4 *>(p.y_f32 + grow * p.ldy + col0);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-                    }
-                    if (p.y_blocked) {
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            uint4 q;
-                            q.x = pack_bf16(f[8 * c + 0], f[8 * c + 1]);
-                            q.y = pack_bf16(f[8 * c + 2], f[8 * c + 3]);
-                            q.z = pack_bf16(f[8 * c + 4], f[8 * c + 5]);
-                            q.w = pack_bf16(f[8 * c + 6], f[8 * c + 7]);
-                            const int chunk = h * 4 + c;
-                            *reinterpret_cast<uint4 *>(sbuf + row * 128 + ((chunk ^ (row & 7)) << 4)) = q;
-                        }
+                        for (int j = 0; j < 8; ++j)
+                            dst[8 + j] = make_float4(__uint_as_float(v1[4 * j]), __uint_as_float(v1[4 * j + 1]), __uint_as_float(v1[4 * j + 2]), __uint_as_float(v1[4 * j + 3]));
                     }
                 }
-                if (p.bits_out) p.bits_out[grow * p.nblk_out + g] = dout;
                 if (p.y_blocked) {
+                    uint4 q[8];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        q[c] = make_uint4(pack_bf16(__uint_as_float(v0[8 * c]), __uint_as_float(v0[8 * c + 1])),
+                                          pack_bf16(__uint_as_float(v0[8 * c + 2]), __uint_as_float(v0[8 * c + 3])),
+                                          pack_bf16(__uint_as_float(v0[8 * c + 4]), __uint_as_float(v0[8 * c + 5])),
+                                          pack_bf16(__uint_as_float(v0[8 * c + 6]), __uint_as_float(v0[8 * c + 7])));
+                        q[4 + c] = make_uint4(pack_bf16(__uint_as_float(v1[8 * c]), __uint_as_float(v1[8 * c + 1])),
+                                              pack_bf16(__uint_as_float(v1[8 * c + 2]), __uint_as_float(v1[8 * c + 3])),
+                                              pack_bf16(__uint_as_float(v1[8 * c + 4]), __uint_as_float(v1[8 * c + 5])),
+                                              pack_bf16(__uint_as_float(v1[8 * c + 6]), __uint_as_float(v1[8 * c + 7])));
+                    }
+                    if (st == 0) bulk_wait_read<0>();      // the previous store from this staging buffer has been read
+                    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        *reinterpret_cast<uint4 *>(sbuf + row * 128 + ((c ^ (row & 7)) << 4)) = q[c];
                     fence_proxy_async();
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
-                    if (et == 0) {
+                    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+                    if (st == 0) {
                         bulk_s2g(p.y_blocked + ((size_t)tile * p.nblk_out + g) * kBlockBytes, sbuf, kBlockBytes);
                         bulk_commit();
                     }
                     if (p.colsum) {
-                        // thread (q = et>>5, l = et&31): columns 2l, 2l+1 of this group over rows [32q, 32q+32)
-                        const int q = et >> 5, l = et & 31;
+                        // thread (qq = st>>5, l = st&31): columns 2l, 2l+1 of this group over rows [32qq, 32qq+32)
+                        const int qq = st >> 5, l = st & 31;
                         float s0 = 0.f, s1 = 0.f;
 #pragma unroll 8
-                        for (int r = q * 32; r < q * 32 + 32; ++r) {
+                        for (int r = qq * 32; r < qq * 32 + 32; ++r) {
                             const uint32_t w2 = *reinterpret_cast<const uint32_t *>(sbuf + r * 128 + (((l >> 2) ^ (r & 7)) << 4) + (l & 3) * 4);
                             s0 += bf16_lo(w2); s1 += bf16_hi(w2);
                         }
-                        atomicAdd(&colsum_s[g * 64 + 2 * l], s0);
-                        atomicAdd(&colsum_s[g * 64 + 2 * l + 1], s1);
+                        atomicAdd(&colsum_s[col0 + 2 * l], s0);
+                        atomicAdd(&colsum_s[col0 + 2 * l + 1], s1);
                     }
-                    sb ^= 1;
                 }
             }
             tc_fence_before();
             mbar_arrive(&tempty[acc]);
         }
-        if (p.y_blocked && et == 0) bulk_wait<0>();
+        if (p.y_blocked && st == 0) bulk_wait<0>();
         if (p.colsum) {
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            for (int c = et; c < p.N; c += 128) atomicAdd(p.colsum + c, colsum_s[c]);
+            asm volatile("bar.sync 3, 256;" ::: "memory");
+            for (int c = threadIdx.x - 128; c < p.N; c += 256) atomicAdd(p.colsum + c, colsum_s[c]);
         }
     }
 
     tc_fence_before();
     __syncthreads();
     if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+template <int EPI>
+static int launch_linear(const LinearParams &p, int smem, cudaStream_t stream)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        PAPR_CUDA_TRY(cudaFuncSetAttribute(linear_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        attr_set = true;
+    }
+    const int grid = (int)(p.n_tiles < kNumSMs ? p.n_tiles : kNumSMs);
+    linear_kernel<EPI><<<grid, kLinThreads, smem, stream>>>(p);
+    return check_launch();
 }
 
 }  // namespace papr
@@ -208,23 +248,25 @@ extern "C" int papr_linear_bf16(const void *x, const void *w_image, const float 
     if (!x || !w_image || (!y_blocked && !y_f32)) return PAPR_ERR_INVALID_ARGUMENT;
     if (rows <= 0 || rows % kTileRows || N < 32 || N > 256 || N % 32 || K < 16 || K > 256 || K % 16) return PAPR_ERR_INVALID_ARGUMENT;
     if (y_f32 && (ldy < N || ldy % 4)) return PAPR_ERR_INVALID_ARGUMENT;
+    if (sign_bits_in && (bias || act || sign_bits_out)) return PAPR_ERR_INVALID_ARGUMENT;   // dgrad mode is exclusive
+    if (sign_bits_out && !(bias && act)) return PAPR_ERR_INVALID_ARGUMENT;
+    if (act && !bias) return PAPR_ERR_INVALID_ARGUMENT;
+    if (colsum && (!y_blocked || bias)) return PAPR_ERR_INVALID_ARGUMENT;
     LinearParams p;
     p.x = (const uint8_t *)x; p.w = (const uint8_t *)w_image; p.bias = bias;
     p.y_blocked = (uint8_t *)y_blocked; p.y_f32 = y_f32; p.bits_out = sign_bits_out; p.bits_in = sign_bits_in;
     p.colsum = colsum; p.n_tiles = rows / kTileRows; p.N = N; p.kblk = (K + 63) / 64; p.k_steps = K / 16;
     p.nblk_out = (N + 63) / 64; p.act = act; p.ldy = (int)ldy; p.slope = slope;
     const int wbytes = ((p.kblk * N * 128) + 1023) & ~1023;
-    const int fixed = 1024 + wbytes + 2 * kBlockBytes + 2048;
+    const int fixed = 1024 + wbytes + 2 * kBlockBytes + 1280;
     p.stages = (kMaxSmem - fixed) / kBlockBytes;
     if (p.stages > 8) p.stages = 8;
     if (p.stages < 2) return PAPR_ERR_INVALID_ARGUMENT;
     const int smem = fixed + p.stages * kBlockBytes;
-    static bool attr_set = false;
-    if (!attr_set) {
-        PAPR_CUDA_TRY(cudaFuncSetAttribute(linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-        attr_set = true;
-    }
-    const int grid = (int)(p.n_tiles < kNumSMs ? p.n_tiles : kNumSMs);
-    linear_kernel<<<grid, kLinThreads, smem, (cudaStream_t)stream>>>(p);
-    return check_launch();
+    cudaStream_t s = (cudaStream_t)stream;
+    if (sign_bits_in) return launch_linear<EPI_MASK>(p, smem, s);
+    if (sign_bits_out) return launch_linear<EPI_BIAS_ACT_BITS>(p, smem, s);
+    if (act) return launch_linear<EPI_BIAS_ACT>(p, smem, s);
+    if (bias) return launch_linear<EPI_BIAS>(p, smem, s);
+    return launch_linear<EPI_PLAIN>(p, smem, s);
 }
