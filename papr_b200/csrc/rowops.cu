@@ -311,6 +311,241 @@ __global__ void __launch_bounds__(kRowThreads) attn_prologue_bwd_kernel(const Pr
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------ fast prologue
+// Product-path variants (no fp32 taps): positional encodings come from ONE accurate sincosf per geometry scalar plus
+// the double-angle recurrence (abs. error <= 2^5 * 1 ulp ~ 4e-6, far below bf16 resolution), computed by 9 lanes and
+// shared through shared memory; LayerNorm affine terms live in registers; feature gradients use 16-byte vector
+// reductions (red.global.add.v4.f32).
+__device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d)
+{
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// lanes 0..8: fill pe[src*S + slot] for geometry scalar `src` = lane
+__device__ __forceinline__ void pe_fill(float x, int L, float *dst)
+{
+    float s, c;
+    sincosf(x, &s, &c);
+    dst[0] = x;
+    for (int i = 0; i < L; ++i) {
+        dst[1 + 2 * i] = s; dst[2 + 2 * i] = c;
+        const float s2 = 2.f * s * c, c2 = (c - s) * (c + s);
+        s = s2; c = c2;
+    }
+}
+
+__global__ void __launch_bounds__(kRowThreads) attn_prologue_fwd_fast_kernel(const PrologueParams p)
+{
+    __shared__ float pe_s[kRowWarps][kMaxDk];
+    __shared__ float geo_s[kRowWarps][32][9];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int S = 1 + 2 * p.L;
+    const int64_t M = p.R * p.K;
+    float *pe = pe_s[warp];
+    const int dpe = 6 * S;
+
+    // this lane's key chunk (columns 8*lane .. 8*lane+7): LayerNorm affine terms in registers
+    float a2[8], b2[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int j = lane * 8 + e;
+        a2[e] = (j < p.dk) ? p.a2[j] : 0.f;
+        b2[e] = (j < p.dk) ? p.b2[j] : 0.f;
+    }
+
+    for (int64_t ray = (int64_t)blockIdx.x * kRowWarps + warp; ray < p.R; ray += (int64_t)gridDim.x * kRowWarps) {
+        const int64_t view = ray / p.rays_per_view;
+        int pidx = 0;
+        if (lane < p.K) {
+            float u[3], den;
+            pidx = p.idx[ray * p.K + lane];
+            const Geometry geo = ray_point_geometry(p.points + (size_t)pidx * 3, p.rays_o + view * 3, p.rays_d + ray * 3, p.eps, u, &den);
+#pragma unroll
+            for (int i = 0; i < 9; ++i) geo_s[warp][lane][i] = geo.g[i];
+        }
+        __syncwarp();
+        for (int k = 0; k < p.K; ++k) {
+            const int64_t row = ray * p.K + k;
+            const int pk = __shfl_sync(0xffffffffu, pidx, k);
+            if (lane < 9) pe_fill(geo_s[warp][k][lane], p.L, pe + lane * S);
+            __syncwarp();
+            float sum = 0.f, val[4];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const int j = lane + 32 * m;
+                val[m] = (j < p.dk) ? pe[j] : 0.f;
+                sum += val[m];
+            }
+            const float mean = warp_sum(sum) / (float)p.dk;
+            float sq = 0.f;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) { const float c = val[m] - mean; if (lane + 32 * m < p.dk) sq += c * c; }
+            const float rstd = 1.f / (sqrtf(warp_sum(sq) / (float)(p.dk - 1)) + p.eps);
+            if (lane < p.nblk_k * 8) {
+                float f[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int j = lane * 8 + e;
+                    f[e] = (j < p.dk) ? a2[e] * (pe[j] - mean) * rstd + b2[e] : 0.f;
+                }
+                *reinterpret_cast<uint4 *>(p.kin + blocked_chunk_offset(row, lane, p.nblk_k)) =
+                    make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+            }
+            if (lane < p.nblk_v * 8) {
+                float f[8];
+                const int j0 = lane * 8;
+                if (j0 + 8 <= dpe) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) f[e] = pe[j0 + e + 3 * S];
+                } else if (j0 >= dpe && j0 + 8 <= p.dv && ((p.F & 3) == 0) && ((dpe & 1) == 0)) {
+                    // all eight columns are point features
+                    const float *src = p.feats + (size_t)pk * p.F + (j0 - dpe);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) f[e] = __ldg(src + e);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int j = j0 + e;
+                        float t = 0.f;
+                        if (j < dpe) t = pe[j + 3 * S];
+                        else if (j < p.dv) t = __ldg(p.feats + (size_t)pk * p.F + (j - dpe));
+                        f[e] = t;
+                    }
+                }
+                *reinterpret_cast<uint4 *>(p.vin + blocked_chunk_offset(row, lane, p.nblk_v)) =
+                    make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+            }
+            __syncwarp();
+        }
+    }
+    const int64_t M_pad = (M + 127) / 128 * 128;
+    const int per_row = (p.nblk_k + p.nblk_v) * 8;
+    for (int64_t i = (int64_t)blockIdx.x * kRowThreads + threadIdx.x; i < (M_pad - M) * per_row; i += (int64_t)gridDim.x * kRowThreads) {
+        const int64_t row = M + i / per_row;
+        const int c = (int)(i % per_row);
+        if (c < p.nblk_k * 8) *reinterpret_cast<uint4 *>(p.kin + blocked_chunk_offset(row, c, p.nblk_k)) = make_uint4(0, 0, 0, 0);
+        else *reinterpret_cast<uint4 *>(p.vin + blocked_chunk_offset(row, c - p.nblk_k * 8, p.nblk_v)) = make_uint4(0, 0, 0, 0);
+    }
+}
+
+__global__ void __launch_bounds__(kRowThreads) attn_prologue_bwd_fast_kernel(const PrologueParams p)
+{
+    __shared__ float pe_s[kRowWarps][kMaxDk];      // pe values
+    __shared__ float dpe_s[kRowWarps][kMaxDk];     // d pe (LayerNorm backward + value-stack gradient)
+    __shared__ float gk_s[kRowWarps][kMaxDk];      // d kin
+    __shared__ __align__(16) float gv_s[kRowWarps][kMaxDv];   // d vin
+    __shared__ float geo_s[kRowWarps][32][9];
+    __shared__ float dx_s[kRowWarps][32][6];       // per candidate: d proj (3), d D (3)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int S = 1 + 2 * p.L;
+    float *pe = pe_s[warp], *dpe = dpe_s[warp], *gk = gk_s[warp], *gv = gv_s[warp];
+    float a2c[4], acc_a2[4] = {0, 0, 0, 0}, acc_b2[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int m = 0; m < 4; ++m) a2c[m] = (lane + 32 * m < p.dk) ? p.a2[lane + 32 * m] : 0.f;
+    const bool vec_feats = (p.F % 4 == 0) && ((6 * S) % 4 == 0 || true);
+
+    for (int64_t ray = (int64_t)blockIdx.x * kRowWarps + warp; ray < p.R; ray += (int64_t)gridDim.x * kRowWarps) {
+        const int64_t view = ray / p.rays_per_view;
+        float u[3] = {0, 0, 0}, den = 1.f;
+        int pidx = 0;
+        if (lane < p.K) {
+            pidx = p.idx[ray * p.K + lane];
+            const Geometry geo = ray_point_geometry(p.points + (size_t)pidx * 3, p.rays_o + view * 3, p.rays_d + ray * 3, p.eps, u, &den);
+#pragma unroll
+            for (int i = 0; i < 9; ++i) geo_s[warp][lane][i] = geo.g[i];
+        }
+        __syncwarp();
+        for (int k = 0; k < p.K; ++k) {
+            const int64_t row = ray * p.K + k;
+            const int pk = __shfl_sync(0xffffffffu, pidx, k);
+            if (lane < 9) pe_fill(geo_s[warp][k][lane], p.L, pe + lane * S);
+            if (lane < p.nblk_k * 8) {
+                float f[8];
+                unpack8(*reinterpret_cast<const uint4 *>(p.dkin + blocked_chunk_offset(row, lane, p.nblk_k)), f);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) gk[lane * 8 + e] = f[e];
+            }
+            if (lane < p.nblk_v * 8) {
+                float f[8];
+                unpack8(*reinterpret_cast<const uint4 *>(p.dvin + blocked_chunk_offset(row, lane, p.nblk_v)), f);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) gv[lane * 8 + e] = f[e];
+            }
+            __syncwarp();
+            float val[4], sum = 0.f;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const int j = lane + 32 * m;
+                val[m] = (j < p.dk) ? pe[j] : 0.f;
+                sum += val[m];
+            }
+            const float mean = warp_sum(sum) / (float)p.dk;
+            float sq = 0.f;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) { const float c = val[m] - mean; if (lane + 32 * m < p.dk) sq += c * c; }
+            const float stdv = sqrtf(warp_sum(sq) / (float)(p.dk - 1));
+            const float rstd = 1.f / (stdv + p.eps);
+            float z[4], gz[4], s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const int j = lane + 32 * m;
+                z[m] = 0.f; gz[m] = 0.f;
+                if (j < p.dk) {
+                    z[m] = (val[m] - mean) * rstd;
+                    const float go = gk[j];
+                    acc_a2[m] += go * z[m]; acc_b2[m] += go;
+                    gz[m] = go * a2c[m];
+                    s1 += gz[m]; s2 += gz[m] * z[m];
+                }
+            }
+            s1 = warp_sum(s1) / (float)p.dk;
+            s2 = warp_sum(s2) / ((float)(p.dk - 1) * stdv);
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const int j = lane + 32 * m;
+                if (j >= 3 * S && j < p.dk) dpe[j] = rstd * (gz[m] - s1) - z[m] * s2 + gv[j - 3 * S];
+            }
+            __syncwarp();
+            if (lane < 6) {
+                // d(scalar) = sum over its S slots of d pe * d(slot)/dx, using the same recurrence values
+                const float *pv = pe + (3 + lane) * S;
+                const float *dv = dpe + (3 + lane) * S;
+                float t = dv[0], scale = 1.f;
+                for (int i = 0; i < p.L; ++i) {
+                    const float sn = pv[1 + 2 * i], cs = pv[2 + 2 * i];
+                    t += scale * (dv[1 + 2 * i] * cs - dv[2 + 2 * i] * sn);
+                    scale *= 2.f;
+                }
+                dx_s[warp][k][lane] = t;
+            }
+            if (vec_feats) {
+                for (int c = lane; c < p.F / 4; c += 32) {
+                    const float *g4 = gv + 6 * S + c * 4;
+                    red_add_v4(p.g_feats + (size_t)pk * p.F + c * 4, g4[0], g4[1], g4[2], g4[3]);
+                }
+            } else {
+                for (int c = lane; c < p.F; c += 32) atomicAdd(p.g_feats + (size_t)pk * p.F + c, gv[6 * S + c]);
+            }
+            __syncwarp();
+        }
+        if (lane < p.K) {
+            const float *dx = dx_s[warp][lane];
+            const float e0 = dx[0] - dx[3], e1 = dx[1] - dx[4], e2 = dx[2] - dx[5];
+            const float s = (e0 * u[0] + e1 * u[1] + e2 * u[2]) / den;
+            atomicAdd(p.g_points + (size_t)pidx * 3 + 0, dx[3] + u[0] * s);
+            atomicAdd(p.g_points + (size_t)pidx * 3 + 1, dx[4] + u[1] * s);
+            atomicAdd(p.g_points + (size_t)pidx * 3 + 2, dx[5] + u[2] * s);
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        const int j = lane + 32 * m;
+        if (j < p.dk) { atomicAdd(p.g_a2 + j, acc_a2[m]); atomicAdd(p.g_b2 + j, acc_b2[m]); }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ score + blend
 struct ScoreParams {
     const uint8_t *h5;      // blocked bf16 [M_pad, 256] key stack output (before its LayerNorm)
@@ -557,7 +792,8 @@ extern "C" int papr_attn_prologue_fwd(const float *rays_o, const float *rays_d, 
     p.R = R; p.rays_per_view = rays_per_view; p.K = K; p.L = L; p.F = F; p.dk = 9 * (1 + 2 * L); p.dv = 6 * (1 + 2 * L) + F;
     p.nblk_k = dk_pad / 64; p.nblk_v = dv_pad / 64; p.eps = eps;
     p.kin = (uint8_t *)kin; p.vin = (uint8_t *)vin; p.kin_f32 = kin_f32; p.vin_f32 = vin_f32;
-    attn_prologue_fwd_kernel<<<row_grid(R), kRowThreads, 0, (cudaStream_t)stream>>>(p);
+    if (kin_f32 || vin_f32) attn_prologue_fwd_kernel<<<row_grid(R), kRowThreads, 0, (cudaStream_t)stream>>>(p);
+    else attn_prologue_fwd_fast_kernel<<<row_grid(R), kRowThreads, 0, (cudaStream_t)stream>>>(p);
     return check_launch();
 }
 
@@ -577,7 +813,8 @@ extern "C" int papr_attn_prologue_bwd(const float *rays_o, const float *rays_d, 
     p.nblk_k = dk_pad / 64; p.nblk_v = dv_pad / 64; p.eps = eps;
     p.dkin = (const uint8_t *)dkin; p.dvin = (const uint8_t *)dvin; p.dkin_f32 = dkin_f32; p.dvin_f32 = dvin_f32;
     p.g_points = g_points; p.g_feats = g_feats; p.g_a2 = g_ln_a; p.g_b2 = g_ln_b;
-    attn_prologue_bwd_kernel<<<row_grid(R), kRowThreads, 0, (cudaStream_t)stream>>>(p);
+    if (dkin_f32 || dvin_f32) attn_prologue_bwd_kernel<<<row_grid(R), kRowThreads, 0, (cudaStream_t)stream>>>(p);
+    else attn_prologue_bwd_fast_kernel<<<row_grid(R), kRowThreads, 0, (cudaStream_t)stream>>>(p);
     return check_launch();
 }
 
