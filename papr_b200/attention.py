@@ -229,6 +229,37 @@ def _stack_backward(dz, inputs, bits_list, weights, slope, g_bias_last, in_valid
     return dz, gWs, gbs
 
 
+class _StackBf16Fn(torch.autograd.Function):
+    """A whole MLP stack (Linear+act ... Linear) for per-ray fp32 tensors: activations stay tile-blocked bf16 between
+    layers, sign bits drive the dgrad masks and the dgrad epilogues produce the bias gradients."""
+
+    @staticmethod
+    def forward(ctx, x, slope, n, *wb):
+        ws, bs = wb[:n], wb[n:]
+        xb = ops.Blocked.from_f32(x)
+        save = any(ctx.needs_input_grad)
+        inputs, bits, y = _stack_forward(xb, [w.detach() for w in ws], bs, slope, x.shape[1], save, last_f32=True)
+        n_out = ws[-1].shape[0]
+        if save:
+            ctx.blocked = (inputs, bits)
+            ctx.slope, ctx.n, ctx.rows, ctx.n_in = slope, n, x.shape[0], x.shape[1]
+            ctx.save_for_backward(*ws)
+        return y[: x.shape[0], :n_out]
+
+    @staticmethod
+    def backward(ctx, gy):
+        ws = ctx.saved_tensors
+        inputs, bits = ctx.blocked
+        n_out = ws[-1].shape[0]
+        g = gy.contiguous()
+        dz = ops.Blocked.from_f32(g, cols_pad=max(ops.pad_cols(n_out), 128))
+        gb_last = g.sum(0)
+        in_pad = ops.pad_cols(ctx.n_in)
+        dx, gWs, gbs = _stack_backward(dz, inputs, bits, ws, ctx.slope, gb_last, ctx.n_in, in_pad)
+        ctx.blocked = None
+        return (dx.to_f32(ctx.rows, ctx.n_in), None, None, *gWs, *gbs)
+
+
 class RowAttentionFn(torch.autograd.Function):
     """(points, pc_feats, influ, ua, c', key-in LayerNorm, key/value stack weights) -> (fused, attn)."""
 
@@ -357,8 +388,11 @@ class ProximityAttention(nn.Module):
         fq = self.embed.embed_q
         q = fq.innorm(q)
         lins = fq.mlp.linears()
-        for i, lin in enumerate(lins):
-            q = _linear(q, lin, self.q_slope if i < len(lins) - 1 else None, precision)
+        if precision == "fp32" or fq.mlp.skip_layers:
+            for i, lin in enumerate(lins):
+                q = _linear(q, lin, self.q_slope if i < len(lins) - 1 else None, precision)
+        else:
+            q = _StackBf16Fn.apply(q, self.q_slope, len(lins), *[l.weight for l in lins], *[l.bias for l in lins])
         q = fq.outnorm(q)
         al = self.attention_layer
         qp = _linear(q, al.w_q, None, precision)                               # q' (R,256)
