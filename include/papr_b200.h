@@ -74,11 +74,14 @@ int papr_pack_weight(const float *w, int64_t ld, int src_rows, int src_cols, int
  * colsum[N] += column sums of the bf16 output (bias gradients).
  * Backward use (dgrad): X = dZ, weight image packed with transpose=1, sign_bits_in = the forward layer's sign bits:
  * output column j is multiplied by 1 (bit set) or `slope` (bit clear), i.e. by act'(.) of relu/leakyrelu.
+ * addend_f32 (rows, ld_addend) fp32, optional: added to X W^T before bias/activation/mask -- the other half of a layer
+ * whose input is a concatenation (mlp.py:54-55 skip_layers: [h, inp] W^T = h W1^T + inp W2^T), or an extra gradient term.
  * act: 0 none, 1 relu/leakyrelu with negative slope `slope`.  rows % 128 == 0; N a multiple of 32, K a multiple of 16, both <= 256.
  */
 int papr_linear_bf16(const void *x, const void *w_image, const float *bias, void *y_blocked, float *y_f32,
                      int64_t ldy, uint64_t *sign_bits_out, const uint64_t *sign_bits_in, float *colsum,
-                     int64_t rows, int N, int K, int act, float slope, void *stream);
+                     const float *addend_f32, int64_t ld_addend, int64_t rows, int N, int K, int act, float slope,
+                     void *stream);
 /*
  * Weight gradient of a Linear layer (autograd of models/mlp.py:53-58): C[a,b] += sum_rows A[row,a] * B[row,b] with
  * A, B tile-blocked bf16 (a_cols, b_cols wide; a_cols >= 128*ceil(a_valid/128)); C fp32 (leading dim ldc), updated

@@ -20,7 +20,7 @@ SIGNATURES = {
     "papr_blocked_from_f32": [_ptr, _i64, _i32, _i64, _ptr, _i64, _i32, _ptr],
     "papr_blocked_to_f32": [_ptr, _i32, _ptr, _i64, _i32, _i64, _ptr],
     "papr_pack_weight": [_ptr, _i64, _i32, _i32, _i32, _i32, _i32, _f32, _ptr, _ptr],
-    "papr_linear_bf16": [_ptr, _ptr, _ptr, _ptr, _ptr, _i64, _ptr, _ptr, _ptr, _i64, _i32, _i32, _i32, _f32, _ptr],
+    "papr_linear_bf16": [_ptr, _ptr, _ptr, _ptr, _ptr, _i64, _ptr, _ptr, _ptr, _ptr, _i64, _i64, _i32, _i32, _i32, _f32, _ptr],
     "papr_attn_prologue_fwd": [_ptr] * 7 + [_i64, _i64, _i32, _i32, _i32, _f32, _ptr, _i32, _ptr, _i32, _ptr, _ptr, _ptr],
     "papr_attn_prologue_bwd": [_ptr] * 5 + [_i64, _i64, _i32, _i32, _i32, _f32, _ptr, _i32, _ptr, _i32] + [_ptr] * 7,
     "papr_score_blend_fwd": [_ptr] * 7 + [_i64, _i64, _i32, _i32, _i32, _i32, _f32, _f32] + [_ptr] * 5,

@@ -99,6 +99,8 @@ class _Shape:
         self.eps = attn.eps
         self.k_slope, self.v_slope = attn.k_slope, attn.v_slope
         self.score_relu, self.normalize, self.bkg_score = attn.score_relu, attn.normalize, attn.bkg_score
+        self.k_skip = tuple(attn.embed.embed_k.mlp.skip_layers)
+        self.v_skip = tuple(attn.embed.embed_v.mlp.skip_layers)
 
 
 def _prologue_fwd(sh, rays_o, rays_d, points, feats, idx, ln_a, ln_b, taps=False):
@@ -176,56 +178,69 @@ def _pad_bias(b, N):
     return b if b.numel() == N else F.pad(b, (0, N - b.numel()))
 
 
-def _stack_forward(x, weights, biases, slope, n_in0, save, last_f32=False):
-    """Run one MLP stack on the tensor cores.  Returns (layer inputs, sign bits, last output: Blocked or fp32)."""
+def _stack_forward(x, weights, biases, slope, n_in0, save, last_f32=False, skip_layers=()):
+    """Run one MLP stack on the tensor cores.  Returns (layer inputs, sign bits, last output: Blocked or fp32).
+    A skip layer (mlp.py:54-55: input = cat[h, stack input]) is two GEMMs into one accumulator: the stack-input half
+    is computed first in fp32 and handed to the main launch as its `addend`."""
     inputs, bits_list = [], []
     h = x
     n_layers = len(weights)
     out = None
+    K0 = (n_in0 + 15) // 16 * 16
     for i, (w, b) in enumerate(zip(weights, biases)):
-        n_out, n_in = w.shape
+        n_out = w.shape[0]
+        n_in = w.shape[1] - (n_in0 if i in skip_layers else 0)
         K = (n_in + 15) // 16 * 16
         N = (n_out + 31) // 32 * 32
         last = i == n_layers - 1
-        img = ops.pack_weight(w, N, K)
+        addend = None
+        if i in skip_layers:
+            _, addend, _ = ops.linear_bf16(x, ops.pack_weight(w[:, n_in:], N, K0), N, K0, out_blocked=False, out_f32=True)
+        img = ops.pack_weight(w[:, :n_in], N, K)
         inputs.append(h)
         f32 = last and last_f32
         yb, yf, bits = ops.linear_bf16(h, img, N, K, bias=_pad_bias(b, N), act=(not last) and slope is not None,
                                        slope=slope or 0.0, out_blocked=not f32, out_f32=f32,
-                                       sign_bits_out=save and not last and slope is not None)
+                                       sign_bits_out=save and not last and slope is not None, addend=addend)
         bits_list.append(bits)
         h = yb
         out = yf if f32 else yb
     return inputs, bits_list, out
 
 
-def _stack_backward(dz, inputs, bits_list, weights, slope, g_bias_last, in_valid, in_pad):
+def _stack_backward(dz, inputs, bits_list, weights, slope, g_bias_last, in_valid, in_pad, skip_layers=()):
     """Backward of _stack_forward.  dz: Blocked gradient of the last layer's output.  Returns (d_input Blocked,
     [gW], [gb])."""
     n_layers = len(weights)
     gWs, gbs = [None] * n_layers, [None] * n_layers
     gbs[-1] = g_bias_last
+    d_in_extra = None          # fp32 gradient reaching the stack input through skip connections
     for i in range(n_layers - 1, -1, -1):
         w = weights[i]
-        n_out, n_in = w.shape
-        gW = torch.zeros_like(w, dtype=torch.float32)
+        n_out = w.shape[0]
+        n_in = w.shape[1] - (in_valid if i in skip_layers else 0)
+        gW = torch.zeros(w.shape, dtype=torch.float32, device=w.device)
         x = inputs[i]
         if n_out < 128:     # narrow output (value head): swap operands so that M = n_in
             ops.wgrad_bf16(x, dz, gW, n_in, n_out, transpose_out=True)
         else:
             ops.wgrad_bf16(dz, x, gW, n_out, n_in)
-        gWs[i] = gW
         Kd = (n_out + 15) // 16 * 16
+        if i in skip_layers:
+            ops.wgrad_bf16(dz, inputs[0], gW[:, n_in:], n_out, in_valid)
+            _, extra, _ = ops.linear_bf16(dz, ops.pack_weight(w[:, n_in:], in_pad, Kd, transpose=True), in_pad, Kd,
+                                          out_blocked=False, out_f32=True)
+            d_in_extra = extra if d_in_extra is None else d_in_extra + extra
+        gWs[i] = gW
         if i > 0:
-            Nd = n_in
-            img_t = ops.pack_weight(w, Nd, Kd, transpose=True)
+            img_t = ops.pack_weight(w[:, :n_in], n_in, Kd, transpose=True)
             gb_prev = torch.zeros((weights[i - 1].shape[0],), device=w.device)
-            dz, _, _ = ops.linear_bf16(dz, img_t, Nd, Kd, sign_bits_in=bits_list[i - 1] if slope is not None else None,
+            dz, _, _ = ops.linear_bf16(dz, img_t, n_in, Kd, sign_bits_in=bits_list[i - 1] if slope is not None else None,
                                        slope=slope or 0.0, colsum=gb_prev)
             gbs[i - 1] = gb_prev
         else:
             img_t = ops.pack_weight(w, in_pad, Kd, transpose=True)
-            dz, _, _ = ops.linear_bf16(dz, img_t, in_pad, Kd)
+            dz, _, _ = ops.linear_bf16(dz, img_t, in_pad, Kd, addend=d_in_extra)
     return dz, gWs, gbs
 
 
@@ -272,8 +287,9 @@ class RowAttentionFn(torch.autograd.Function):
         pts = points.detach().contiguous()
         fts = feats.detach().contiguous() if feats is not None else None
         kin, vin, _, _ = _prologue_fwd(sh, rays_o, rays_d, pts, fts, idx, ln_a.detach(), ln_b.detach())
-        k_in, k_bits, h5 = _stack_forward(kin, [w.detach() for w in kw], kb, sh.k_slope, sh.dk, save)
-        v_in, v_bits, v = _stack_forward(vin, [w.detach() for w in vw], vb, sh.v_slope, sh.dv, save, last_f32=True)
+        k_in, k_bits, h5 = _stack_forward(kin, [w.detach() for w in kw], kb, sh.k_slope, sh.dk, save, skip_layers=sh.k_skip)
+        v_in, v_bits, v = _stack_forward(vin, [w.detach() for w in vw], vb, sh.v_slope, sh.dv, save, last_f32=True,
+                                         skip_layers=sh.v_skip)
         infl = influ.detach().reshape(-1).contiguous()
         fused, attn, sc, stats = _score_blend_fwd(sh, h5, None, ua.detach().contiguous(), cprime.detach().contiguous(),
                                                   infl, idx, v)
@@ -293,9 +309,9 @@ class RowAttentionFn(torch.autograd.Function):
         P = pts.shape[0]
         d_attn_c = d_attn.contiguous() if d_attn is not None else None
         dv, d_score, g_influ, g_bv = _blend_bwd(sh, d_fused.contiguous(), d_attn_c, attn, sc, infl, idx, v, P)
-        d_vin, gvW, gvb = _stack_backward(dv, v_in, v_bits, vw, sh.v_slope, g_bv, sh.dv, sh.dv_pad)
+        d_vin, gvW, gvb = _stack_backward(dv, v_in, v_bits, vw, sh.v_slope, g_bv, sh.dv, sh.dv_pad, sh.v_skip)
         dh5, _, zsum, dssum, g_b5 = _key_score_bwd(sh, d_score, h5, None, stats, ua)
-        d_kin, gkW, gkb = _stack_backward(dh5, k_in, k_bits, kw, sh.k_slope, g_b5, sh.dk, sh.dk_pad)
+        d_kin, gkW, gkb = _stack_backward(dh5, k_in, k_bits, kw, sh.k_slope, g_b5, sh.dk, sh.dk_pad, sh.k_skip)
         g_points, g_feats, g_a, g_b = _prologue_bwd(sh, rays_o, rays_d, pts, idx, ln_a, d_kin, d_vin, None, None, P)
         ctx.blocked = None
         return (None, None, None, None, g_points, g_feats, g_influ.reshape(-1, 1), zsum, dssum, g_a, g_b, None,
@@ -388,9 +404,10 @@ class ProximityAttention(nn.Module):
         fq = self.embed.embed_q
         q = fq.innorm(q)
         lins = fq.mlp.linears()
-        if precision == "fp32" or fq.mlp.skip_layers:
-            for i, lin in enumerate(lins):
-                q = _linear(q, lin, self.q_slope if i < len(lins) - 1 else None, precision)
+        if precision == "fp32":
+            q = fq.mlp(q)
+        elif fq.mlp.skip_layers:
+            raise NotImplementedError("skip_layers in the query stack are not used by any shipped config")
         else:
             q = _StackBf16Fn.apply(q, self.q_slope, len(lins), *[l.weight for l in lins], *[l.bias for l in lins])
         q = fq.outnorm(q)
@@ -419,9 +436,6 @@ class ProximityAttention(nn.Module):
         idx = idx.reshape(-1, K).contiguous()
         ua, cprime = self.query_terms(rd, precision)
         fk, fv = self.embed.embed_k, self.embed.embed_v
-        if fv.mlp.skip_layers or fk.mlp.skip_layers:
-            if precision != "fp32":
-                raise NotImplementedError("skip_layers are only supported by the fp32 parity path so far")
         if precision == "fp32":
             kin, vin = _PrologueFp32Fn.apply(sh, rays_o, rd, idx, points, feats, fk.innorm.a_2, fk.innorm.b_2)
             h5 = fk.mlp(kin)

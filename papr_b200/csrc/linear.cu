@@ -29,6 +29,8 @@ struct LinearParams {
     uint64_t *bits_out;      // [M, nblk_out] sign bits of the pre-activation (bit j of word g: column 64g+j > 0) or null
     const uint64_t *bits_in; // dgrad: multiply column j by act'(.) read from these bits, or null
     float *colsum;           // [N] += column sums of the bf16 output (atomic), or null
+    const float *addend;     // fp32 row-major [M, ld_add] added to the accumulator before bias/activation, or null
+    int64_t ld_add;
     int64_t n_tiles;
     int N, kblk, k_steps, nblk_out, act, ldy, stages;
     float slope;             // negative slope of the activation (0 relu, 0.2 leakyrelu) for act and for bits_in
@@ -157,6 +159,27 @@ __global__ void __launch_bounds__(kLinThreads, 1) linear_kernel(const LinearPara
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v1[j] = 0;
                 }
+                if (p.addend) {      // partial product of a split-K layer (skip connections), see papr_linear_bf16
+                    const float4 *src = reinterpret_cast<const float4 *>(p.addend + grow * p.ld_add + col0);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 a = __ldg(src + j);
+                        v0[4 * j] = __float_as_uint(__uint_as_float(v0[4 * j]) + a.x);
+                        v0[4 * j + 1] = __float_as_uint(__uint_as_float(v0[4 * j + 1]) + a.y);
+                        v0[4 * j + 2] = __float_as_uint(__uint_as_float(v0[4 * j + 2]) + a.z);
+                        v0[4 * j + 3] = __float_as_uint(__uint_as_float(v0[4 * j + 3]) + a.w);
+                    }
+                    if (second) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 a = __ldg(src + 8 + j);
+                            v1[4 * j] = __float_as_uint(__uint_as_float(v1[4 * j]) + a.x);
+                            v1[4 * j + 1] = __float_as_uint(__uint_as_float(v1[4 * j + 1]) + a.y);
+                            v1[4 * j + 2] = __float_as_uint(__uint_as_float(v1[4 * j + 2]) + a.z);
+                            v1[4 * j + 3] = __float_as_uint(__uint_as_float(v1[4 * j + 3]) + a.w);
+                        }
+                    }
+                }
                 uint32_t blo = 0, bhi = 0;
                 epilogue_math<EPI>(v0, bias_s, col0, p.slope, (uint32_t)din[gi], blo);
                 if (second) epilogue_math<EPI>(v1, bias_s, col0 + 32, p.slope, (uint32_t)(din[gi] >> 32), bhi);
@@ -242,12 +265,14 @@ static int launch_linear(const LinearParams &p, int smem, cudaStream_t stream)
 
 extern "C" int papr_linear_bf16(const void *x, const void *w_image, const float *bias, void *y_blocked, float *y_f32,
                                 int64_t ldy, uint64_t *sign_bits_out, const uint64_t *sign_bits_in, float *colsum,
-                                int64_t rows, int N, int K, int act, float slope, void *stream)
+                                const float *addend_f32, int64_t ld_addend, int64_t rows, int N, int K, int act,
+                                float slope, void *stream)
 {
     using namespace papr;
     if (!x || !w_image || (!y_blocked && !y_f32)) return PAPR_ERR_INVALID_ARGUMENT;
     if (rows <= 0 || rows % kTileRows || N < 32 || N > 256 || N % 32 || K < 16 || K > 256 || K % 16) return PAPR_ERR_INVALID_ARGUMENT;
     if (y_f32 && (ldy < N || ldy % 4)) return PAPR_ERR_INVALID_ARGUMENT;
+    if (addend_f32 && (ld_addend < N || ld_addend % 4)) return PAPR_ERR_INVALID_ARGUMENT;
     if (sign_bits_in && (bias || act || sign_bits_out)) return PAPR_ERR_INVALID_ARGUMENT;   // dgrad mode is exclusive
     if (sign_bits_out && !(bias && act)) return PAPR_ERR_INVALID_ARGUMENT;
     if (act && !bias) return PAPR_ERR_INVALID_ARGUMENT;
@@ -255,6 +280,7 @@ extern "C" int papr_linear_bf16(const void *x, const void *w_image, const float 
     LinearParams p;
     p.x = (const uint8_t *)x; p.w = (const uint8_t *)w_image; p.bias = bias;
     p.y_blocked = (uint8_t *)y_blocked; p.y_f32 = y_f32; p.bits_out = sign_bits_out; p.bits_in = sign_bits_in;
+    p.addend = addend_f32; p.ld_add = ld_addend;
     p.colsum = colsum; p.n_tiles = rows / kTileRows; p.N = N; p.kblk = (K + 63) / 64; p.k_steps = K / 16;
     p.nblk_out = (N + 63) / 64; p.act = act; p.ldy = (int)ldy; p.slope = slope;
     const int wbytes = ((p.kblk * N * 128) + 1023) & ~1023;

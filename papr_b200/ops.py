@@ -122,7 +122,7 @@ def pack_weight(w, N, K, transpose=False, scale=1.0):
 
 
 def linear_bf16(x, w_image, N, K, bias=None, act=False, slope=0.0, out_blocked=True, out_f32=False,
-                sign_bits_out=False, sign_bits_in=None, colsum=None):
+                sign_bits_out=False, sign_bits_in=None, colsum=None, addend=None):
     """Y = act(X W^T + b) on tcgen05 (see papr_linear_bf16).  Returns (Blocked|None, f32|None, bits|None)."""
     dev = x.buf.device
     rows_pad = x.rows_pad
@@ -131,12 +131,15 @@ def linear_bf16(x, w_image, N, K, bias=None, act=False, slope=0.0, out_blocked=T
     yf = torch.empty((rows_pad, N), dtype=torch.float32, device=dev) if out_f32 else None
     bits = torch.empty((rows_pad, pad_cols(N) // 64), dtype=torch.int64, device=dev) if sign_bits_out else None
     nbytes = rows_pad * (2.0 * pad_cols(K) + (2.0 * pad_cols(N) if out_blocked else 0) + (4.0 * N if out_f32 else 0)
-                         + (8.0 * pad_cols(N) / 64 if sign_bits_out else 0) + (8.0 * pad_cols(N) / 64 if sign_bits_in is not None else 0))
+                         + (8.0 * pad_cols(N) / 64 if sign_bits_out else 0) + (8.0 * pad_cols(N) / 64 if sign_bits_in is not None else 0)
+                         + (4.0 * N if addend is not None else 0))
     call("papr_linear_bf16",
          x.data_ptr(), w_image.data_ptr(), bias.data_ptr() if bias is not None else None,
          yb.data_ptr() if yb is not None else None, yf.data_ptr() if yf is not None else None, N,
          bits.data_ptr() if bits is not None else None, sign_bits_in.data_ptr() if sign_bits_in is not None else None,
-         colsum.data_ptr() if colsum is not None else None, rows_pad, N, K, int(act), float(slope),
+         colsum.data_ptr() if colsum is not None else None,
+         addend.data_ptr() if addend is not None else None, addend.stride(0) if addend is not None else 0,
+         rows_pad, N, K, int(act), float(slope),
          flops=2.0 * x.rows * N * K, nbytes=nbytes)
     return yb, yf, bits
 

@@ -50,7 +50,7 @@ def _fp64_oracle_grads(cfg, params, g):
 
 
 def _supported(name, precision):
-    return not (precision == "bf16" and name.startswith("lego_like"))    # skip_layers: fp32 path only so far
+    return True
 
 
 @pytest.mark.parametrize("name", GOLDEN_CASES)
