@@ -147,6 +147,30 @@ int papr_key_score_bwd(const float *d_score, const void *h5, const float *h5_f32
                        const float *ua, int64_t R, int K, float eps, void *dh5_blocked, float *dh5_f32,
                        float *zsum, float *dssum, float *g_bias5, void *stream);
 
+/*
+ * A whole MLP stack per launch (fused papr_linear_bf16 chain, reference models/mlp.py:47-59): the 128-row activation
+ * tiles stay in shared memory between layers; CTA pairs (tcgen05 cta_group::2) split every weight chunk.  Layer l maps
+ * its K_l inputs (K_0 = K0, K_l = N_{l-1}) to N_l outputs; hidden layers must have N = 256, the last one 32..256.
+ * Per layer, the same options as papr_linear_bf16: bias/act (forward), sign_bits_out, sign_bits_in + colsum (dgrad),
+ * out_blocked (tile-blocked copy of the layer's output: the stash the weight-gradient kernel needs, or the final
+ * result) and out_f32.  `layers` is a HOST array.
+ */
+typedef struct papr_stack_layer {
+    const void *w_image;          /* papr_pack_weight image, N x K_l */
+    const float *bias;            /* [N] or NULL */
+    void *out_blocked;            /* tile-blocked bf16 [rows, ceil(N/64)*64] or NULL */
+    float *out_f32;               /* fp32 row-major [rows, ld_f32] or NULL */
+    int64_t ld_f32;
+    uint64_t *sign_bits_out;      /* [rows, ceil(N/64)] or NULL */
+    const uint64_t *sign_bits_in; /* [rows, ceil(N/64)] or NULL */
+    float *colsum;                /* [N] accumulated, or NULL */
+    int32_t N;
+    int32_t act;                  /* 0 none, 1 relu/leakyrelu(slope) */
+} papr_stack_layer;
+
+int papr_stack_bf16(const void *x, int K0, const papr_stack_layer *layers, int n_layers, int64_t rows, float slope,
+                    void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -26,9 +26,17 @@ SIGNATURES = {
     "papr_score_blend_fwd": [_ptr] * 7 + [_i64, _i64, _i32, _i32, _i32, _i32, _f32, _f32] + [_ptr] * 5,
     "papr_blend_bwd": [_ptr] * 7 + [_i64, _i64, _i32, _i32, _i32, _i32] + [_ptr] * 5,
     "papr_key_score_bwd": [_ptr] * 5 + [_i64, _i32, _f32] + [_ptr] * 6,
+    "papr_stack_bf16": [_ptr, _i32, _ptr, _i32, _i64, _f32, _ptr],
     "papr_wgrad_bf16": [_ptr, _i32, _ptr, _i32, _ptr, _i64, _i32, _i32, _i32, _i64, _ptr],
 }
 _RESTYPE = {"papr_status_string": _c.c_char_p, "papr_last_cuda_error": _c.c_char_p}
+
+
+class StackLayer(ctypes.Structure):
+    """papr_stack_layer of include/papr_b200.h"""
+    _fields_ = [("w_image", _ptr), ("bias", _ptr), ("out_blocked", _ptr), ("out_f32", _ptr), ("ld_f32", _i64),
+                ("sign_bits_out", _ptr), ("sign_bits_in", _ptr), ("colsum", _ptr), ("N", ctypes.c_int32),
+                ("act", ctypes.c_int32)]
 
 
 class PaprError(RuntimeError):

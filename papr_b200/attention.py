@@ -178,10 +178,48 @@ def _pad_bias(b, N):
     return b if b.numel() == N else F.pad(b, (0, N - b.numel()))
 
 
+FUSE_STACKS = True      # one cta_group::2 launch per MLP stack (papr_stack_bf16) instead of one launch per layer
+
+
+def _stack_forward_fused(x, weights, biases, slope, n_in0, save, last_f32):
+    n_layers = len(weights)
+    dev = weights[0].device
+    K0 = (n_in0 + 15) // 16 * 16
+    layers, inputs, bits_list = [], [x], []
+    out = None
+    for i, (w, b) in enumerate(zip(weights, biases)):
+        n_out, n_in = w.shape
+        K = (n_in + 15) // 16 * 16
+        N = (n_out + 31) // 32 * 32
+        last = i == n_layers - 1
+        act = (not last) and slope is not None
+        spec = dict(w_image=ops.pack_weight(w, N, K), N=N, bias=_pad_bias(b, N), act=act)
+        bits = None
+        if save and act:
+            bits = torch.empty((x.rows_pad, ops.pad_cols(N) // 64), dtype=torch.int64, device=dev)
+            spec["sign_bits_out"] = bits
+        bits_list.append(bits)
+        if last and last_f32:
+            out = torch.empty((x.rows_pad, N), dtype=torch.float32, device=dev)
+            spec["out_f32"] = out
+        elif last or save:                       # hidden outputs only leave the SM when backward needs them
+            ob = ops.Blocked(x.rows, N, dev)
+            spec["out_blocked"] = ob
+            if last:
+                out = ob
+            else:
+                inputs.append(ob)
+        layers.append(spec)
+    ops.stack_bf16(x, K0, layers, slope=slope or 0.0)
+    return inputs, bits_list, out
+
+
 def _stack_forward(x, weights, biases, slope, n_in0, save, last_f32=False, skip_layers=()):
     """Run one MLP stack on the tensor cores.  Returns (layer inputs, sign bits, last output: Blocked or fp32).
     A skip layer (mlp.py:54-55: input = cat[h, stack input]) is two GEMMs into one accumulator: the stack-input half
     is computed first in fp32 and handed to the main launch as its `addend`."""
+    if FUSE_STACKS and not skip_layers and len(weights) <= 8 and all(w.shape[0] == 256 for w in weights[:-1]):
+        return _stack_forward_fused(x, weights, biases, slope, n_in0, save, last_f32)
     inputs, bits_list = [], []
     h = x
     n_layers = len(weights)
@@ -214,6 +252,37 @@ def _stack_backward(dz, inputs, bits_list, weights, slope, g_bias_last, in_valid
     n_layers = len(weights)
     gWs, gbs = [None] * n_layers, [None] * n_layers
     gbs[-1] = g_bias_last
+    if FUSE_STACKS and not skip_layers and n_layers <= 8 and all(w.shape[0] == 256 for w in weights[:-1]):
+        # dgrad of the whole stack in one launch; the per-layer dZ tiles it stashes feed the weight-gradient launches
+        dev = weights[0].device
+        layers, dzs = [], [dz]
+        for i in range(n_layers - 1, -1, -1):
+            w = weights[i]
+            n_out, n_in = w.shape
+            Kd = (n_out + 15) // 16 * 16
+            Nd = n_in if i > 0 else in_pad
+            ob = ops.Blocked(dz.rows, Nd, dev)
+            spec = dict(w_image=ops.pack_weight(w, Nd, Kd, transpose=True), N=Nd, out_blocked=ob)
+            if i > 0:
+                gbs[i - 1] = torch.zeros((weights[i - 1].shape[0],), device=dev)
+                spec["colsum"] = gbs[i - 1]
+                if slope is not None:
+                    spec["sign_bits_in"] = bits_list[i - 1]
+            layers.append(spec)
+            dzs.append(ob)
+        K0 = (weights[-1].shape[0] + 15) // 16 * 16
+        ops.stack_bf16(dz, K0, layers, slope=slope or 0.0)
+        for i in range(n_layers - 1, -1, -1):
+            w = weights[i]
+            n_out, n_in = w.shape
+            gW = torch.zeros(w.shape, dtype=torch.float32, device=dev)
+            dzi = dzs[n_layers - 1 - i]
+            if n_out < 128:
+                ops.wgrad_bf16(inputs[i], dzi, gW, n_in, n_out, transpose_out=True)
+            else:
+                ops.wgrad_bf16(dzi, inputs[i], gW, n_out, n_in)
+            gWs[i] = gW
+        return dzs[-1], gWs, gbs
     d_in_extra = None          # fp32 gradient reaching the stack input through skip connections
     for i in range(n_layers - 1, -1, -1):
         w = weights[i]

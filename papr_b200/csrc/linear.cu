@@ -36,24 +36,6 @@ struct LinearParams {
     float slope;             // negative slope of the activation (0 relu, 0.2 leakyrelu) for act and for bits_in
 };
 
-// Epilogue flavours (compile-time so the per-element code carries no dead predicates)
-enum { EPI_PLAIN = 0, EPI_BIAS = 1, EPI_BIAS_ACT = 2, EPI_BIAS_ACT_BITS = 3, EPI_MASK = 4 };
-
-template <int EPI>
-__device__ __forceinline__ void epilogue_math(uint32_t (&v)[32], const float *bias_s, int col0, float slope, uint32_t din,
-                                              uint32_t &dout)
-{
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-        float t = __uint_as_float(v[j]);
-        if (EPI == EPI_BIAS || EPI == EPI_BIAS_ACT || EPI == EPI_BIAS_ACT_BITS) t += bias_s[col0 + j];
-        if (EPI == EPI_BIAS_ACT_BITS) dout |= (t > 0.f ? 1u : 0u) << j;
-        if (EPI == EPI_BIAS_ACT || EPI == EPI_BIAS_ACT_BITS) t = t > 0.f ? t : t * slope;
-        if (EPI == EPI_MASK) t = ((din >> j) & 1u) ? t : t * slope;
-        v[j] = __float_as_uint(t);
-    }
-}
-
 template <int EPI>
 __global__ void __launch_bounds__(kLinThreads, 1) linear_kernel(const LinearParams p)
 {

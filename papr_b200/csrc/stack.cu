@@ -1,0 +1,339 @@
+// Stages a7/a12, fused: a whole MLP stack (up to 8 Linear layers, forward or dgrad direction) per launch, with the
+// 128-row activation tiles kept in shared memory from layer to layer (reference models/mlp.py:47-59 loop).
+//
+// CTA pairs (cluster of 2, tcgen05 cta_group::2): one tcgen05.mma covers M = 256 rows -- 128 from each CTA -- and each
+// CTA stages only HALF of every weight chunk (N/2 rows), so the weight stream from L2 costs 64 KB per tile-layer
+// instead of 128 KB and the tensor pipe, not L2, becomes the limit.  Each CTA keeps two tiles in flight ("slots"):
+// while the tensor core multiplies slot 1, the eight epilogue warps drain slot 0 (TMEM -> bias/activation or
+// activation-derivative mask -> bf16 -> back into the slot's shared-memory tile, which is the next layer's A operand).
+//
+//   warp 0      producer : input tiles (TMA bulk, per slot) and this CTA's half of every weight chunk (ring of stages)
+//   warp 1      MMA issuer (leader CTA only): waits both CTAs' data, issues tcgen05.mma.cta_group::2, commits with
+//               multicast so the "stage free" / "accumulator full" barriers fire in both CTAs
+//   warp 2      TMEM allocator (both CTAs, cta_group::2)
+//   warp 3      relay (peer CTA only): forwards "my TMA data landed" to the leader's barriers
+//   warps 4-11  epilogue
+// Training-time by-products are written as they appear: each layer's output tile (the next layer's input, needed by
+// the weight-gradient kernel) straight from the shared-memory tile with a TMA bulk store, activation sign bits, and
+// per-column sums (bias gradients) in the dgrad direction.
+#include "tc_common.cuh"
+
+namespace papr {
+
+constexpr int kStkThreads = 384;
+constexpr int kStkMaxLayers = 8;
+constexpr int kSlotBytes = 4 * kBlockBytes;      // one 128 x 256 bf16 tile
+constexpr int kStkMaxSmem = 232448;
+
+struct StackLayerDev {
+    const uint8_t *w;          // weight image [kblk][N rows][128 B]
+    const float *bias;         // [N] or null
+    uint8_t *out_blocked;      // this layer's output as a tile-blocked tensor (stash / final), or null
+    float *out_f32;            // fp32 row-major output, or null
+    uint64_t *bits_out;        // sign bits of the pre-activation, or null
+    const uint64_t *bits_in;   // activation-derivative mask bits (dgrad), or null
+    float *colsum;             // [N] += column sums of the bf16 output, or null
+    int64_t ld_f32;
+    int N, kblk, k_steps, act;
+};
+
+struct StackParams {
+    const uint8_t *x;          // tile-blocked input [rows, kblk0*64]
+    int64_t n_tiles;
+    int n_layers, kblk0, stages, any_stash;
+    float slope;
+    StackLayerDev L[kStkMaxLayers];
+};
+
+template <int EPI>
+__device__ __forceinline__ void stack_math(uint32_t (&v0)[32], uint32_t (&v1)[32], bool second, const float *bias, int col0,
+                                           float slope, uint64_t din, uint64_t &dout)
+{
+    uint32_t blo = 0, bhi = 0;
+    epilogue_math<EPI>(v0, bias, col0, slope, (uint32_t)din, blo);
+    if (second) epilogue_math<EPI>(v1, bias, col0 + 32, slope, (uint32_t)(din >> 32), bhi);
+    dout = ((uint64_t)bhi << 32) | blo;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kStkThreads, 1) stack_kernel(const __grid_constant__ StackParams p)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *act = smem;                                   // 2 slots x 64 KB
+    uint8_t *ring = act + 2 * kSlotBytes;                  // stages x 16 KB (this CTA's half of a weight chunk)
+    uint64_t *bars = (uint64_t *)(ring + p.stages * kBlockBytes);
+    uint64_t *w_full = bars, *w_empty = bars + 8, *pw_full = bars + 16;
+    uint64_t *in_full = bars + 24, *pin_full = bars + 26, *in_free = bars + 28, *act_ready = bars + 30, *acc_full = bars + 32;
+    uint32_t *tmem_slot = (uint32_t *)(bars + 34);
+    float *vec_s = (float *)(bars + 36);                   // [layers][256]: biases (forward) or column sums (dgrad)
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int64_t cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    const int64_t n_quads = (p.n_tiles + 3) >> 2;
+    const int L = p.n_layers;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 8; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); mbar_init(&pw_full[i], 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&in_full[i], 1); mbar_init(&pin_full[i], 1); mbar_init(&in_free[i], 8);
+            mbar_init(&act_ready[i], 16); mbar_init(&acc_full[i], 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc2(tmem_slot, 512);
+    for (int i = threadIdx.x; i < L * 256; i += kStkThreads) {
+        const int l = i >> 8, c = i & 255;
+        vec_s[i] = (p.L[l].bias && c < p.L[l].N) ? p.L[l].bias[c] : 0.f;
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int st = 0; uint32_t ph = 0; int64_t qi = 0;
+            for (int64_t q = cluster_id; q < n_quads; q += n_clusters, ++qi) {
+                for (int l = 0; l < L; ++l) {
+                    const StackLayerDev &Ld = p.L[l];
+                    const uint32_t chunk_bytes = (uint32_t)(Ld.N >> 1) * 128u;
+                    for (int s = 0; s < 2; ++s) {
+                        if (l == 0) {
+                            if (qi > 0) mbar_wait(&in_free[s], (uint32_t)((qi - 1) & 1));
+                            int64_t tile = 4 * q + 2 * s + rank;
+                            if (tile >= p.n_tiles) tile = p.n_tiles - 1;
+                            mbar_arrive_expect_tx(&in_full[s], (uint32_t)(p.kblk0 * kBlockBytes));
+                            for (int kb = 0; kb < p.kblk0; ++kb)
+                                bulk_g2s(act + s * kSlotBytes + kb * kBlockBytes, p.x + ((size_t)tile * p.kblk0 + kb) * kBlockBytes,
+                                         kBlockBytes, &in_full[s]);
+                        }
+                        for (int kc = 0; kc < Ld.kblk; ++kc) {
+                            mbar_wait(&w_empty[st], ph ^ 1);
+                            mbar_arrive_expect_tx(&w_full[st], chunk_bytes);
+                            bulk_g2s(ring + st * kBlockBytes, Ld.w + (size_t)kc * Ld.N * 128 + (size_t)rank * chunk_bytes, chunk_bytes, &w_full[st]);
+                            if (++st == p.stages) { st = 0; ph ^= 1; }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 3) {
+        if (lane == 0 && rank == 1) {       // relay: tell the leader that this CTA's TMA data has landed
+            int st = 0; uint32_t ph = 0; int64_t qi = 0;
+            for (int64_t q = cluster_id; q < n_quads; q += n_clusters, ++qi) {
+                for (int l = 0; l < L; ++l) {
+                    for (int s = 0; s < 2; ++s) {
+                        if (l == 0) { mbar_wait(&in_full[s], (uint32_t)(qi & 1)); mbar_arrive_remote(&pin_full[s], 0); }
+                        for (int kc = 0; kc < p.L[l].kblk; ++kc) {
+                            mbar_wait(&w_full[st], ph);
+                            mbar_arrive_remote(&pw_full[st], 0);
+                            if (++st == p.stages) { st = 0; ph ^= 1; }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            int st = 0; uint32_t ph = 0; int64_t qi = 0;
+            int64_t js[2] = {0, 0};
+            for (int64_t q = cluster_id; q < n_quads; q += n_clusters, ++qi) {
+                for (int l = 0; l < L; ++l) {
+                    const StackLayerDev &Ld = p.L[l];
+                    const uint32_t idesc = umma_idesc(256, Ld.N, false, false);
+                    for (int s = 0; s < 2; ++s) {
+                        if (l == 0) {
+                            mbar_wait(&in_full[s], (uint32_t)(qi & 1));
+                            mbar_wait_cluster(&pin_full[s], (uint32_t)(qi & 1));
+                        }
+                        if (js[s] > 0) mbar_wait_cluster(&act_ready[s], (uint32_t)((js[s] - 1) & 1));
+                        tc_fence_after();
+                        const uint32_t d = tmem_base + s * 256;
+                        for (int kc = 0; kc < Ld.kblk; ++kc) {
+                            mbar_wait(&w_full[st], ph);
+                            mbar_wait_cluster(&pw_full[st], ph);
+                            tc_fence_after();
+                            const uint32_t a0 = smem_u32(act + s * kSlotBytes + kc * kBlockBytes);
+                            const uint32_t b0 = smem_u32(ring + st * kBlockBytes);
+                            const int nk = min(4, Ld.k_steps - 4 * kc);
+                            for (int k = 0; k < nk; ++k)
+                                umma2_bf16(d, umma_desc(a0 + k * 32, 16, 1024), umma_desc(b0 + k * 32, 16, 1024), idesc, (uint32_t)((kc | k) != 0));
+                            umma2_commit(&w_empty[st]);
+                            if (++st == p.stages) { st = 0; ph ^= 1; }
+                        }
+                        umma2_commit(&acc_full[s]);
+                        ++js[s];
+                    }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        const int ew = warp - 4;
+        const int set = ew >> 2, quad = ew & 3;
+        const int row = quad * 32 + lane;
+        const int sthr = quad * 32 + lane;                 // thread index within the set
+        const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+        const int bar_id = 1 + set;
+        int64_t je[2] = {0, 0};
+        for (int64_t q = cluster_id; q < n_quads; q += n_clusters) {
+            for (int l = 0; l < L; ++l) {
+                const StackLayerDev &Ld = p.L[l];
+                const int ngroups = (Ld.N + 63) >> 6;
+                const bool last = l == L - 1;
+                const bool to_act = !last || Ld.out_blocked != nullptr;
+                float *vec = vec_s + l * 256;
+                for (int s = 0; s < 2; ++s) {
+                    const int64_t tile = 4 * q + 2 * s + rank;
+                    const bool valid = tile < p.n_tiles;
+                    const int64_t grow = tile * kTileRows + row;
+                    uint64_t din[2] = {0, 0};
+                    if (Ld.bits_in && valid) {
+                        if (set < ngroups) din[0] = Ld.bits_in[grow * ngroups + set];
+                        if (set + 2 < ngroups) din[1] = Ld.bits_in[grow * ngroups + set + 2];
+                    }
+                    mbar_wait(&acc_full[s], (uint32_t)(je[s] & 1));
+                    tc_fence_after();
+                    for (int gi = 0; gi < 2; ++gi) {
+                        const int g = set + 2 * gi;
+                        if (g >= ngroups) break;
+                        const int col0 = g * 64;
+                        uint32_t v0[32], v1[32];
+                        const bool second = col0 + 32 < Ld.N;
+                        tmem_ld32(tmem_base + lane_base + s * 256 + col0, v0);
+                        if (second) tmem_ld32(tmem_base + lane_base + s * 256 + col0 + 32, v1);
+                        tmem_ld_wait();
+                        if (!second) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v1[j] = 0;
+                        }
+                        uint64_t dout = 0;
+                        if (Ld.bits_in) stack_math<EPI_MASK>(v0, v1, second, vec, col0, p.slope, din[gi], dout);
+                        else if (Ld.bits_out) stack_math<EPI_BIAS_ACT_BITS>(v0, v1, second, vec, col0, p.slope, 0, dout);
+                        else if (Ld.act) stack_math<EPI_BIAS_ACT>(v0, v1, second, vec, col0, p.slope, 0, dout);
+                        else if (Ld.bias) stack_math<EPI_BIAS>(v0, v1, second, vec, col0, p.slope, 0, dout);
+                        if (Ld.bits_out && valid) Ld.bits_out[grow * ngroups + g] = dout;
+                        if (Ld.out_f32 && valid) {
+                            float4 *dst = reinterpret_cast<float4 *>(Ld.out_f32 + grow * Ld.ld_f32 + col0);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                dst[j] = make_float4(__uint_as_float(v0[4 * j]), __uint_as_float(v0[4 * j + 1]), __uint_as_float(v0[4 * j + 2]), __uint_as_float(v0[4 * j + 3]));
+                            if (second) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j)
+                                    dst[8 + j] = make_float4(__uint_as_float(v1[4 * j]), __uint_as_float(v1[4 * j + 1]), __uint_as_float(v1[4 * j + 2]), __uint_as_float(v1[4 * j + 3]));
+                            }
+                        }
+                        if (to_act) {
+                            uint4 qv[8];
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) {
+                                qv[c] = make_uint4(pack_bf16(__uint_as_float(v0[8 * c]), __uint_as_float(v0[8 * c + 1])),
+                                                   pack_bf16(__uint_as_float(v0[8 * c + 2]), __uint_as_float(v0[8 * c + 3])),
+                                                   pack_bf16(__uint_as_float(v0[8 * c + 4]), __uint_as_float(v0[8 * c + 5])),
+                                                   pack_bf16(__uint_as_float(v0[8 * c + 6]), __uint_as_float(v0[8 * c + 7])));
+                                qv[4 + c] = make_uint4(pack_bf16(__uint_as_float(v1[8 * c]), __uint_as_float(v1[8 * c + 1])),
+                                                       pack_bf16(__uint_as_float(v1[8 * c + 2]), __uint_as_float(v1[8 * c + 3])),
+                                                       pack_bf16(__uint_as_float(v1[8 * c + 4]), __uint_as_float(v1[8 * c + 5])),
+                                                       pack_bf16(__uint_as_float(v1[8 * c + 6]), __uint_as_float(v1[8 * c + 7])));
+                            }
+                            uint8_t *blk = act + s * kSlotBytes + g * kBlockBytes;
+                            if (p.any_stash) {      // an earlier TMA store may still be reading this block
+                                if (sthr == 0) bulk_wait_read<0>();
+                                asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+                            }
+#pragma unroll
+                            for (int c = 0; c < 8; ++c)
+                                *reinterpret_cast<uint4 *>(blk + row * 128 + ((c ^ (row & 7)) << 4)) = qv[c];
+                            fence_proxy_async();
+                            if (Ld.out_blocked || Ld.colsum) {
+                                asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+                                if (sthr == 0 && valid && Ld.out_blocked) {
+                                    bulk_s2g(Ld.out_blocked + ((size_t)tile * ngroups + g) * kBlockBytes, blk, kBlockBytes);
+                                    bulk_commit();
+                                }
+                                if (Ld.colsum && valid) {
+                                    const int qq = sthr >> 5, ll = sthr & 31;
+                                    float s0 = 0.f, s1 = 0.f;
+#pragma unroll 8
+                                    for (int r = qq * 32; r < qq * 32 + 32; ++r) {
+                                        const uint32_t w2 = *reinterpret_cast<const uint32_t *>(blk + r * 128 + (((ll >> 2) ^ (r & 7)) << 4) + (ll & 3) * 4);
+                                        s0 += bf16_lo(w2); s1 += bf16_hi(w2);
+                                    }
+                                    atomicAdd(&vec[col0 + 2 * ll], s0);
+                                    atomicAdd(&vec[col0 + 2 * ll + 1], s1);
+                                }
+                            }
+                        }
+                    }
+                    tc_fence_before();
+                    if (last && sthr == 0 && p.any_stash) bulk_wait_read<0>();   // the slot is about to be refilled by the producer
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (last) mbar_arrive(&in_free[s]);
+                        if (rank == 0) mbar_arrive(&act_ready[s]); else mbar_arrive_remote(&act_ready[s], 0);
+                    }
+                    ++je[s];
+                }
+            }
+        }
+        if (sthr == 0) bulk_wait<0>();
+        asm volatile("bar.sync 3, 256;" ::: "memory");
+        for (int i = threadIdx.x - 128; i < L * 256; i += 256) {
+            const int l = i >> 8, c = i & 255;
+            if (p.L[l].colsum && c < p.L[l].N) atomicAdd(p.L[l].colsum + c, vec_s[i]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 2) tmem_dealloc2(tmem_base, 512);
+}
+
+}  // namespace papr
+
+extern "C" int papr_stack_bf16(const void *x, int K0, const papr_stack_layer *layers, int n_layers, int64_t rows, float slope,
+                               void *stream)
+{
+    using namespace papr;
+    if (!x || !layers || n_layers < 1 || n_layers > kStkMaxLayers) return PAPR_ERR_INVALID_ARGUMENT;
+    if (rows <= 0 || rows % kTileRows || K0 < 16 || K0 > 256 || K0 % 16) return PAPR_ERR_INVALID_ARGUMENT;
+    StackParams p;
+    p.x = (const uint8_t *)x; p.n_tiles = rows / kTileRows; p.n_layers = n_layers; p.kblk0 = (K0 + 63) / 64; p.slope = slope;
+    p.any_stash = 0;
+    int K = K0;
+    for (int l = 0; l < n_layers; ++l) {
+        const papr_stack_layer &h = layers[l];
+        const bool last = l == n_layers - 1;
+        if (!h.w_image || h.N < 32 || h.N > 256 || h.N % 32) return PAPR_ERR_INVALID_ARGUMENT;
+        if (!last && h.N != 256) return PAPR_ERR_INVALID_ARGUMENT;            // hidden activations fill one 128 x 256 slot
+        if (last && !h.out_blocked && !h.out_f32) return PAPR_ERR_INVALID_ARGUMENT;
+        if (h.out_f32 && (h.ld_f32 < h.N || h.ld_f32 % 4)) return PAPR_ERR_INVALID_ARGUMENT;
+        if (h.sign_bits_in && (h.bias || h.act || h.sign_bits_out)) return PAPR_ERR_INVALID_ARGUMENT;
+        if (h.sign_bits_out && !(h.bias && h.act)) return PAPR_ERR_INVALID_ARGUMENT;
+        if (h.act && !h.bias) return PAPR_ERR_INVALID_ARGUMENT;
+        if (h.colsum && h.bias) return PAPR_ERR_INVALID_ARGUMENT;
+        StackLayerDev &d = p.L[l];
+        d.w = (const uint8_t *)h.w_image; d.bias = h.bias; d.out_blocked = (uint8_t *)h.out_blocked; d.out_f32 = h.out_f32;
+        d.bits_out = h.sign_bits_out; d.bits_in = h.sign_bits_in; d.colsum = h.colsum; d.ld_f32 = h.ld_f32;
+        d.N = h.N; d.kblk = (K + 63) / 64; d.k_steps = K / 16; d.act = h.act;
+        if (h.out_blocked) p.any_stash = 1;
+        K = h.N;
+    }
+    const int fixed = 1024 + 2 * kSlotBytes + 512 + n_layers * 1024;
+    p.stages = (kStkMaxSmem - fixed) / kBlockBytes;
+    if (p.stages > 8) p.stages = 8;
+    if (p.stages < 3) return PAPR_ERR_INVALID_ARGUMENT;
+    const int smem = fixed + p.stages * kBlockBytes;
+    static bool attr_set = false;
+    if (!attr_set) {
+        PAPR_CUDA_TRY(cudaFuncSetAttribute(stack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStkMaxSmem));
+        attr_set = true;
+    }
+    const int64_t n_quads = (p.n_tiles + 3) / 4;
+    const int grid = (int)(2 * (n_quads < kNumSMs / 2 ? n_quads : kNumSMs / 2));
+    stack_kernel<<<grid, kStkThreads, smem, (cudaStream_t)stream>>>(p);
+    return check_launch();
+}

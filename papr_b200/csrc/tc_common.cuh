@@ -132,6 +132,80 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar)
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+
+// ------------------------------------------------------------------ cluster / 2-CTA (cta_group::2) variants
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t *bar, uint32_t cta)
+{
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)), "r"(cta) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAITC_%=:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONEC_%=;\n\t"
+        "bra WAITC_%=;\n\t"
+        "DONEC_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t *smem_dst, uint32_t ncols)
+{
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t addr, uint32_t ncols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+// M = 256 across the CTA pair: each CTA supplies its 128 rows of A and half (N/2 rows) of B; issued by the leader only
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrives on the barrier at this offset in BOTH CTAs of the pair once all prior MMAs of this thread completed
+__device__ __forceinline__ void umma2_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+
+// Epilogue flavours (compile-time so the per-element code carries no dead predicates)
+enum { EPI_PLAIN = 0, EPI_BIAS = 1, EPI_BIAS_ACT = 2, EPI_BIAS_ACT_BITS = 3, EPI_MASK = 4 };
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_math(uint32_t (&v)[32], const float *bias_s, int col0, float slope, uint32_t din,
+                                              uint32_t &dout)
+{
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        float t = __uint_as_float(v[j]);
+        if (EPI == EPI_BIAS || EPI == EPI_BIAS_ACT || EPI == EPI_BIAS_ACT_BITS) t += bias_s[col0 + j];
+        if (EPI == EPI_BIAS_ACT_BITS) dout |= (t > 0.f ? 1u : 0u) << j;
+        if (EPI == EPI_BIAS_ACT || EPI == EPI_BIAS_ACT_BITS) t = t > 0.f ? t : t * slope;
+        if (EPI == EPI_MASK) t = ((din >> j) & 1u) ? t : t * slope;
+        v[j] = __float_as_uint(t);
+    }
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi)
 {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

@@ -151,3 +151,29 @@ def wgrad_bf16(a, b, out, a_valid, b_valid, transpose_out=False):
          a_valid, b_valid, int(transpose_out), a.rows_pad, flops=2.0 * a.rows * a_valid * b_valid,
          nbytes=2.0 * a.rows_pad * (128 * ((a_valid + 127) // 128) + pad_cols(b_valid)))
     return out
+
+
+def stack_bf16(x, K0, layers, slope=0.0):
+    """Fused MLP stack (papr_stack_bf16).  `layers`: list of dicts with keys w_image, N and optionally bias, act,
+    out_blocked (Blocked), out_f32 (tensor), sign_bits_out (tensor), sign_bits_in (tensor), colsum (tensor)."""
+    import ctypes
+    from ._lib import StackLayer
+    arr = (StackLayer * len(layers))()
+    flops, nbytes = 0.0, 2.0 * x.rows_pad * x.cols_pad
+    K = K0
+    for i, l in enumerate(layers):
+        def ptr(key):
+            v = l.get(key)
+            return v.data_ptr() if v is not None else None
+        arr[i].w_image, arr[i].bias = ptr("w_image"), ptr("bias")
+        arr[i].out_blocked, arr[i].out_f32 = ptr("out_blocked"), ptr("out_f32")
+        arr[i].ld_f32 = l["out_f32"].stride(0) if l.get("out_f32") is not None else 0
+        arr[i].sign_bits_out, arr[i].sign_bits_in, arr[i].colsum = ptr("sign_bits_out"), ptr("sign_bits_in"), ptr("colsum")
+        arr[i].N, arr[i].act = int(l["N"]), int(bool(l.get("act")))
+        flops += 2.0 * x.rows * l["N"] * K
+        nbytes += x.rows_pad * ((2.0 * pad_cols(l["N"]) if l.get("out_blocked") is not None else 0)
+                                + (4.0 * l["N"] if l.get("out_f32") is not None else 0)
+                                + (8.0 * pad_cols(l["N"]) / 64 if (l.get("sign_bits_out") is not None or l.get("sign_bits_in") is not None) else 0))
+        K = l["N"]
+    call("papr_stack_bf16", x.data_ptr(), K0, ctypes.cast(arr, ctypes.c_void_p), len(layers), x.rows_pad, float(slope),
+         flops=flops, nbytes=nbytes)

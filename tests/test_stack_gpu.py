@@ -1,0 +1,91 @@
+"""GPU: the fused MLP-stack kernel (cta_group::2) must reproduce the per-layer tcgen05 kernel bit for bit
+(both round activations to bf16 between layers and accumulate in fp32)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _weights(dims, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    ws, bs = [], []
+    for k, n in zip(dims[:-1], dims[1:]):
+        ws.append(torch.randn(n, k, device="cuda", generator=g) * (2.0 / k) ** 0.5)
+        bs.append(torch.randn(n, device="cuda", generator=g) * 0.1)
+    return ws, bs
+
+
+@pytest.mark.parametrize("rows", [128, 512, 128 * 7, 128 * 601 + 5])
+@pytest.mark.parametrize("dims", [(117, 256, 256, 256, 256, 256), (142, 256, 256, 256, 256, 256, 256, 256, 32), (39, 256, 256)])
+def test_stack_forward_matches_per_layer(rows, dims):
+    from papr_b200 import ops
+    ws, bs = _weights(dims, rows + len(dims))
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = ops.Blocked.from_f32(torch.randn(rows, dims[0], device="cuda", generator=g))
+    n = len(ws)
+    K0 = (dims[0] + 15) // 16 * 16
+    # reference: one launch per layer
+    h, ref_out, ref_bits = x, [], []
+    for i, (w, b) in enumerate(zip(ws, bs)):
+        last = i == n - 1
+        N, K = (w.shape[0] + 31) // 32 * 32, (w.shape[1] + 15) // 16 * 16
+        yb, yf, bits = ops.linear_bf16(h, ops.pack_weight(w, N, K), N, K, bias=b, act=not last, slope=0.2,
+                                       out_blocked=True, out_f32=last, sign_bits_out=not last)
+        ref_out.append(yb); ref_bits.append(bits); h = yb
+    ref_f32 = yf
+    # fused
+    layers, outs, bits_l = [], [], []
+    for i, (w, b) in enumerate(zip(ws, bs)):
+        last = i == n - 1
+        N, K = (w.shape[0] + 31) // 32 * 32, (w.shape[1] + 15) // 16 * 16
+        ob = ops.Blocked(rows, N, "cuda")
+        bt = None if last else torch.zeros((x.rows_pad, ops.pad_cols(N) // 64), dtype=torch.int64, device="cuda")
+        outs.append(ob); bits_l.append(bt)
+        layers.append(dict(w_image=ops.pack_weight(w, N, K), N=N, bias=b, act=not last, out_blocked=ob, sign_bits_out=bt,
+                           out_f32=torch.zeros((x.rows_pad, N), device="cuda") if last else None))
+    ops.stack_bf16(x, K0, layers, slope=0.2)
+    torch.cuda.synchronize()
+    for i in range(n):
+        a, b = outs[i].to_f32(), ref_out[i].to_f32()
+        assert torch.equal(a, b), f"layer {i}: max diff {(a - b).abs().max().item()}"
+        if bits_l[i] is not None:
+            assert torch.equal(bits_l[i][:rows], ref_bits[i][:rows]), f"sign bits of layer {i}"
+    assert torch.equal(layers[-1]["out_f32"][:rows], ref_f32[:rows])
+
+
+@pytest.mark.parametrize("rows", [128 * 3, 128 * 300])
+def test_stack_dgrad_matches_per_layer(rows):
+    """Backward direction of an 8-layer value-like stack: masks from sign bits, bias-gradient column sums, dZ stash."""
+    from papr_b200 import ops
+    dims = (142, 256, 256, 256, 256, 256, 256, 256, 32)
+    ws, _ = _weights(dims, 7)
+    g = torch.Generator(device="cuda").manual_seed(2)
+    dz0 = ops.Blocked.from_f32(torch.randn(rows, 32, device="cuda", generator=g))
+    rows_pad = dz0.rows_pad
+    bits = [torch.randint(-2 ** 62, 2 ** 62, (rows_pad, 4), device="cuda", generator=g, dtype=torch.int64) for _ in range(7)]
+    # per-layer reference (layers 7..0)
+    dz, ref, ref_cs = dz0, [], []
+    for i in range(7, -1, -1):
+        w = ws[i]
+        Kd = (w.shape[0] + 15) // 16 * 16
+        Nd = 256 if i > 0 else 192
+        cs = torch.zeros(Nd, device="cuda") if i > 0 else None
+        dz, _, _ = ops.linear_bf16(dz, ops.pack_weight(w, Nd, Kd, transpose=True), Nd, Kd,
+                                   sign_bits_in=bits[i - 1] if i > 0 else None, slope=0.2, colsum=cs)
+        ref.append(dz); ref_cs.append(cs)
+    layers, outs, css = [], [], []
+    for i in range(7, -1, -1):
+        w = ws[i]
+        Kd = (w.shape[0] + 15) // 16 * 16
+        Nd = 256 if i > 0 else 192
+        ob = ops.Blocked(rows, Nd, "cuda")
+        cs = torch.zeros(Nd, device="cuda") if i > 0 else None
+        outs.append(ob); css.append(cs)
+        layers.append(dict(w_image=ops.pack_weight(w, Nd, Kd, transpose=True), N=Nd, out_blocked=ob,
+                           sign_bits_in=bits[i - 1] if i > 0 else None, colsum=cs))
+    ops.stack_bf16(dz0, 32, layers, slope=0.2)
+    torch.cuda.synchronize()
+    for j in range(8):
+        assert torch.equal(outs[j].to_f32(), ref[j].to_f32()), f"dgrad step {j}"
+        if css[j] is not None:
+            assert (css[j] - ref_cs[j]).abs().max().item() <= 1e-3 * max(1.0, ref_cs[j].abs().max().item())
