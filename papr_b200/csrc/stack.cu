@@ -12,7 +12,7 @@
 //               multicast so the "stage free" / "accumulator full" barriers fire in both CTAs
 //   warp 2      TMEM allocator (both CTAs, cta_group::2)
 //   warp 3      relay (peer CTA only): forwards "my TMA data landed" to the leader's barriers
-//   warps 4-11  epilogue
+//   warps 4-11  epilogue of slot 0, warps 12-19 epilogue of slot 1
 // Training-time by-products are written as they appear: each layer's output tile (the next layer's input, needed by
 // the weight-gradient kernel) straight from the shared-memory tile with a TMA bulk store, activation sign bits, and
 // per-column sums (bias gradients) in the dgrad direction.
@@ -20,7 +20,7 @@
 
 namespace papr {
 
-constexpr int kStkThreads = 384;
+constexpr int kStkThreads = 640;     // 4 control warps + 2 x 8 epilogue warps
 constexpr int kStkMaxLayers = 8;
 constexpr int kSlotBytes = 4 * kBlockBytes;      // one 128 x 256 bf16 tile
 constexpr int kStkMaxSmem = 232448;
@@ -44,16 +44,6 @@ struct StackParams {
     float slope;
     StackLayerDev L[kStkMaxLayers];
 };
-
-template <int EPI>
-__device__ __forceinline__ void stack_math(uint32_t (&v0)[32], uint32_t (&v1)[32], bool second, const float *bias, int col0,
-                                           float slope, uint64_t din, uint64_t &dout)
-{
-    uint32_t blo = 0, bhi = 0;
-    epilogue_math<EPI>(v0, bias, col0, slope, (uint32_t)din, blo);
-    if (second) epilogue_math<EPI>(v1, bias, col0 + 32, slope, (uint32_t)(din >> 32), bhi);
-    dout = ((uint64_t)bhi << 32) | blo;
-}
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kStkThreads, 1) stack_kernel(const __grid_constant__ StackParams p)
 {
@@ -170,117 +160,125 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kStkThreads, 1) stac
             }
         }
     } else if (warp >= 4) {
-        const int ew = warp - 4;
-        const int set = ew >> 2, quad = ew & 3;
+        // Two epilogue groups of eight warps: group `slot` drains only that slot's accumulator, so the two slots'
+        // epilogues overlap each other as well as the other slot's MMAs.
+        const int slot = (warp - 4) >> 3;
+        const int ew = (warp - 4) & 7;
+        const int set = ew >> 2, quad = ew & 3;               // quad == warp % 4: the TMEM lane quadrant this warp may read
         const int row = quad * 32 + lane;
-        const int sthr = quad * 32 + lane;                 // thread index within the set
+        const int sthr = quad * 32 + lane;                     // thread index within the set
         const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-        const int bar_id = 1 + set;
-        int64_t je[2] = {0, 0};
+        const int bar_id = 1 + slot * 2 + set;
+        uint8_t *slot_act = act + slot * kSlotBytes;
+        int64_t je = 0;
+        bool store_pending = false;
         for (int64_t q = cluster_id; q < n_quads; q += n_clusters) {
-            for (int l = 0; l < L; ++l) {
-                const StackLayerDev &Ld = p.L[l];
+            const int64_t tile = 4 * q + 2 * slot + rank;
+            const bool valid = tile < p.n_tiles;
+            const int64_t grow = tile * kTileRows + row;
+            for (int l = 0; l < L; ++l, ++je) {
+                const StackLayerDev Ld = p.L[l];
                 const int ngroups = (Ld.N + 63) >> 6;
                 const bool last = l == L - 1;
                 const bool to_act = !last || Ld.out_blocked != nullptr;
                 float *vec = vec_s + l * 256;
-                for (int s = 0; s < 2; ++s) {
-                    const int64_t tile = 4 * q + 2 * s + rank;
-                    const bool valid = tile < p.n_tiles;
-                    const int64_t grow = tile * kTileRows + row;
-                    uint64_t din[2] = {0, 0};
-                    if (Ld.bits_in && valid) {
-                        if (set < ngroups) din[0] = Ld.bits_in[grow * ngroups + set];
-                        if (set + 2 < ngroups) din[1] = Ld.bits_in[grow * ngroups + set + 2];
-                    }
-                    mbar_wait(&acc_full[s], (uint32_t)(je[s] & 1));
-                    tc_fence_after();
-                    for (int gi = 0; gi < 2; ++gi) {
-                        const int g = set + 2 * gi;
-                        if (g >= ngroups) break;
-                        const int col0 = g * 64;
-                        uint32_t v0[32], v1[32];
-                        const bool second = col0 + 32 < Ld.N;
-                        tmem_ld32(tmem_base + lane_base + s * 256 + col0, v0);
-                        if (second) tmem_ld32(tmem_base + lane_base + s * 256 + col0 + 32, v1);
-                        tmem_ld_wait();
-                        if (!second) {
+                uint64_t din[2] = {0, 0};
+                if (Ld.bits_in && valid) {
+                    if (set < ngroups) din[0] = Ld.bits_in[grow * ngroups + set];
+                    if (set + 2 < ngroups) din[1] = Ld.bits_in[grow * ngroups + set + 2];
+                }
+                mbar_wait(&acc_full[slot], (uint32_t)(je & 1));
+                tc_fence_after();
+                if (store_pending && to_act) {            // TMA stores issued from this slot one job ago must have read it
+                    if (sthr == 0) bulk_wait_read<0>();
+                    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+                    store_pending = false;
+                }
+                for (int gi = 0; gi < 2; ++gi) {
+                    const int g = set + 2 * gi;
+                    if (g >= ngroups) break;
+                    uint8_t *blk = slot_act + g * kBlockBytes;
+                    uint64_t dout = 0;
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) v1[j] = 0;
+                    for (int h = 0; h < 2; ++h) {
+                        const int col0 = g * 64 + h * 32;
+                        if (col0 >= Ld.N) {
+                            if (to_act) {
+#pragma unroll
+                                for (int c = 0; c < 4; ++c)
+                                    *reinterpret_cast<uint4 *>(blk + row * 128 + (((h * 4 + c) ^ (row & 7)) << 4)) = make_uint4(0, 0, 0, 0);
+                            }
+                            continue;
                         }
-                        uint64_t dout = 0;
-                        if (Ld.bits_in) stack_math<EPI_MASK>(v0, v1, second, vec, col0, p.slope, din[gi], dout);
-                        else if (Ld.bits_out) stack_math<EPI_BIAS_ACT_BITS>(v0, v1, second, vec, col0, p.slope, 0, dout);
-                        else if (Ld.act) stack_math<EPI_BIAS_ACT>(v0, v1, second, vec, col0, p.slope, 0, dout);
-                        else if (Ld.bias) stack_math<EPI_BIAS>(v0, v1, second, vec, col0, p.slope, 0, dout);
-                        if (Ld.bits_out && valid) Ld.bits_out[grow * ngroups + g] = dout;
+                        uint32_t v[32];
+                        tmem_ld32(tmem_base + lane_base + slot * 256 + col0, v);
+                        tmem_ld_wait();
+                        uint32_t bits = 0;
+                        const uint32_t dh = (uint32_t)(din[gi] >> (32 * h));
+                        if (Ld.bits_in) epilogue_math<EPI_MASK>(v, vec, col0, p.slope, dh, bits);
+                        else if (Ld.bits_out) epilogue_math<EPI_BIAS_ACT_BITS>(v, vec, col0, p.slope, 0, bits);
+                        else if (Ld.act) epilogue_math<EPI_BIAS_ACT>(v, vec, col0, p.slope, 0, bits);
+                        else if (Ld.bias) epilogue_math<EPI_BIAS>(v, vec, col0, p.slope, 0, bits);
+                        dout |= (uint64_t)bits << (32 * h);
                         if (Ld.out_f32 && valid) {
                             float4 *dst = reinterpret_cast<float4 *>(Ld.out_f32 + grow * Ld.ld_f32 + col0);
 #pragma unroll
                             for (int j = 0; j < 8; ++j)
-                                dst[j] = make_float4(__uint_as_float(v0[4 * j]), __uint_as_float(v0[4 * j + 1]), __uint_as_float(v0[4 * j + 2]), __uint_as_float(v0[4 * j + 3]));
-                            if (second) {
-#pragma unroll
-                                for (int j = 0; j < 8; ++j)
-                                    dst[8 + j] = make_float4(__uint_as_float(v1[4 * j]), __uint_as_float(v1[4 * j + 1]), __uint_as_float(v1[4 * j + 2]), __uint_as_float(v1[4 * j + 3]));
-                            }
+                                dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
                         }
                         if (to_act) {
-                            uint4 qv[8];
 #pragma unroll
                             for (int c = 0; c < 4; ++c) {
-                                qv[c] = make_uint4(pack_bf16(__uint_as_float(v0[8 * c]), __uint_as_float(v0[8 * c + 1])),
-                                                   pack_bf16(__uint_as_float(v0[8 * c + 2]), __uint_as_float(v0[8 * c + 3])),
-                                                   pack_bf16(__uint_as_float(v0[8 * c + 4]), __uint_as_float(v0[8 * c + 5])),
-                                                   pack_bf16(__uint_as_float(v0[8 * c + 6]), __uint_as_float(v0[8 * c + 7])));
-                                qv[4 + c] = make_uint4(pack_bf16(__uint_as_float(v1[8 * c]), __uint_as_float(v1[8 * c + 1])),
-                                                       pack_bf16(__uint_as_float(v1[8 * c + 2]), __uint_as_float(v1[8 * c + 3])),
-                                                       pack_bf16(__uint_as_float(v1[8 * c + 4]), __uint_as_float(v1[8 * c + 5])),
-                                                       pack_bf16(__uint_as_float(v1[8 * c + 6]), __uint_as_float(v1[8 * c + 7])));
-                            }
-                            uint8_t *blk = act + s * kSlotBytes + g * kBlockBytes;
-                            if (p.any_stash) {      // an earlier TMA store may still be reading this block
-                                if (sthr == 0) bulk_wait_read<0>();
-                                asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-                            }
-#pragma unroll
-                            for (int c = 0; c < 8; ++c)
-                                *reinterpret_cast<uint4 *>(blk + row * 128 + ((c ^ (row & 7)) << 4)) = qv[c];
-                            fence_proxy_async();
-                            if (Ld.out_blocked || Ld.colsum) {
-                                asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-                                if (sthr == 0 && valid && Ld.out_blocked) {
-                                    bulk_s2g(Ld.out_blocked + ((size_t)tile * ngroups + g) * kBlockBytes, blk, kBlockBytes);
-                                    bulk_commit();
-                                }
-                                if (Ld.colsum && valid) {
-                                    const int qq = sthr >> 5, ll = sthr & 31;
-                                    float s0 = 0.f, s1 = 0.f;
-#pragma unroll 8
-                                    for (int r = qq * 32; r < qq * 32 + 32; ++r) {
-                                        const uint32_t w2 = *reinterpret_cast<const uint32_t *>(blk + r * 128 + (((ll >> 2) ^ (r & 7)) << 4) + (ll & 3) * 4);
-                                        s0 += bf16_lo(w2); s1 += bf16_hi(w2);
-                                    }
-                                    atomicAdd(&vec[col0 + 2 * ll], s0);
-                                    atomicAdd(&vec[col0 + 2 * ll + 1], s1);
-                                }
+                                const uint4 qv = make_uint4(pack_bf16(__uint_as_float(v[8 * c]), __uint_as_float(v[8 * c + 1])),
+                                                            pack_bf16(__uint_as_float(v[8 * c + 2]), __uint_as_float(v[8 * c + 3])),
+                                                            pack_bf16(__uint_as_float(v[8 * c + 4]), __uint_as_float(v[8 * c + 5])),
+                                                            pack_bf16(__uint_as_float(v[8 * c + 6]), __uint_as_float(v[8 * c + 7])));
+                                *reinterpret_cast<uint4 *>(blk + row * 128 + (((h * 4 + c) ^ (row & 7)) << 4)) = qv;
                             }
                         }
                     }
-                    tc_fence_before();
-                    if (last && sthr == 0 && p.any_stash) bulk_wait_read<0>();   // the slot is about to be refilled by the producer
-                    __syncwarp();
-                    if (lane == 0) {
-                        if (last) mbar_arrive(&in_free[s]);
-                        if (rank == 0) mbar_arrive(&act_ready[s]); else mbar_arrive_remote(&act_ready[s], 0);
+                    if (Ld.bits_out && valid) Ld.bits_out[grow * ngroups + g] = dout;
+                }
+                if (to_act) fence_proxy_async();          // generic-proxy tile writes -> visible to tcgen05.mma / TMA store
+                if (to_act && (Ld.out_blocked || Ld.colsum)) {
+                    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+                    for (int gi = 0; gi < 2; ++gi) {
+                        const int g = set + 2 * gi;
+                        if (g >= ngroups) break;
+                        uint8_t *blk = slot_act + g * kBlockBytes;
+                        if (sthr == 0 && valid && Ld.out_blocked) {
+                            bulk_s2g(Ld.out_blocked + ((size_t)tile * ngroups + g) * kBlockBytes, blk, kBlockBytes);
+                            bulk_commit();
+                        }
+                        if (Ld.colsum && valid) {
+                            const int qq = sthr >> 5, ll = sthr & 31;
+                            float s0 = 0.f, s1 = 0.f;
+#pragma unroll 8
+                            for (int r = qq * 32; r < qq * 32 + 32; ++r) {
+                                const uint32_t w2 = *reinterpret_cast<const uint32_t *>(blk + r * 128 + (((ll >> 2) ^ (r & 7)) << 4) + (ll & 3) * 4);
+                                s0 += bf16_lo(w2); s1 += bf16_hi(w2);
+                            }
+                            atomicAdd(&vec[g * 64 + 2 * ll], s0);
+                            atomicAdd(&vec[g * 64 + 2 * ll + 1], s1);
+                        }
                     }
-                    ++je[s];
+                    if (Ld.out_blocked) store_pending = true;
+                }
+                tc_fence_before();
+                if (last && store_pending) {               // the slot is about to be refilled by the producer
+                    if (sthr == 0) bulk_wait_read<0>();
+                    store_pending = false;
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    if (last) mbar_arrive(&in_free[slot]);
+                    if (rank == 0) mbar_arrive(&act_ready[slot]); else mbar_arrive_remote(&act_ready[slot], 0);
                 }
             }
         }
         if (sthr == 0) bulk_wait<0>();
-        asm volatile("bar.sync 3, 256;" ::: "memory");
-        for (int i = threadIdx.x - 128; i < L * 256; i += 256) {
+        asm volatile("bar.sync 5, 512;" ::: "memory");
+        for (int i = threadIdx.x - 128; i < L * 256; i += 512) {
             const int l = i >> 8, c = i & 255;
             if (p.L[l].colsum && c < p.L[l].N) atomicAdd(p.L[l].colsum + c, vec_s[i]);
         }
