@@ -166,6 +166,10 @@ typedef struct papr_stack_layer {
     float *colsum;                /* [N] accumulated, or NULL */
     int32_t N;
     int32_t act;                  /* 0 none, 1 relu/leakyrelu(slope) */
+    int32_t w_replicas;           /* >= 1: identical copies of the image, w_replica_stride bytes apart; CTA pairs read different
+                                     copies so that 148 SMs streaming the same chunk do not hammer the same L2 slices */
+    int32_t _pad;
+    int64_t w_replica_stride;
 } papr_stack_layer;
 
 int papr_stack_bf16(const void *x, int K0, const papr_stack_layer *layers, int n_layers, int64_t rows, float slope,

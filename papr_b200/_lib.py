@@ -36,7 +36,7 @@ class StackLayer(ctypes.Structure):
     """papr_stack_layer of include/papr_b200.h"""
     _fields_ = [("w_image", _ptr), ("bias", _ptr), ("out_blocked", _ptr), ("out_f32", _ptr), ("ld_f32", _i64),
                 ("sign_bits_out", _ptr), ("sign_bits_in", _ptr), ("colsum", _ptr), ("N", ctypes.c_int32),
-                ("act", ctypes.c_int32)]
+                ("act", ctypes.c_int32), ("w_replicas", ctypes.c_int32), ("_pad", ctypes.c_int32), ("w_replica_stride", _i64)]
 
 
 class PaprError(RuntimeError):

@@ -193,7 +193,7 @@ def _stack_forward_fused(x, weights, biases, slope, n_in0, save, last_f32):
         N = (n_out + 31) // 32 * 32
         last = i == n_layers - 1
         act = (not last) and slope is not None
-        spec = dict(w_image=ops.pack_weight(w, N, K), N=N, bias=_pad_bias(b, N), act=act)
+        spec = dict(w_image=ops.pack_weight(w, N, K, replicas=ops.WEIGHT_REPLICAS), N=N, bias=_pad_bias(b, N), act=act)
         bits = None
         if save and act:
             bits = torch.empty((x.rows_pad, ops.pad_cols(N) // 64), dtype=torch.int64, device=dev)
@@ -262,7 +262,7 @@ def _stack_backward(dz, inputs, bits_list, weights, slope, g_bias_last, in_valid
             Kd = (n_out + 15) // 16 * 16
             Nd = n_in if i > 0 else in_pad
             ob = ops.Blocked(dz.rows, Nd, dev)
-            spec = dict(w_image=ops.pack_weight(w, Nd, Kd, transpose=True), N=Nd, out_blocked=ob)
+            spec = dict(w_image=ops.pack_weight(w, Nd, Kd, transpose=True, replicas=ops.WEIGHT_REPLICAS), N=Nd, out_blocked=ob)
             if i > 0:
                 gbs[i - 1] = torch.zeros((weights[i - 1].shape[0],), device=dev)
                 spec["colsum"] = gbs[i - 1]

@@ -12,11 +12,12 @@
 //               multicast so the "stage free" / "accumulator full" barriers fire in both CTAs
 //   warp 2      TMEM allocator (both CTAs, cta_group::2)
 //   warp 3      relay (peer CTA only): forwards "my TMA data landed" to the leader's barriers
-//   warps 4-11  epilogue of slot 0, warps 12-19 epilogue of slot 1
+//   warps 4-19  epilogue: warp (g, quad) drains 64-column group g of the current job for TMEM lane quadrant quad
 // Training-time by-products are written as they appear: each layer's output tile (the next layer's input, needed by
 // the weight-gradient kernel) straight from the shared-memory tile with a TMA bulk store, activation sign bits, and
 // per-column sums (bias gradients) in the dgrad direction.
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 namespace papr {
 
@@ -24,6 +25,7 @@ constexpr int kStkThreads = 640;     // 4 control warps + 2 x 8 epilogue warps
 constexpr int kStkMaxLayers = 8;
 constexpr int kSlotBytes = 4 * kBlockBytes;      // one 128 x 256 bf16 tile
 constexpr int kStkMaxSmem = 232448;
+constexpr int kStageBytes = 2 * kBlockBytes;    // weight-ring stage: K = 128 per barrier round trip (8 MMAs)
 
 struct StackLayerDev {
     const uint8_t *w;          // weight image [kblk][N rows][128 B]
@@ -34,7 +36,8 @@ struct StackLayerDev {
     const uint64_t *bits_in;   // activation-derivative mask bits (dgrad), or null
     float *colsum;             // [N] += column sums of the bf16 output, or null
     int64_t ld_f32;
-    int N, kblk, k_steps, act;
+    int64_t w_rep_stride;      // byte distance between identical copies of the weight image
+    int N, kblk, k_steps, act, w_reps;
 };
 
 struct StackParams {
@@ -42,6 +45,7 @@ struct StackParams {
     int64_t n_tiles;
     int n_layers, kblk0, stages, any_stash;
     float slope;
+    long long *trace;          // debug: per-job clock stamps of cluster 0 (null in production)
     StackLayerDev L[kStkMaxLayers];
 };
 
@@ -50,8 +54,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kStkThreads, 1) stac
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t *act = smem;                                   // 2 slots x 64 KB
-    uint8_t *ring = act + 2 * kSlotBytes;                  // stages x 16 KB (this CTA's half of a weight chunk)
-    uint64_t *bars = (uint64_t *)(ring + p.stages * kBlockBytes);
+    uint8_t *ring = act + 2 * kSlotBytes;                  // stages x 32 KB (this CTA's half of two 64-wide weight chunks)
+    uint64_t *bars = (uint64_t *)(ring + p.stages * kStageBytes);
     uint64_t *w_full = bars, *w_empty = bars + 8, *pw_full = bars + 16;
     uint64_t *in_full = bars + 24, *pin_full = bars + 26, *in_free = bars + 28, *act_ready = bars + 30, *acc_full = bars + 32;
     uint32_t *tmem_slot = (uint32_t *)(bars + 34);
@@ -66,8 +70,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kStkThreads, 1) stac
     if (threadIdx.x == 0) {
         for (int i = 0; i < 8; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); mbar_init(&pw_full[i], 1); }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&in_full[i], 1); mbar_init(&pin_full[i], 1); mbar_init(&in_free[i], 8);
-            mbar_init(&act_ready[i], 16); mbar_init(&acc_full[i], 1);
+            mbar_init(&in_full[i], 1); mbar_init(&pin_full[i], 1); mbar_init(&in_free[i], 16);
+            mbar_init(&act_ready[i], 32); mbar_init(&acc_full[i], 1);
         }
         fence_barrier_init();
     }
@@ -99,10 +103,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kStkThreads, 1) stac
                                 bulk_g2s(act + s * kSlotBytes + kb * kBlockBytes, p.x + ((size_t)tile * p.kblk0 + kb) * kBlockBytes,
                                          kBlockBytes, &in_full[s]);
                         }
-                        for (int kc = 0; kc < Ld.kblk; ++kc) {
+                        const uint8_t *wsrc = Ld.w + (size_t)(cluster_id % Ld.w_reps) * Ld.w_rep_stride + (size_t)rank * chunk_bytes;
+                        for (int kc = 0; kc < Ld.kblk; kc += 2) {
+                            const int nc = min(2, Ld.kblk - kc);
                             mbar_wait(&w_empty[st], ph ^ 1);
-                            mbar_arrive_expect_tx(&w_full[st], chunk_bytes);
-                            bulk_g2s(ring + st * kBlockBytes, Ld.w + (size_t)kc * Ld.N * 128 + (size_t)rank * chunk_bytes, chunk_bytes, &w_full[st]);
+                            mbar_arrive_expect_tx(&w_full[st], chunk_bytes * nc);
+                            for (int c = 0; c < nc; ++c)
+                                bulk_g2s(ring + st * kStageBytes + c * kBlockBytes, wsrc + (size_t)(kc + c) * Ld.N * 128, chunk_bytes, &w_full[st]);
                             if (++st == p.stages) { st = 0; ph ^= 1; }
                         }
                     }
@@ -116,7 +123,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kStkThreads, 1) stac
                 for (int l = 0; l < L; ++l) {
                     for (int s = 0; s < 2; ++s) {
                         if (l == 0) { mbar_wait(&in_full[s], (uint32_t)(qi & 1)); mbar_arrive_remote(&pin_full[s], 0); }
-                        for (int kc = 0; kc < p.L[l].kblk; ++kc) {
+                        for (int kc = 0; kc < p.L[l].kblk; kc += 2) {
                             mbar_wait(&w_full[st], ph);
                             mbar_arrive_remote(&pw_full[st], 0);
                             if (++st == p.stages) { st = 0; ph ^= 1; }
@@ -140,139 +147,149 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kStkThreads, 1) stac
                         }
                         if (js[s] > 0) mbar_wait_cluster(&act_ready[s], (uint32_t)((js[s] - 1) & 1));
                         tc_fence_after();
+                        if (p.trace && blockIdx.x == 0 && qi < 4) p.trace[((qi * 16 + l) * 2 + s) * 8 + 0] = clock64();
                         const uint32_t d = tmem_base + s * 256;
-                        for (int kc = 0; kc < Ld.kblk; ++kc) {
+                        const uint64_t a_desc0 = umma_desc(smem_u32(act + s * kSlotBytes), 16, 1024);
+                        uint32_t acc = 0;
+                        for (int kc = 0; kc < Ld.kblk; kc += 2) {
                             mbar_wait(&w_full[st], ph);
                             mbar_wait_cluster(&pw_full[st], ph);
                             tc_fence_after();
-                            const uint32_t a0 = smem_u32(act + s * kSlotBytes + kc * kBlockBytes);
-                            const uint32_t b0 = smem_u32(ring + st * kBlockBytes);
-                            const int nk = min(4, Ld.k_steps - 4 * kc);
-                            for (int k = 0; k < nk; ++k)
-                                umma2_bf16(d, umma_desc(a0 + k * 32, 16, 1024), umma_desc(b0 + k * 32, 16, 1024), idesc, (uint32_t)((kc | k) != 0));
+                            const int nc = min(2, Ld.kblk - kc);
+                            // descriptors are built once per 64-wide block; a K step of 16 bf16 = 32 B = +2 in the address field
+                            uint64_t ad = a_desc0 + (uint64_t)(kc * (kBlockBytes >> 4));
+                            uint64_t bd = umma_desc(smem_u32(ring + st * kStageBytes), 16, 1024);
+                            for (int c = 0; c < nc; ++c) {
+                                const int nk = min(4, Ld.k_steps - 4 * (kc + c));
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    if (k < nk) { umma2_bf16(d, ad + 2 * k, bd + 2 * k, idesc, acc); acc = 1; }
+                                }
+                                ad += kBlockBytes >> 4;
+                                bd += kBlockBytes >> 4;
+                            }
                             umma2_commit(&w_empty[st]);
                             if (++st == p.stages) { st = 0; ph ^= 1; }
                         }
                         umma2_commit(&acc_full[s]);
+                        if (p.trace && blockIdx.x == 0 && qi < 4) p.trace[((qi * 16 + l) * 2 + s) * 8 + 1] = clock64();
                         ++js[s];
                     }
                 }
             }
         }
     } else if (warp >= 4) {
-        // Two epilogue groups of eight warps: group `slot` drains only that slot's accumulator, so the two slots'
-        // epilogues overlap each other as well as the other slot's MMAs.
-        const int slot = (warp - 4) >> 3;
-        const int ew = (warp - 4) & 7;
-        const int set = ew >> 2, quad = ew & 3;               // quad == warp % 4: the TMEM lane quadrant this warp may read
+        // Sixteen epilogue warps drain the jobs in issue order; warp (g, quad) owns 64-column group g of the tile for
+        // the TMEM lane quadrant quad (== warp % 4), so one job is four independent 128-thread groups.
+        const int ew = warp - 4;
+        const int g = ew >> 2, quad = ew & 3;
         const int row = quad * 32 + lane;
-        const int sthr = quad * 32 + lane;                     // thread index within the set
+        const int sthr = quad * 32 + lane;                     // thread index within the group
         const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-        const int bar_id = 1 + slot * 2 + set;
-        uint8_t *slot_act = act + slot * kSlotBytes;
-        int64_t je = 0;
-        bool store_pending = false;
+        const int bar_id = 1 + g;
+        int64_t je[2] = {0, 0};
+        bool store_pending[2] = {false, false};
         for (int64_t q = cluster_id; q < n_quads; q += n_clusters) {
-            const int64_t tile = 4 * q + 2 * slot + rank;
-            const bool valid = tile < p.n_tiles;
-            const int64_t grow = tile * kTileRows + row;
-            for (int l = 0; l < L; ++l, ++je) {
+            const int64_t tq = (q - cluster_id) / n_clusters;
+            for (int l = 0; l < L; ++l) {
                 const StackLayerDev Ld = p.L[l];
                 const int ngroups = (Ld.N + 63) >> 6;
                 const bool last = l == L - 1;
                 const bool to_act = !last || Ld.out_blocked != nullptr;
+                const bool mine = g < ngroups;
                 float *vec = vec_s + l * 256;
-                uint64_t din[2] = {0, 0};
-                if (Ld.bits_in && valid) {
-                    if (set < ngroups) din[0] = Ld.bits_in[grow * ngroups + set];
-                    if (set + 2 < ngroups) din[1] = Ld.bits_in[grow * ngroups + set + 2];
-                }
-                mbar_wait(&acc_full[slot], (uint32_t)(je & 1));
-                tc_fence_after();
-                if (store_pending && to_act) {            // TMA stores issued from this slot one job ago must have read it
-                    if (sthr == 0) bulk_wait_read<0>();
-                    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-                    store_pending = false;
-                }
-                for (int gi = 0; gi < 2; ++gi) {
-                    const int g = set + 2 * gi;
-                    if (g >= ngroups) break;
-                    uint8_t *blk = slot_act + g * kBlockBytes;
-                    uint64_t dout = 0;
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int col0 = g * 64 + h * 32;
-                        if (col0 >= Ld.N) {
+                for (int s = 0; s < 2; ++s) {
+                    const int64_t tile = 4 * q + 2 * s + rank;
+                    const bool valid = tile < p.n_tiles;
+                    const int64_t grow = tile * kTileRows + row;
+                    const bool tr = p.trace && blockIdx.x < 2 && tq < 4 && ew == 0 && lane == 0;
+                    uint64_t din = 0;
+                    if (Ld.bits_in && valid && mine) din = Ld.bits_in[grow * ngroups + g];
+                    mbar_wait(&acc_full[s], (uint32_t)(je[s] & 1));
+                    tc_fence_after();
+                    if (tr) p.trace[((tq * 16 + l) * 2 + s) * 8 + 2 + 3 * rank] = clock64();
+                    if (mine) {
+                        uint8_t *blk = act + s * kSlotBytes + g * kBlockBytes;
+                        if (store_pending[s] && to_act) {      // the TMA store issued from this block one job ago must have read it
+                            if (sthr == 0) bulk_wait_read<0>();
+                            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+                            store_pending[s] = false;
+                        }
+                        uint64_t dout = 0;
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int col0 = g * 64 + h * 32;
+                            if (col0 >= Ld.N) {
+                                if (to_act) {
+#pragma unroll
+                                    for (int c = 0; c < 4; ++c)
+                                        *reinterpret_cast<uint4 *>(blk + row * 128 + (((h * 4 + c) ^ (row & 7)) << 4)) = make_uint4(0, 0, 0, 0);
+                                }
+                                continue;
+                            }
+                            uint32_t v[32];
+                            tmem_ld32(tmem_base + lane_base + s * 256 + col0, v);
+                            tmem_ld_wait();
+                            uint32_t bits = 0;
+                            const uint32_t dh = (uint32_t)(din >> (32 * h));
+                            if (Ld.bits_in) epilogue_math<EPI_MASK>(v, vec, col0, p.slope, dh, bits);
+                            else if (Ld.bits_out) epilogue_math<EPI_BIAS_ACT_BITS>(v, vec, col0, p.slope, 0, bits);
+                            else if (Ld.act) epilogue_math<EPI_BIAS_ACT>(v, vec, col0, p.slope, 0, bits);
+                            else if (Ld.bias) epilogue_math<EPI_BIAS>(v, vec, col0, p.slope, 0, bits);
+                            dout |= (uint64_t)bits << (32 * h);
+                            if (Ld.out_f32 && valid) {
+                                float4 *dst = reinterpret_cast<float4 *>(Ld.out_f32 + grow * Ld.ld_f32 + col0);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j)
+                                    dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                            }
                             if (to_act) {
 #pragma unroll
-                                for (int c = 0; c < 4; ++c)
-                                    *reinterpret_cast<uint4 *>(blk + row * 128 + (((h * 4 + c) ^ (row & 7)) << 4)) = make_uint4(0, 0, 0, 0);
-                            }
-                            continue;
-                        }
-                        uint32_t v[32];
-                        tmem_ld32(tmem_base + lane_base + slot * 256 + col0, v);
-                        tmem_ld_wait();
-                        uint32_t bits = 0;
-                        const uint32_t dh = (uint32_t)(din[gi] >> (32 * h));
-                        if (Ld.bits_in) epilogue_math<EPI_MASK>(v, vec, col0, p.slope, dh, bits);
-                        else if (Ld.bits_out) epilogue_math<EPI_BIAS_ACT_BITS>(v, vec, col0, p.slope, 0, bits);
-                        else if (Ld.act) epilogue_math<EPI_BIAS_ACT>(v, vec, col0, p.slope, 0, bits);
-                        else if (Ld.bias) epilogue_math<EPI_BIAS>(v, vec, col0, p.slope, 0, bits);
-                        dout |= (uint64_t)bits << (32 * h);
-                        if (Ld.out_f32 && valid) {
-                            float4 *dst = reinterpret_cast<float4 *>(Ld.out_f32 + grow * Ld.ld_f32 + col0);
-#pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-                        }
-                        if (to_act) {
-#pragma unroll
-                            for (int c = 0; c < 4; ++c) {
-                                const uint4 qv = make_uint4(pack_bf16(__uint_as_float(v[8 * c]), __uint_as_float(v[8 * c + 1])),
-                                                            pack_bf16(__uint_as_float(v[8 * c + 2]), __uint_as_float(v[8 * c + 3])),
-                                                            pack_bf16(__uint_as_float(v[8 * c + 4]), __uint_as_float(v[8 * c + 5])),
-                                                            pack_bf16(__uint_as_float(v[8 * c + 6]), __uint_as_float(v[8 * c + 7])));
-                                *reinterpret_cast<uint4 *>(blk + row * 128 + (((h * 4 + c) ^ (row & 7)) << 4)) = qv;
+                                for (int c = 0; c < 4; ++c) {
+                                    const uint4 qv = make_uint4(pack_bf16(__uint_as_float(v[8 * c]), __uint_as_float(v[8 * c + 1])),
+                                                                pack_bf16(__uint_as_float(v[8 * c + 2]), __uint_as_float(v[8 * c + 3])),
+                                                                pack_bf16(__uint_as_float(v[8 * c + 4]), __uint_as_float(v[8 * c + 5])),
+                                                                pack_bf16(__uint_as_float(v[8 * c + 6]), __uint_as_float(v[8 * c + 7])));
+                                    *reinterpret_cast<uint4 *>(blk + row * 128 + (((h * 4 + c) ^ (row & 7)) << 4)) = qv;
+                                }
                             }
                         }
-                    }
-                    if (Ld.bits_out && valid) Ld.bits_out[grow * ngroups + g] = dout;
-                }
-                if (to_act) fence_proxy_async();          // generic-proxy tile writes -> visible to tcgen05.mma / TMA store
-                if (to_act && (Ld.out_blocked || Ld.colsum)) {
-                    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-                    for (int gi = 0; gi < 2; ++gi) {
-                        const int g = set + 2 * gi;
-                        if (g >= ngroups) break;
-                        uint8_t *blk = slot_act + g * kBlockBytes;
-                        if (sthr == 0 && valid && Ld.out_blocked) {
-                            bulk_s2g(Ld.out_blocked + ((size_t)tile * ngroups + g) * kBlockBytes, blk, kBlockBytes);
-                            bulk_commit();
-                        }
-                        if (Ld.colsum && valid) {
-                            const int qq = sthr >> 5, ll = sthr & 31;
-                            float s0 = 0.f, s1 = 0.f;
+                        if (Ld.bits_out && valid) Ld.bits_out[grow * ngroups + g] = dout;
+                        if (to_act) fence_proxy_async();      // generic-proxy tile writes -> visible to tcgen05.mma / TMA store
+                        if (to_act && (Ld.out_blocked || Ld.colsum)) {
+                            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+                            if (sthr == 0 && valid && Ld.out_blocked) {
+                                bulk_s2g(Ld.out_blocked + ((size_t)tile * ngroups + g) * kBlockBytes, blk, kBlockBytes);
+                                bulk_commit();
+                            }
+                            if (Ld.colsum && valid) {
+                                const int qq = sthr >> 5, ll = sthr & 31;
+                                float s0 = 0.f, s1 = 0.f;
 #pragma unroll 8
-                            for (int r = qq * 32; r < qq * 32 + 32; ++r) {
-                                const uint32_t w2 = *reinterpret_cast<const uint32_t *>(blk + r * 128 + (((ll >> 2) ^ (r & 7)) << 4) + (ll & 3) * 4);
-                                s0 += bf16_lo(w2); s1 += bf16_hi(w2);
+                                for (int r = qq * 32; r < qq * 32 + 32; ++r) {
+                                    const uint32_t w2 = *reinterpret_cast<const uint32_t *>(blk + r * 128 + (((ll >> 2) ^ (r & 7)) << 4) + (ll & 3) * 4);
+                                    s0 += bf16_lo(w2); s1 += bf16_hi(w2);
+                                }
+                                atomicAdd(&vec[g * 64 + 2 * ll], s0);
+                                atomicAdd(&vec[g * 64 + 2 * ll + 1], s1);
                             }
-                            atomicAdd(&vec[g * 64 + 2 * ll], s0);
-                            atomicAdd(&vec[g * 64 + 2 * ll + 1], s1);
+                            if (Ld.out_blocked) store_pending[s] = true;
                         }
                     }
-                    if (Ld.out_blocked) store_pending = true;
-                }
-                tc_fence_before();
-                if (last && store_pending) {               // the slot is about to be refilled by the producer
-                    if (sthr == 0) bulk_wait_read<0>();
-                    store_pending = false;
-                }
-                __syncwarp();
-                if (lane == 0) {
-                    if (last) mbar_arrive(&in_free[slot]);
-                    if (rank == 0) mbar_arrive(&act_ready[slot]); else mbar_arrive_remote(&act_ready[slot], 0);
+                    if (tr) p.trace[((tq * 16 + l) * 2 + s) * 8 + 3 + 3 * rank] = clock64();
+                    tc_fence_before();
+                    if (last && store_pending[s]) {            // the slot is about to be refilled by the producer
+                        if (sthr == 0) bulk_wait_read<0>();
+                        store_pending[s] = false;
+                    }
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (last) mbar_arrive(&in_free[s]);
+                        if (rank == 0) mbar_arrive(&act_ready[s]); else mbar_arrive_remote(&act_ready[s], 0);
+                    }
+                    if (tr) p.trace[((tq * 16 + l) * 2 + s) * 8 + 4 + 3 * rank] = clock64();
+                    ++je[s];
                 }
             }
         }
@@ -292,6 +309,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kStkThreads, 1) stac
 
 }  // namespace papr
 
+static long long *g_stack_trace = nullptr;
+// debug hook (not part of the public header): device buffer receiving clock stamps of cluster 0
+extern "C" void papr_debug_stack_trace(long long *buf) { g_stack_trace = buf; }
+
 extern "C" int papr_stack_bf16(const void *x, int K0, const papr_stack_layer *layers, int n_layers, int64_t rows, float slope,
                                void *stream)
 {
@@ -301,6 +322,7 @@ extern "C" int papr_stack_bf16(const void *x, int K0, const papr_stack_layer *la
     StackParams p;
     p.x = (const uint8_t *)x; p.n_tiles = rows / kTileRows; p.n_layers = n_layers; p.kblk0 = (K0 + 63) / 64; p.slope = slope;
     p.any_stash = 0;
+    p.trace = g_stack_trace;
     int K = K0;
     for (int l = 0; l < n_layers; ++l) {
         const papr_stack_layer &h = layers[l];
@@ -317,14 +339,15 @@ extern "C" int papr_stack_bf16(const void *x, int K0, const papr_stack_layer *la
         d.w = (const uint8_t *)h.w_image; d.bias = h.bias; d.out_blocked = (uint8_t *)h.out_blocked; d.out_f32 = h.out_f32;
         d.bits_out = h.sign_bits_out; d.bits_in = h.sign_bits_in; d.colsum = h.colsum; d.ld_f32 = h.ld_f32;
         d.N = h.N; d.kblk = (K + 63) / 64; d.k_steps = K / 16; d.act = h.act;
+        d.w_reps = h.w_replicas > 1 ? h.w_replicas : 1; d.w_rep_stride = h.w_replica_stride;
         if (h.out_blocked) p.any_stash = 1;
         K = h.N;
     }
     const int fixed = 1024 + 2 * kSlotBytes + 512 + n_layers * 1024;
-    p.stages = (kStkMaxSmem - fixed) / kBlockBytes;
+    p.stages = (kStkMaxSmem - fixed) / kStageBytes;
     if (p.stages > 8) p.stages = 8;
-    if (p.stages < 3) return PAPR_ERR_INVALID_ARGUMENT;
-    const int smem = fixed + p.stages * kBlockBytes;
+    if (p.stages < 2) return PAPR_ERR_INVALID_ARGUMENT;
+    const int smem = fixed + p.stages * kStageBytes;
     static bool attr_set = false;
     if (!attr_set) {
         PAPR_CUDA_TRY(cudaFuncSetAttribute(stack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStkMaxSmem));

@@ -191,19 +191,46 @@ __device__ __forceinline__ void umma2_commit(uint64_t *bar)
 // Epilogue flavours (compile-time so the per-element code carries no dead predicates)
 enum { EPI_PLAIN = 0, EPI_BIAS = 1, EPI_BIAS_ACT = 2, EPI_BIAS_ACT_BITS = 3, EPI_MASK = 4 };
 
+__device__ __forceinline__ float4 lds_f4(uint32_t saddr)
+{
+    float4 r;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(saddr));
+    return r;
+}
+
+// 32 accumulator columns of one row: bias (from shared memory at bias_saddr), activation, sign bits / derivative mask.
+// RELU: negative slope is exactly 0 (max(t,0)); otherwise leaky with 0 <= slope <= 1 (max(t, slope*t)).
+template <int EPI, bool RELU>
+__device__ __forceinline__ void epilogue_math32(uint32_t (&v)[32], uint32_t bias_saddr, float slope, uint32_t din, uint32_t &dout)
+{
+    constexpr bool kBias = EPI == EPI_BIAS || EPI == EPI_BIAS_ACT || EPI == EPI_BIAS_ACT_BITS;
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4) {
+        float b[4] = {0.f, 0.f, 0.f, 0.f};
+        if (kBias) { const float4 q = lds_f4(bias_saddr + j4 * 16); b[0] = q.x; b[1] = q.y; b[2] = q.z; b[3] = q.w; }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int j = j4 * 4 + e;
+            float t = __uint_as_float(v[j]);
+            if (kBias) t += b[e];
+            if (EPI == EPI_BIAS_ACT_BITS) { if (t > 0.f) dout |= 1u << j; }
+            if (EPI == EPI_BIAS_ACT || EPI == EPI_BIAS_ACT_BITS) t = RELU ? fmaxf(t, 0.f) : fmaxf(t, t * slope);
+            if (EPI == EPI_MASK) {
+                if (RELU) t = __uint_as_float(__float_as_uint(t) & (uint32_t)((int32_t)(din << (31 - j)) >> 31));
+                else t = ((din >> j) & 1u) ? t : t * slope;
+            }
+            v[j] = __float_as_uint(t);
+        }
+    }
+}
+
 template <int EPI>
 __device__ __forceinline__ void epilogue_math(uint32_t (&v)[32], const float *bias_s, int col0, float slope, uint32_t din,
                                               uint32_t &dout)
 {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-        float t = __uint_as_float(v[j]);
-        if (EPI == EPI_BIAS || EPI == EPI_BIAS_ACT || EPI == EPI_BIAS_ACT_BITS) t += bias_s[col0 + j];
-        if (EPI == EPI_BIAS_ACT_BITS) dout |= (t > 0.f ? 1u : 0u) << j;
-        if (EPI == EPI_BIAS_ACT || EPI == EPI_BIAS_ACT_BITS) t = t > 0.f ? t : t * slope;
-        if (EPI == EPI_MASK) t = ((din >> j) & 1u) ? t : t * slope;
-        v[j] = __float_as_uint(t);
-    }
+    const uint32_t ba = smem_u32(bias_s + col0);
+    if (slope == 0.f) epilogue_math32<EPI, true>(v, ba, slope, din, dout);
+    else epilogue_math32<EPI, false>(v, ba, slope, din, dout);
 }
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi)

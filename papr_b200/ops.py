@@ -112,8 +112,15 @@ class Blocked:
         return out
 
 
-def pack_weight(w, N, K, transpose=False, scale=1.0):
-    """bf16 weight image (uint8 tensor) for linear_bf16 from a torch Linear weight (out,in)."""
+WEIGHT_REPLICAS = 8      # copies of every weight image handed to the fused stack kernel (see papr_stack_layer)
+
+
+def pack_weight(w, N, K, transpose=False, scale=1.0, replicas=1):
+    """bf16 weight image (uint8 tensor) for linear_bf16 from a torch Linear weight (out,in); `replicas` > 1 returns
+    that many identical copies back to back (shape (replicas, bytes))."""
+    if replicas > 1:
+        one = pack_weight(w, N, K, transpose, scale)
+        return one.unsqueeze(0).repeat(replicas, 1)
     w = _f32c(w)
     img = torch.empty(((K + 63) // 64) * N * 128, dtype=torch.uint8, device=w.device)
     call("papr_pack_weight", w.data_ptr(), w.stride(0), w.shape[0], w.shape[1], int(transpose), N, K, float(scale),
@@ -170,6 +177,9 @@ def stack_bf16(x, K0, layers, slope=0.0):
         arr[i].ld_f32 = l["out_f32"].stride(0) if l.get("out_f32") is not None else 0
         arr[i].sign_bits_out, arr[i].sign_bits_in, arr[i].colsum = ptr("sign_bits_out"), ptr("sign_bits_in"), ptr("colsum")
         arr[i].N, arr[i].act = int(l["N"]), int(bool(l.get("act")))
+        img = l["w_image"]
+        arr[i].w_replicas = img.shape[0] if img.dim() == 2 else 1
+        arr[i].w_replica_stride = img.stride(0) if img.dim() == 2 else 0
         flops += 2.0 * x.rows * l["N"] * K
         nbytes += x.rows_pad * ((2.0 * pad_cols(l["N"]) if l.get("out_blocked") is not None else 0)
                                 + (4.0 * l["N"] if l.get("out_f32") is not None else 0)
