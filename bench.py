@@ -247,19 +247,34 @@ def main():
         return
 
     peaks = load_peaks()
-    lin = kern.get("papr_linear_bf16", dict(launches=0, ms=1e-9, flops=0, bytes=0))
-    wg = kern.get("papr_wgrad_bf16", dict(launches=0, ms=1e-9, flops=0, bytes=0))
-    sel = kern.get("papr_select_topk", dict(launches=0, ms=1e-9, flops=0, bytes=0))
-    tc_ms = lin["ms"] + wg["ms"]
-    tc_flops = lin["flops"] + wg["flops"]
-    achieved = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
+    zero = dict(launches=0, ms=0.0, flops=0.0, bytes=0.0)
+    tc_names = ("papr_stack_bf16", "papr_linear_bf16", "papr_wgrad_bf16")
+    tc = [kern.get(n, zero) for n in tc_names]
+    sel = kern.get("papr_select_topk", zero)
+    tc_ms = max(sum(k["ms"] for k in tc), 1e-9)
+    tc_flops = sum(k["flops"] for k in tc)
+    tc_bytes = sum(k["bytes"] for k in tc)
+    tc_launches = sum(k["launches"] for k in tc)
+    achieved = tc_flops / (tc_ms * 1e-3) / 1e12
+    stack = kern.get("papr_stack_bf16", zero)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")      # dram bytes per launch from the committed ncu capture
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get("tcgen05_kernels_bytes_per_step")
     roofline = {
-        "bound": "tensor", "kernel": "linear_kernel+wgrad_kernel (tcgen05 GEMMs of the key/value/query stacks)",
+        "bound": "tensor",
+        "kernel": "tcgen05 GEMM kernels of the key/value/query stacks: stack_kernel (fused fwd + dgrad, cta_group::2), wgrad_kernel, linear_kernel",
         "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_sustained"],
-        "peak_source": peaks["source"] + " bf16 sustained", "traffic": None,
-        "launches_per_step": (lin["launches"] + wg["launches"]) / steps, "ms_per_step": tc_ms / steps,
-        "share_of_step": tc_ms / steps / ms_step,
-        "hbm_gbs": (lin["bytes"] + wg["bytes"]) / (tc_ms * 1e-3) / 1e9, "hbm_frac": (lin["bytes"] + wg["bytes"]) / (tc_ms * 1e-3) / 1e9 / peaks["hbm"],
+        "peak_source": peaks["source"] + " bf16 sustained (kernels timed inside a long step)",
+        "traffic": traffic, "traffic_unit": "bytes per step over these launches (ncu dram__bytes_read+write)",
+        "algorithmic_bytes_per_step": tc_bytes / steps,
+        "launches_per_step": tc_launches / steps, "ms_per_step": tc_ms / steps, "share_of_step": tc_ms / steps / ms_step,
+        "hbm_gbs": tc_bytes / (tc_ms * 1e-3) / 1e9, "hbm_frac": tc_bytes / (tc_ms * 1e-3) / 1e9 / peaks["hbm"],
+        "by_kernel": {n: {"ms_per_step": k["ms"] / steps, "tflops": k["flops"] / max(k["ms"], 1e-9) / 1e9,
+                          "tensor_frac": k["flops"] / max(k["ms"], 1e-9) / 1e9 / peaks["tf_sustained"],
+                          "hbm_gbs": k["bytes"] / max(k["ms"], 1e-9) / 1e6, "hbm_frac": k["bytes"] / max(k["ms"], 1e-9) / 1e6 / peaks["hbm"]}
+                      for n, k in zip(tc_names, tc) if k["launches"]},
     }
     kernels = {k: dict(launches_per_step=v["launches"] / steps, ms_per_step=v["ms"] / steps,
                        tflops=v["flops"] / max(v["ms"], 1e-9) / 1e9, gbs=v["bytes"] / max(v["ms"], 1e-9) / 1e6)

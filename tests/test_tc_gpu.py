@@ -92,3 +92,21 @@ def test_wgrad(A, B, tr, rows):
         want = want.t()
     err = (out - 1.0 - want).abs().max().item()
     assert err < 2e-3 * rows ** 0.5, err
+
+
+def test_linear_addend_split_k():
+    """Skip-connection layers (mlp.py:54-55): [h, inp] W^T = h W1^T + inp W2^T through the fp32 addend."""
+    from papr_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(11)
+    rows = 1000
+    h = torch.randn(rows, 256, device="cuda", generator=g)
+    inp = torch.randn(rows, 142, device="cuda", generator=g)
+    w = torch.randn(256, 398, device="cuda", generator=g) / 20
+    b = torch.randn(256, device="cuda", generator=g)
+    hb, ib = ops.Blocked.from_f32(h), ops.Blocked.from_f32(inp)
+    _, part, _ = ops.linear_bf16(ib, ops.pack_weight(w[:, 256:], 256, 144), 256, 144, out_blocked=False, out_f32=True)
+    _, y, _ = ops.linear_bf16(hb, ops.pack_weight(w[:, :256], 256, 256), 256, 256, bias=b, act=True, slope=0.2,
+                              out_blocked=False, out_f32=True, addend=part)
+    pre = _bf(torch.cat([h, inp], 1)) @ _bf(w).t() + b
+    want = torch.where(pre > 0, pre, 0.2 * pre)
+    assert (y[:rows] - want).abs().max().item() < 3e-3
