@@ -175,6 +175,19 @@ typedef struct papr_stack_layer {
 int papr_stack_bf16(const void *x, int K0, const papr_stack_layer *layers, int n_layers, int64_t rows, float slope,
                     void *stream);
 
+/*
+ * Per-ray query tail -- replaces the query stack's output LayerNorm, w_q, and the part of AttentionLayer that depends
+ * only on the ray (reference attn.py:39-42, 117, 217-218, 53-54).  Everything after the normalisation is linear, so the
+ * host folds the LayerNorm affine terms, w_q, w_k and the key out-norm into one 256x256 matrix A, a bias c0, a vector
+ * w_c and a scalar c_const:  ua = A z + c0 (papr_linear_bf16),  c' = w_c . z + c_const (here).
+ *   fwd: q5 (R,256) f32 -> z tile-blocked bf16 (R_pad,256) = (q5-mean)/(std+eps), stats (R,2), cprime (R)
+ *   bwd: dz (R,256; ld_dz) = gradient w.r.t. z through A, dc (R) -> dq5 (R,256); g_wc (256) +=, g_cconst (1) +=
+ */
+int papr_query_tail_fwd(const float *q5, const float *w_c, float c_const, float eps, int64_t R, void *z_blocked,
+                        float *stats, float *cprime, void *stream);
+int papr_query_tail_bwd(const float *q5, const float *stats, const float *w_c, const float *dz, int64_t ld_dz,
+                        const float *dc, float eps, int64_t R, float *dq5, float *g_wc, float *g_cconst, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

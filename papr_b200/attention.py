@@ -344,6 +344,47 @@ class _StackBf16Fn(torch.autograd.Function):
         return (dx.to_f32(ctx.rows, ctx.n_in), None, None, *gWs, *gbs)
 
 
+class _QueryTailFn(torch.autograd.Function):
+    """(q5, A, c0, w_c) -> (ua, w_c . z):  z = normalise(q5);  ua = z A^T + c0."""
+
+    @staticmethod
+    def forward(ctx, q5, A, c0, w_c, eps):
+        R = q5.shape[0]
+        dev = q5.device
+        q5c = q5.detach().contiguous()
+        wc = w_c.detach().contiguous()
+        zb = ops.Blocked(R, 256, dev)
+        stats = torch.empty((R, 2), device=dev)
+        cprime = torch.empty((R,), device=dev)
+        ops.call("papr_query_tail_fwd", q5c.data_ptr(), wc.data_ptr(), 0.0, float(eps), R, zb.data_ptr(),
+                 stats.data_ptr(), cprime.data_ptr(), nbytes=R * (1024.0 + 512 + 12))
+        _, ua, _ = ops.linear_bf16(zb, ops.pack_weight(A, 256, 256), 256, 256, bias=c0.detach().contiguous(),
+                                   out_blocked=False, out_f32=True)
+        ctx.save_for_backward(q5c, stats, wc, A.detach())
+        ctx.zb, ctx.eps = zb, eps
+        return ua[:R], cprime
+
+    @staticmethod
+    def backward(ctx, d_ua, d_c):
+        q5, stats, wc, A = ctx.saved_tensors
+        R = q5.shape[0]
+        dev = q5.device
+        d_ua = d_ua.contiguous()
+        d_c = d_c.contiguous()
+        dub = ops.Blocked.from_f32(d_ua)
+        _, dz, _ = ops.linear_bf16(dub, ops.pack_weight(A, 256, 256, transpose=True), 256, 256, out_blocked=False, out_f32=True)
+        gA = torch.zeros((256, 256), device=dev)
+        ops.wgrad_bf16(dub, ctx.zb, gA, 256, 256)
+        dq5 = torch.empty((R, 256), device=dev)
+        g_wc = torch.zeros(256, device=dev)
+        g_cc = torch.zeros(1, device=dev)
+        ops.call("papr_query_tail_bwd", q5.data_ptr(), stats.data_ptr(), wc.data_ptr(), dz.data_ptr(), dz.stride(0),
+                 d_c.data_ptr(), float(ctx.eps), R, dq5.data_ptr(), g_wc.data_ptr(), g_cc.data_ptr(),
+                 nbytes=R * (3 * 1024.0 + 12))
+        ctx.zb = None
+        return dq5, gA, d_ua.sum(0), g_wc, None
+
+
 class RowAttentionFn(torch.autograd.Function):
     """(points, pc_feats, influ, ua, c', key-in LayerNorm, key/value stack weights) -> (fused, attn)."""
 
@@ -479,17 +520,29 @@ class ProximityAttention(nn.Module):
             raise NotImplementedError("skip_layers in the query stack are not used by any shipped config")
         else:
             q = _StackBf16Fn.apply(q, self.q_slope, len(lins), *[l.weight for l in lins], *[l.bias for l in lins])
-        q = fq.outnorm(q)
         al = self.attention_layer
-        qp = _linear(q, al.w_q, None, precision)                               # q' (R,256)
         scale = 1.0 / math.sqrt(self.d_model)
-        if precision == "fp32":
-            u = (qp @ al.w_k.weight) * scale
-        else:
-            u = _LinearBf16Fn.apply(qp, al.w_k.weight.t(), torch.zeros_like(al.w_k.bias), None) * scale
         on = self.embed.embed_k.outnorm
-        ua = u * on.a_2
-        cprime = (u * on.b_2).sum(-1) + (qp @ al.w_k.bias) * scale
+        if precision == "fp32":
+            q = fq.outnorm(q)
+            qp = _linear(q, al.w_q, None, precision)                           # q' (R,256)
+            u = (qp @ al.w_k.weight) * scale
+            ua = u * on.a_2
+            cprime = (u * on.b_2).sum(-1) + (qp @ al.w_k.bias) * scale
+            return ua, cprime
+        # Everything after the normalisation z = (q - mean)/(std + eps) is linear in z (attn.py:39-42, 217-218, 53-54):
+        #   q' = W_q (a_q z + b_q) + c_q ;  u = W_k^T q' / sqrt(d) ;  ua = u a_k ;  c' = u . b_k2 + q' . c_k / sqrt(d)
+        # so it is folded into ONE 256x256 matrix (tiny fp32 torch ops, differentiable) applied on the tensor cores.
+        qn = fq.outnorm
+        M1 = scale * (al.w_k.weight.t() @ al.w_q.weight)                        # u = M1 (a_q z) + u0
+        q0 = al.w_q.weight @ qn.b_2 + al.w_q.bias
+        u0 = scale * (al.w_k.weight.t() @ q0)
+        A = on.a_2[:, None] * M1 * qn.a_2[None, :]
+        c0 = on.a_2 * u0
+        w_c = (M1.t() @ on.b_2 + scale * (al.w_q.weight.t() @ al.w_k.bias)) * qn.a_2
+        c_const = on.b_2 @ u0 + scale * (al.w_k.bias @ q0)
+        ua, cdot = _QueryTailFn.apply(q, A, c0, w_c, self.eps)
+        cprime = cdot + c_const
         return ua, cprime
 
     def forward(self, rays_o, rays_d, idx, points, feats, influ, precision=None):

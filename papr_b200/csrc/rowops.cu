@@ -791,6 +791,92 @@ __global__ void __launch_bounds__(kRowThreads) key_score_bwd_kernel(const ScoreP
         *reinterpret_cast<uint4 *>(p.dh5 + blocked_chunk_offset(M + i / 32, (int)(i % 32), 4)) = make_uint4(0, 0, 0, 0);
 }
 
+
+// ------------------------------------------------------------------------------------------------ query tail
+// Per ray: z = (q5 - mean)/(std + eps) of the query stack's output (attn.py:39-42 without the affine part, which the
+// host folds -- together with w_q, w_k and the key out-norm -- into one 256x256 matrix applied by papr_linear_bf16) and
+// c' = w_c . z + c_const.  Warp per ray, eight columns per lane.
+struct QueryTailParams {
+    const float *q5;        // [R,256]
+    const float *wc;        // [256]
+    float c_const, eps;
+    int64_t R;
+    uint8_t *z;             // blocked bf16 [R_pad,256]
+    float *stats, *cprime;  // [R,2], [R]
+    // backward
+    const float *dz, *dc;   // [R,256] (ld), [R]
+    int64_t ld_dz;
+    float *dq5, *g_wc, *g_cc;   // [R,256], [256] +=, [1] +=
+};
+
+__global__ void __launch_bounds__(kRowThreads) query_tail_fwd_kernel(const QueryTailParams p)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float wc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) wc[e] = p.wc[lane * 8 + e];
+    for (int64_t ray = (int64_t)blockIdx.x * kRowWarps + warp; ray < p.R; ray += (int64_t)gridDim.x * kRowWarps) {
+        const float4 a = *reinterpret_cast<const float4 *>(p.q5 + ray * 256 + lane * 8);
+        const float4 b = *reinterpret_cast<const float4 *>(p.q5 + ray * 256 + lane * 8 + 4);
+        const float h[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        float s = 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s += h[e];
+        const float mean = warp_sum(s) * (1.f / 256.f);
+        float sq = 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { const float c = h[e] - mean; sq += c * c; }
+        const float rstd = 1.f / (sqrtf(warp_sum(sq) * (1.f / 255.f)) + p.eps);
+        float z[8], dot = 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { z[e] = (h[e] - mean) * rstd; dot += z[e] * wc[e]; }
+        dot = warp_sum(dot);
+        *reinterpret_cast<uint4 *>(p.z + blocked_chunk_offset(ray, lane, 4)) =
+            make_uint4(pack_bf16(z[0], z[1]), pack_bf16(z[2], z[3]), pack_bf16(z[4], z[5]), pack_bf16(z[6], z[7]));
+        if (lane == 0) { p.stats[ray * 2] = mean; p.stats[ray * 2 + 1] = rstd; p.cprime[ray] = dot + p.c_const; }
+    }
+    const int64_t R_pad = (p.R + 127) / 128 * 128;
+    for (int64_t i = (int64_t)blockIdx.x * kRowThreads + threadIdx.x; i < (R_pad - p.R) * 32; i += (int64_t)gridDim.x * kRowThreads)
+        *reinterpret_cast<uint4 *>(p.z + blocked_chunk_offset(p.R + i / 32, (int)(i % 32), 4)) = make_uint4(0, 0, 0, 0);
+}
+
+__global__ void __launch_bounds__(kRowThreads) query_tail_bwd_kernel(const QueryTailParams p)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float wc[8], acc_wc[8], acc_cc = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { wc[e] = p.wc[lane * 8 + e]; acc_wc[e] = 0.f; }
+    for (int64_t ray = (int64_t)blockIdx.x * kRowWarps + warp; ray < p.R; ray += (int64_t)gridDim.x * kRowWarps) {
+        const float4 a = *reinterpret_cast<const float4 *>(p.q5 + ray * 256 + lane * 8);
+        const float4 b = *reinterpret_cast<const float4 *>(p.q5 + ray * 256 + lane * 8 + 4);
+        const float4 ga = *reinterpret_cast<const float4 *>(p.dz + ray * p.ld_dz + lane * 8);
+        const float4 gb = *reinterpret_cast<const float4 *>(p.dz + ray * p.ld_dz + lane * 8 + 4);
+        const float h[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        float g[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+        const float mean = p.stats[ray * 2], rstd = p.stats[ray * 2 + 1], dc = p.dc[ray];
+        float z[8], s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            z[e] = (h[e] - mean) * rstd;
+            acc_wc[e] += dc * z[e];
+            g[e] += dc * wc[e];                 // d z = (d ua) A + d c' * w_c
+            s1 += g[e]; s2 += g[e] * z[e];
+        }
+        acc_cc += dc;
+        s1 = warp_sum(s1) * (1.f / 256.f);
+        const float sigma = 1.f / rstd - p.eps;
+        s2 = warp_sum(s2) / (255.f * sigma);
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = rstd * (g[e] - s1) - z[e] * s2;
+        *reinterpret_cast<float4 *>(p.dq5 + ray * 256 + lane * 8) = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<float4 *>(p.dq5 + ray * 256 + lane * 8 + 4) = make_float4(o[4], o[5], o[6], o[7]);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) atomicAdd(p.g_wc + lane * 8 + e, acc_wc[e]);
+    if (lane == 0) atomicAdd(p.g_cc, acc_cc);
+}
+
 static int row_grid(int64_t R)
 {
     const int64_t blocks = (R + kRowWarps - 1) / kRowWarps;
@@ -889,5 +975,26 @@ extern "C" int papr_key_score_bwd(const float *d_score, const void *h5, const fl
     p.d_score_in = d_score; p.h5 = (const uint8_t *)h5; p.h5_f32 = h5_f32; p.stats = const_cast<float *>(stats); p.ua = ua; p.R = R; p.K = K;
     p.eps = eps; p.dh5 = (uint8_t *)dh5_blocked; p.dh5_f32 = dh5_f32; p.zsum = zsum; p.dssum = dssum; p.g_b5 = g_bias5;
     key_score_bwd_kernel<<<row_grid(R), kRowThreads, 0, (cudaStream_t)stream>>>(p);
+    return check_launch();
+}
+
+extern "C" int papr_query_tail_fwd(const float *q5, const float *w_c, float c_const, float eps, int64_t R, void *z_blocked,
+                                   float *stats, float *cprime, void *stream)
+{
+    if (!q5 || !w_c || !z_blocked || !stats || !cprime || R <= 0) return PAPR_ERR_INVALID_ARGUMENT;
+    QueryTailParams p = {};
+    p.q5 = q5; p.wc = w_c; p.c_const = c_const; p.eps = eps; p.R = R; p.z = (uint8_t *)z_blocked; p.stats = stats; p.cprime = cprime;
+    query_tail_fwd_kernel<<<row_grid(R), kRowThreads, 0, (cudaStream_t)stream>>>(p);
+    return check_launch();
+}
+
+extern "C" int papr_query_tail_bwd(const float *q5, const float *stats, const float *w_c, const float *dz, int64_t ld_dz,
+                                   const float *dc, float eps, int64_t R, float *dq5, float *g_wc, float *g_cconst, void *stream)
+{
+    if (!q5 || !stats || !w_c || !dz || !dc || !dq5 || !g_wc || !g_cconst || R <= 0 || ld_dz < 256 || ld_dz % 4) return PAPR_ERR_INVALID_ARGUMENT;
+    QueryTailParams p = {};
+    p.q5 = q5; p.stats = const_cast<float *>(stats); p.wc = w_c; p.dz = dz; p.ld_dz = ld_dz; p.dc = dc; p.eps = eps; p.R = R;
+    p.dq5 = dq5; p.g_wc = g_wc; p.g_cc = g_cconst;
+    query_tail_bwd_kernel<<<row_grid(R), kRowThreads, 0, (cudaStream_t)stream>>>(p);
     return check_launch();
 }
