@@ -47,6 +47,19 @@ int papr_select_topk(const float *rays_o, const float *rays_d, const float *poin
                      int32_t *idx_out, void *stream);
 
 /*
+ * Stage a1 with spatial culling (same result as papr_select_topk, bit for bit).  The caller provides the points sorted
+ * along a space-filling curve and padded to a multiple of 32 with far-away points (coordinates ~1e18):
+ *   sorted_points (P_pad,3) f32; perm (P_pad) i32 = original index of each sorted point (-1 for padding);
+ *   spheres (P_pad/32, 4) f32 = centre xyz + radius of each group of 32 consecutive sorted points (radius rounded up);
+ *   spheres8 (ceil(P_pad/256), 4) f32 = the same around every 8 consecutive groups (two-level culling);
+ *   pmax: DEVICE pointer to one float >= max |p| over the real points.
+ * idx_out holds ORIGINAL point indices ordered by (distance, original index).
+ */
+int papr_select_topk_sorted(const float *rays_o, const float *rays_d, const float *sorted_points, const int32_t *perm,
+                            const float *spheres, const float *spheres8, int64_t n_views, int64_t rays_per_view, int64_t P_pad, int64_t P,
+                            int K, float eps, const float *pmax, int32_t *idx_out, void *stream);
+
+/*
  * Tensor-core building blocks (stages a7/a8/a12).  Activations use the library's "tile-blocked" bf16 layout: a logical
  * [rows, cols] matrix (rows % 128 == 0, cols % 64 == 0) stored as [rows/128][cols/64] blocks of 16 KB, each block
  * 128 rows x 64 columns with the eight 16-byte chunks of a row XOR-swizzled by (row & 7) -- the shared-memory image

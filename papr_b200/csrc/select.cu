@@ -19,6 +19,8 @@
 
 namespace papr {
 
+__device__ unsigned long long g_sel_fallbacks = 0;   // debug counter: rays that needed the exact rescan
+
 constexpr int kSelThreads = 256;
 constexpr int kSelWarps = kSelThreads / 32;
 constexpr int kSelTile = 2048;   // points per shared-memory tile (32 KB as float4)
@@ -160,6 +162,7 @@ select_topk2_kernel(const float *__restrict__ rays_o, const float *__restrict__ 
             if (ci >= 0 && rank < K) idx_out[((int64_t)view * rays_per_view + r) * K + rank] = ci;
         } else {
             // exact rescan of every point for this ray (same algorithm as select_topk_kernel, one ray per warp)
+            if (lane == 0) atomicAdd(&g_sel_fallbacks, 1ull);
             float xk = INF, xt = INF;
             int xi = -1;
             for (int c = 0; c < P; c += 32) {
@@ -176,6 +179,213 @@ select_topk2_kernel(const float *__restrict__ rays_o, const float *__restrict__ 
                     const float ck = __shfl_sync(full, key, src);
                     const int cc = c + src;
                     if (ck < xt) xt = list_insert(xk, xi, ck, cc, lane, K - 1);
+                }
+            }
+            if (lane < K) idx_out[((int64_t)view * rays_per_view + r) * K + lane] = xi;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Culled variant (the product path for P >= 1024): the same two-phase exact selection, but the points arrive sorted
+// along a Morton curve in groups of 32 with a bounding sphere per group, and a warp skips a whole group when a
+// conservative lower bound of the cheap key over (every ray of the warp) x (every point of the group) cannot beat the
+// warp's current thresholds.  Skipping such a group never changes the candidate lists (an insertion needs key < thr), so
+// the result is identical to the unculled scan.
+//   bound: every ray direction d of the warp lies within angle rho of the warp's mean direction dc; for a sphere
+//   (centre vc relative to the ray origin, radius r) the distance from any of its points to any of those lines is at
+//   least  |vc x dc| cos(rho) - |vc . dc| sin(rho) - r  =: lb  (lines are unoriented, hence the absolute value), and
+//   the cheap key is >= |d|^2 dist^2 >= dmin^2 lb^2.  Floating-point slack: cos(rho) is lowered / sin(rho), r raised
+//   by 1e-6 relative and the comparison keeps a 0.2% margin.
+// ---------------------------------------------------------------------------------------------------------------
+// lexicographic (key, index) insert for lists whose candidates do not arrive in index order
+__device__ __forceinline__ float list_insert_lex(float &lk, int &li, float ck, int ci, int lane, int last)
+{
+    const unsigned full = 0xffffffffu;
+    const int pos = __popc(__ballot_sync(full, lk < ck || (lk == ck && li < ci && li >= 0)));
+    const float uk = __shfl_up_sync(full, lk, 1);
+    const int ui = __shfl_up_sync(full, li, 1);
+    if (lane == pos) { lk = ck; li = ci; }
+    else if (lane > pos) { lk = uk; li = ui; }
+    return __shfl_sync(full, lk, last);
+}
+
+template <int RPW>
+__global__ void __launch_bounds__(kSelThreads)
+select_topk3_kernel(const float *__restrict__ rays_o, const float *__restrict__ rays_d,
+                    const float *__restrict__ spts /* (P_pad,3) sorted, padded with far points */,
+                    const int32_t *__restrict__ perm /* (P_pad) original index, -1 for padding */,
+                    const float4 *__restrict__ spheres /* (P_pad/32) centre + radius */,
+                    const float4 *__restrict__ spheres8 /* (P_pad/256) spheres around 8 consecutive groups */,
+                    int64_t rays_per_view, int P_pad, int K, float eps, const float *__restrict__ pmax_ptr,
+                    int32_t *__restrict__ idx_out, int blocks_per_view)
+{
+    __shared__ float4 tile[kSelTile];
+    __shared__ float4 sph[kSelTile / 32];
+    __shared__ float4 sph8[kSelTile / 256];
+
+    const int view = blockIdx.x / blocks_per_view;
+    const int blk = blockIdx.x - view * blocks_per_view;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const unsigned full = 0xffffffffu;
+    const float INF = __int_as_float(0x7f800000);
+
+    const float ox = rays_o[3 * view + 0], oy = rays_o[3 * view + 1], oz = rays_o[3 * view + 2];
+    const int64_t ray0 = (int64_t)blk * (kSelWarps * RPW) + warp * RPW;
+    float dx[RPW], dy[RPW], dz[RPW], thr[RPW], lk[RPW];
+    int li[RPW];
+    float cxs = 0.f, cys = 0.f, czs = 0.f, dmin2 = INF;
+#pragma unroll
+    for (int j = 0; j < RPW; ++j) {
+        int64_t r = ray0 + j;
+        if (r >= rays_per_view) r = rays_per_view - 1;
+        const float *d = rays_d + ((int64_t)view * rays_per_view + r) * 3;
+        dx[j] = d[0]; dy[j] = d[1]; dz[j] = d[2];
+        thr[j] = INF; lk[j] = INF; li[j] = -1;
+        const float n2 = dx[j] * dx[j] + dy[j] * dy[j] + dz[j] * dz[j];
+        const float rn = rsqrtf(fmaxf(n2, 1e-30f));
+        cxs += dx[j] * rn; cys += dy[j] * rn; czs += dz[j] * rn;
+        dmin2 = fminf(dmin2, n2);
+    }
+    // mean direction of the warp's rays and the (padded) angle that contains all of them
+    float cosr = 1.f, sinr = 1.f;
+    bool can_cull;
+    {
+        const float n2 = cxs * cxs + cys * cys + czs * czs;
+        can_cull = n2 > 1e-12f && dmin2 > 1e-20f;
+        const float rn = rsqrtf(fmaxf(n2, 1e-30f));
+        cxs *= rn; cys *= rn; czs *= rn;
+#pragma unroll
+        for (int j = 0; j < RPW; ++j) {
+            const float n = rsqrtf(fmaxf(dx[j] * dx[j] + dy[j] * dy[j] + dz[j] * dz[j], 1e-30f));
+            cosr = fminf(cosr, (cxs * dx[j] + cys * dy[j] + czs * dz[j]) * n);
+        }
+        cosr = cosr * (1.f - 2e-6f) - 2e-6f;
+        can_cull = can_cull && cosr > 0.f;
+        sinr = sqrtf(fmaxf(0.f, 1.f - cosr * cosr)) * (1.f + 2e-6f) + 2e-6f;
+        dmin2 *= 0.998f;                       // the comparison margin
+    }
+
+    for (int base = 0; base < P_pad; base += kSelTile) {
+        const int count = min(kSelTile, P_pad - base);      // multiple of 32
+        __syncthreads();
+        for (int i = threadIdx.x; i < count; i += kSelThreads) {
+            const float *p = spts + (int64_t)(base + i) * 3;
+            const float vx = __fsub_rn(p[0], ox), vy = __fsub_rn(p[1], oy), vz = __fsub_rn(p[2], oz);
+            tile[i] = make_float4(vx, vy, vz, fmaf(vz, vz, fmaf(vy, vy, vx * vx)));
+        }
+        for (int i = threadIdx.x; i < count / 32; i += kSelThreads) {
+            const float4 sp = spheres[base / 32 + i];
+            sph[i] = make_float4(sp.x - ox, sp.y - oy, sp.z - oz, sp.w);
+        }
+        for (int i = threadIdx.x; i < (count + 255) / 256; i += kSelThreads) {
+            const float4 sp = spheres8[base / 256 + i];
+            sph8[i] = make_float4(sp.x - ox, sp.y - oy, sp.z - oz, sp.w);
+        }
+        __syncthreads();
+        for (int c = 0; c < count; c += 32) {
+            if (can_cull && (c & 255) == 0) {       // first the sphere around the next 8 groups (256 points)
+                const float4 sp = sph8[c >> 8];
+                const float dotc = fabsf(sp.x * cxs + sp.y * cys + sp.z * czs);
+                const float kx = sp.y * czs - sp.z * cys, ky = sp.z * cxs - sp.x * czs, kz = sp.x * cys - sp.y * cxs;
+                const float crn = sqrtf(kx * kx + ky * ky + kz * kz);
+                const float lb = crn * cosr * (1.f - 4e-6f) - dotc * sinr - sp.w;
+                float tmax = thr[0];
+#pragma unroll
+                for (int j = 1; j < RPW; ++j) tmax = fmaxf(tmax, thr[j]);
+                if (lb > 0.f && lb * lb * dmin2 > tmax) { c += 224; continue; }     // warp-uniform: skip all 8 groups
+            }
+            if (can_cull) {
+                const float4 sp = sph[c >> 5];
+                const float dotc = fabsf(sp.x * cxs + sp.y * cys + sp.z * czs);
+                const float kx = sp.y * czs - sp.z * cys, ky = sp.z * cxs - sp.x * czs, kz = sp.x * cys - sp.y * cxs;
+                const float crn = sqrtf(kx * kx + ky * ky + kz * kz);
+                const float lb = crn * cosr * (1.f - 4e-6f) - dotc * sinr - sp.w;
+                float tmax = thr[0];
+#pragma unroll
+                for (int j = 1; j < RPW; ++j) tmax = fmaxf(tmax, thr[j]);
+                if (lb > 0.f && lb * lb * dmin2 > tmax) continue;       // warp-uniform
+            }
+            const float4 v = tile[c + lane];
+            const int pidx = base + c + lane;
+            const float ew = eps * v.w;
+#pragma unroll
+            for (int j = 0; j < RPW; ++j) {
+                const float cx = fmaf(v.y, dz[j], -v.z * dy[j]);
+                const float cy = fmaf(v.z, dx[j], -v.x * dz[j]);
+                const float cz = fmaf(v.x, dy[j], -v.y * dx[j]);
+                const float a = fmaf(cx, cx, fmaf(cy, cy, fmaf(cz, cz, ew)));
+                unsigned m = __ballot_sync(full, a < thr[j]);
+                while (m) {
+                    const int src = __ffs(m) - 1;
+                    m &= m - 1;
+                    const float ck = __shfl_sync(full, a, src);
+                    const int ci = __shfl_sync(full, pidx, src);
+                    if (ck < thr[j]) thr[j] = list_insert(lk[j], li[j], ck, ci, lane, 31);
+                }
+            }
+        }
+    }
+    // max |v|^2 over all points of the view, conservatively: (|o| + max|p|)^2
+    const float onorm = sqrtf(ox * ox + oy * oy + oz * oz);
+    const float pmax = *pmax_ptr * 1.0001f;
+    const float wmax = (onorm + pmax) * (onorm + pmax) * 1.0001f;
+
+#pragma unroll
+    for (int j = 0; j < RPW; ++j) {
+        const int64_t r = ray0 + j;
+        if (r >= rays_per_view) continue;                       // warp-uniform
+        const float den = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx[j], dx[j]), __fmul_rn(dy[j], dy[j])),
+                                              __fmul_rn(dz[j], dz[j])), eps);
+        const float rinv = __frcp_rn(den);
+        const int si = li[j];                                   // position in the sorted array
+        int ci = -1;                                            // original point index
+        float ek = INF;
+        if (si >= 0) {
+            ci = perm[si];
+            if (ci >= 0) {
+                const float *p = spts + (int64_t)si * 3;
+                ek = exact_key(__fsub_rn(p[0], ox), __fsub_rn(p[1], oy), __fsub_rn(p[2], oz), dx[j], dy[j], dz[j], den, rinv);
+            }
+        }
+        int rank = 0;
+        for (int t = 0; t < 32; ++t) {
+            const float ok = __shfl_sync(full, ek, t);
+            const int oi = __shfl_sync(full, ci, t);
+            rank += (ci >= 0 && oi >= 0 && (ok < ek || (ok == ek && oi < ci))) ? 1 : 0;
+        }
+        const unsigned who = __ballot_sync(full, rank == K - 1 && ci >= 0);
+        const float eK = __shfl_sync(full, ek, who ? __ffs(who) - 1 : 0);
+        const float a32 = thr[j];
+        const float u = 5.9604645e-8f;
+        const float V2 = wmax * den;
+        const float err = 32.f * u * sqrtf(V2 * a32) + 128.f * u * u * V2 + 8.f * u * a32;
+        const bool finite32 = a32 < 1e30f;                      // padding points carry huge finite keys
+        const bool safe = who != 0 && (!finite32 || (a32 > 1e-8f * fmaxf(V2, 1.f) && eK * den * (1.f + 4.f * u) < a32 - err));
+        if (safe) {
+            if (ci >= 0 && rank < K) idx_out[((int64_t)view * rays_per_view + r) * K + rank] = ci;
+        } else {
+            if (lane == 0) atomicAdd(&g_sel_fallbacks, 1ull);
+            float xk = INF, xt = INF;
+            int xi = -1;
+            for (int c = 0; c < P_pad; c += 32) {
+                const int pi = c + lane;
+                const int oi = perm[pi];
+                float key = INF;
+                if (oi >= 0) {
+                    const float *p = spts + (int64_t)pi * 3;
+                    key = exact_key(__fsub_rn(p[0], ox), __fsub_rn(p[1], oy), __fsub_rn(p[2], oz), dx[j], dy[j], dz[j], den, rinv);
+                }
+                unsigned m = __ballot_sync(full, key <= xt && oi >= 0);
+                while (m) {
+                    const int src = __ffs(m) - 1;
+                    m &= m - 1;
+                    const float ck = __shfl_sync(full, key, src);
+                    const int cc = __shfl_sync(full, oi, src);
+                    const float lastk = __shfl_sync(full, xk, K - 1);
+                    const int lasti = __shfl_sync(full, xi, K - 1);
+                    if (ck < lastk || (ck == lastk && (lasti < 0 || cc < lasti))) xt = list_insert_lex(xk, xi, ck, cc, lane, K - 1);
                 }
             }
             if (lane < K) idx_out[((int64_t)view * rays_per_view + r) * K + lane] = xi;
@@ -206,4 +416,32 @@ extern "C" int papr_select_topk(const float *rays_o, const float *rays_d, const 
         select_topk2_kernel<8><<<grid, kSelThreads, 0, (cudaStream_t)stream>>>(rays_o, rays_d, points, rays_per_view, (int)P, K, eps,
                                                                                idx_out, (int)blocks_per_view);
     return check_launch();
+}
+
+extern "C" int papr_select_topk_sorted(const float *rays_o, const float *rays_d, const float *sorted_points, const int32_t *perm,
+                                       const float *spheres, const float *spheres8, int64_t n_views, int64_t rays_per_view, int64_t P_pad, int64_t P,
+                                       int K, float eps, const float *pmax, int32_t *idx_out, void *stream)
+{
+    using namespace papr;
+    if (!rays_o || !rays_d || !sorted_points || !perm || !spheres || !spheres8 || !idx_out) return PAPR_ERR_INVALID_ARGUMENT;
+    if (K < 1 || K > 32 || P <= K || P_pad < P || P_pad % 32 || P_pad > INT32_MAX || n_views < 0 || rays_per_view < 0 || !pmax)
+        return PAPR_ERR_INVALID_ARGUMENT;
+    if (n_views == 0 || rays_per_view == 0) return PAPR_OK;
+    constexpr int RPW = 4;
+    const int64_t rays_per_block = kSelWarps * RPW;
+    const int64_t blocks_per_view = (rays_per_view + rays_per_block - 1) / rays_per_block;
+    if (blocks_per_view * n_views > INT32_MAX) return PAPR_ERR_INVALID_ARGUMENT;
+    select_topk3_kernel<RPW><<<(unsigned)(blocks_per_view * n_views), kSelThreads, 0, (cudaStream_t)stream>>>(
+        rays_o, rays_d, sorted_points, perm, (const float4 *)spheres, (const float4 *)spheres8, rays_per_view, (int)P_pad, K, eps, pmax, idx_out,
+        (int)blocks_per_view);
+    return check_launch();
+}
+
+// debug hook (not in the public header): number of rays that took the exact-rescan path since the last call
+extern "C" long long papr_debug_select_fallbacks(void)
+{
+    unsigned long long v = 0, z = 0;
+    cudaMemcpyFromSymbol(&v, papr::g_sel_fallbacks, sizeof(v));
+    cudaMemcpyToSymbol(papr::g_sel_fallbacks, &z, sizeof(z));
+    return (long long)v;
 }

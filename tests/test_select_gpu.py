@@ -87,3 +87,33 @@ def test_select_rejects_bad_arguments():
         ops.select_topk(torch.zeros(1, 3).cuda(), torch.zeros(1, 2, 2, 3).cuda(), torch.zeros(10, 3).cuda(), 20)
     with pytest.raises(ValueError):
         ops.select_topk(torch.zeros(1, 3).cuda(), torch.zeros(1, 2, 2, 3).cuda(), torch.zeros(100, 3).cuda(), 33)
+
+
+@pytest.mark.parametrize("P,cloud", [(5000, "cube"), (30000, "shell"), (1031, "shell")])
+def test_culled_and_plain_kernels_agree_exactly(P, cloud):
+    """The spatially culled kernel (Morton groups + bounding spheres) returns the plain scan's result bit for bit."""
+    from papr_b200 import ops
+    cfg = make_config("chair")
+    params = O.init_params(cfg, P, seed=P, cloud=cloud)
+    rays_o, rays_d, _ = O.synthetic_rays(256, 256, cfg.dataset.coord_scale, n_views=2, seed=3, h0=100, h1=164, w0=90, w1=150)
+    a = ops.select_topk(rays_o.cuda(), rays_d.cuda(), params["points"].cuda(), 20, cull=True)
+    b = ops.select_topk(rays_o.cuda(), rays_d.cuda(), params["points"].cuda(), 20, cull=False)
+    assert torch.equal(a, b)
+    want, _ = O.select_topk(rays_o[:1], rays_d[:1, :8, :8], params["points"], 20)
+    assert torch.equal(a[:1, :8, :8].cpu().long(), want)
+
+
+def test_culled_kernel_with_ties_duplicates_and_wide_rays():
+    """Lattice ties, exact duplicates and a warp whose rays point in very different directions (culling disabled or
+    useless) still give the oracle's (distance, index) order."""
+    from papr_b200 import ops
+    xs = np.linspace(-12, 12, 11)
+    pts = torch.tensor(np.array([[i, j, k] for i in xs for j in xs for k in xs]), dtype=torch.float32)
+    pts = torch.cat([pts, pts[:200]])
+    g = torch.Generator().manual_seed(4)
+    rays_o = torch.randn(2, 3, generator=g) * 25
+    rays_d = torch.randn(2, 6, 7, 3, generator=g)
+    rays_d[0, 0, :4] = torch.tensor([[0.0, 0.0, -1.0], [1.0, 0.0, 0.0], [0.0, 0.0, 1.0], [0.0, -2.0, 0.0]])
+    got = ops.select_topk(rays_o.cuda(), rays_d.cuda(), pts.cuda(), 20, cull=True).cpu().long()
+    want, _ = O.select_topk(rays_o, rays_d, pts, 20)
+    assert torch.equal(got, want)
