@@ -412,8 +412,9 @@ class RowAttentionFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_fused, d_attn):
         sh, nk, nv = ctx.sh, ctx.nk, ctx.nv
-        rays_o, rays_d, idx, pts, infl, ua, ln_a, v, attn, sc, stats = ctx.saved_tensors[:11]
-        wb = ctx.saved_tensors[11:]
+        saved = ctx.saved_tensors           # one access only (non-reentrant checkpointing unpacks on access)
+        rays_o, rays_d, idx, pts, infl, ua, ln_a, v, attn, sc, stats = saved[:11]
+        wb = saved[11:]
         kw, vw = wb[:nk], wb[2 * nk:2 * nk + nv]
         k_in, k_bits, h5, v_in, v_bits = ctx.blocked
         P = pts.shape[0]
@@ -545,17 +546,10 @@ class ProximityAttention(nn.Module):
         cprime = cdot + c_const
         return ua, cprime
 
-    def forward(self, rays_o, rays_d, idx, points, feats, influ, precision=None):
-        """rays_o (N,3), rays_d (N,H,W,3), idx int32 (N,H,W,K) -> fused (R,C), attn (R,K+1); differentiable."""
-        precision = precision or self.precision
-        N, H, W, _ = rays_d.shape
+    def _rows(self, rays_o, rd, idx, points, feats, influ, precision, n_views, rays_per_view):
+        """One batch of rays: rd (R,3), idx (R,K) -> fused (R,C), attn (R,K+1)."""
         K = idx.shape[-1]
-        if K > 31:
-            raise NotImplementedError("the blend kernel holds the K candidates + background in one warp: K <= 31")
-        sh = _Shape(self, N * H * W, H * W, K)
-        rays_o = rays_o.detach().float().contiguous()
-        rd = rays_d.detach().float().contiguous().reshape(-1, 3)
-        idx = idx.reshape(-1, K).contiguous()
+        sh = _Shape(self, n_views * rays_per_view, rays_per_view, K)
         ua, cprime = self.query_terms(rd, precision)
         fk, fv = self.embed.embed_k, self.embed.embed_v
         if precision == "fp32":
@@ -567,3 +561,44 @@ class ProximityAttention(nn.Module):
         wb = [l.weight for l in klin] + [l.bias for l in klin] + [l.weight for l in vlin] + [l.bias for l in vlin]
         return RowAttentionFn.apply(sh, rays_o, rd, idx, points, feats, influ, ua, cprime, fk.innorm.a_2, fk.innorm.b_2,
                                     len(klin), *wb)
+
+    #: bytes of backward stash per (ray, candidate) row in the bf16 path (layer inputs, sign bits, row statistics)
+    STASH_BYTES_PER_ROW = 8192
+
+    def forward(self, rays_o, rays_d, idx, points, feats, influ, precision=None, ray_chunk=None):
+        """rays_o (N,3), rays_d (N,H,W,3), idx int32 (N,H,W,K) -> fused (R,C), attn (R,K+1); differentiable.
+
+        ray_chunk: process at most that many rays of one view at a time.  Under autograd each chunk is checkpointed
+        (its forward is recomputed during backward), so the backward stash is bounded by one chunk instead of growing
+        with the frame -- the replacement for the reference's fixed 160x160 training patches when a whole frame (or a
+        1920x1080 one) is trained on at once.  None = automatic: chunk only if the stash would not fit in free memory."""
+        precision = precision or self.precision
+        N, H, W, _ = rays_d.shape
+        K = idx.shape[-1]
+        if K > 31:
+            raise NotImplementedError("the blend kernel holds the K candidates + background in one warp: K <= 31")
+        rays_o = rays_o.detach().float().contiguous()
+        rd = rays_d.detach().float().contiguous().reshape(N, H * W, 3)
+        idx = idx.reshape(N, H * W, K).contiguous()
+        grad = torch.is_grad_enabled()
+        if ray_chunk is None and grad and rd.is_cuda:
+            free, _ = torch.cuda.mem_get_info(rd.device)
+            free += torch.cuda.memory_reserved(rd.device) - torch.cuda.memory_allocated(rd.device)
+            need = N * H * W * K * self.STASH_BYTES_PER_ROW
+            if need > 0.8 * free:
+                ray_chunk = max(4096, int(0.4 * free / (K * self.STASH_BYTES_PER_ROW)) // 128 * 128)
+        if not ray_chunk or (N == 1 and H * W <= ray_chunk) or (N * H * W <= ray_chunk):
+            return self._rows(rays_o, rd.reshape(-1, 3), idx.reshape(-1, K), points, feats, influ, precision, N, H * W)
+        from torch.utils.checkpoint import checkpoint
+        fused, attn = [], []
+        for v in range(N):
+            for r0 in range(0, H * W, ray_chunk):
+                r1 = min(r0 + ray_chunk, H * W)
+                args = (rays_o[v:v + 1], rd[v, r0:r1], idx[v, r0:r1], points, feats, influ, precision, 1, r1 - r0)
+                if grad:
+                    f, a = checkpoint(self._rows, *args, use_reentrant=False)
+                else:
+                    f, a = self._rows(*args)
+                fused.append(f)
+                attn.append(a)
+        return torch.cat(fused), torch.cat(attn)

@@ -55,13 +55,14 @@ def _cube_lattice(center, num_pts, scale):
 
 
 class PAPR(nn.Module):
-    def __init__(self, args, device="cuda", precision="bf16", verbose=False):
+    def __init__(self, args, device="cuda", precision="bf16", verbose=False, ray_chunk=None):
         super().__init__()
         self.args = args
         self.eps = args.eps
         self.device = device
         self.verbose = verbose
         self.precision = precision          # "bf16": tcgen05 GEMMs (product) | "fp32": parity mode
+        self.ray_chunk = ray_chunk          # rays per checkpointed chunk in training (None = automatic, see attention.py)
         self.use_amp = args.use_amp
         self.amp_dtype = torch.float16 if args.amp_dtype == "float16" else torch.bfloat16
         # bf16 tensor-core path: no loss scaling needed; the object is kept because callers use scale/step/update
@@ -247,7 +248,7 @@ class PAPR(nn.Module):
         idx = self._get_points(rays_o, rays_d, c2w, step)
         feats = self.pc_feats if self.use_pc_feats else None
         return self.proximity_attn(rays_o, rays_d, idx, self.points, feats, self.points_influ_scores,
-                                   precision=self.precision)
+                                   precision=self.precision, ray_chunk=self.ray_chunk)
 
     def evaluate(self, rays_o, rays_d, c2w, step=-1, shading_code=None):
         N, H, W, _ = rays_d.shape
