@@ -163,3 +163,37 @@ def test_against_oracle_medium(precision):
         assert e_attn <= 1e-5 and e_fused <= 1e-5 and e_rgb <= 1e-4
     else:
         assert e_attn <= 2e-2 and e_fused <= 4e-2 and e_rgb <= 3e-2
+
+
+@pytest.mark.parametrize("K,P", [(1, 50), (31, 200), (20, 21)])
+def test_edge_candidate_counts(K, P):
+    """select_k extremes the kernels accept (1 <= K <= 31 in the blend; P barely above K) against the oracle."""
+    from tests.parity import golden_config
+    cfg = golden_config("chair")
+    cfg.geoms.points["select_k"] = K
+    params = O.init_params(cfg, P, seed=K, cloud="cube")
+    rays_o, rays_d, c2w = O.synthetic_rays(64, 64, cfg.dataset.coord_scale, n_views=1, seed=K, h0=20, h1=28, w0=30, w1=42)
+    model = _build(cfg, params, "fp32")
+    with torch.no_grad():
+        fused, attn = model.evaluate(rays_o.cuda(), rays_d.cuda(), c2w.cuda())
+        idx = model.select_k_ind.cpu()
+        want = O.forward(params, cfg, rays_o, rays_d, idx=idx)
+    o_idx, _ = O.select_topk(rays_o, rays_d, params["points"], K)
+    assert torch.equal(idx, o_idx)
+    assert float((attn.squeeze(-1).cpu() - want["attn"]).abs().max()) <= 1e-5
+    assert rel_err(fused.squeeze(-2).cpu(), want["fused"]) <= 1e-5
+
+
+def test_all_points_bypass_when_k_exceeds_cloud():
+    """model.py:326-327: select_k >= P uses every point for every ray."""
+    from tests.parity import golden_config
+    cfg = golden_config("chair")
+    params = O.init_params(cfg, 12, seed=3, cloud="cube")
+    rays_o, rays_d, c2w = O.synthetic_rays(32, 32, cfg.dataset.coord_scale, n_views=1, seed=1, h0=8, h1=16, w0=8, w1=16)
+    model = _build(cfg, params, "fp32")
+    with torch.no_grad():
+        fused, attn = model.evaluate(rays_o.cuda(), rays_d.cuda(), c2w.cuda())
+        want = O.forward(params, cfg, rays_o, rays_d)
+    assert attn.shape[-2] == 13 and model.select_k_ind.shape[-1] == 12
+    assert float((attn.squeeze(-1).cpu() - want["attn"]).abs().max()) <= 1e-5
+    assert rel_err(fused.squeeze(-2).cpu(), want["fused"]) <= 1e-5
