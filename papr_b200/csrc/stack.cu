@@ -8,14 +8,23 @@
 // activation-derivative mask -> bf16 -> back into the slot's shared-memory tile, which is the next layer's A operand).
 //
 //   warp 0      producer : input tiles (TMA bulk, per slot) and this CTA's half of every weight chunk (ring of stages)
-//   warp 1      MMA issuer (leader CTA only): waits both CTAs' data, issues tcgen05.mma.cta_group::2, commits with
-//               multicast so the "stage free" / "accumulator full" barriers fire in both CTAs
-//   warp 2      TMEM allocator (both CTAs, cta_group::2)
+//   warp 1      MMA issuer (leader CTA only): the whole warp walks the job list so addresses stay in uniform registers,
+//               one elected lane issues tcgen05.mma.cta_group::2 and commits with multicast, so the "stage free" /
+//               "accumulator full" barriers fire in both CTAs
+//   warp 2      TMEM allocator (both CTAs, cta_group::2), then the stash writer: TMA bulk stores of finished tiles,
+//               metered so that weight loads never queue behind more than two 16 KB stores
 //   warp 3      relay (peer CTA only): forwards "my TMA data landed" to the leader's barriers
 //   warps 4-19  epilogue: warp (g, quad) drains 64-column group g of the current job for TMEM lane quadrant quad
 // Training-time by-products are written as they appear: each layer's output tile (the next layer's input, needed by
-// the weight-gradient kernel) straight from the shared-memory tile with a TMA bulk store, activation sign bits, and
+// the weight-gradient kernel) straight from the shared-memory tile with TMA bulk stores, activation sign bits, and
 // per-column sums (bias gradients) in the dgrad direction.
+//
+// Measured on B200 (tools/ubench_tmem.cu, tools/stack_power.py; profiles/r01_stack_kernel_study.md): the tensor pipe
+// needs 2,050 cycles per job (256 rows x 256 x 256) and neither tcgen05.ld, st.shared nor TMA traffic slows it; what
+// did were (a) per-instruction register->uniform broadcast loops around tcgen05.mma issued under `lane == 0` (fixed by
+// elect.sync), (b) an epilogue of ~8 instructions per element (now ~2.5: bias add, one funnel shift for the sign bit,
+// cvt.rn.relu.bf16x2 for activation + packing; the dgrad mask is applied to packed pairs with prmt), and (c) bulk stores
+// of the stash starving the weight loads.  A sustained launch is power-capped (~990 W) on this part.
 #include "tc_common.cuh"
 #include <stdlib.h>
 
@@ -43,12 +52,13 @@ struct StackLayerDev {
 struct StackParams {
     const uint8_t *x;          // tile-blocked input [rows, kblk0*64]
     int64_t n_tiles;
-    int n_layers, kblk0, stages, any_stash;
+    int n_layers, kblk0, stages, any_stash, store_depth;
     float slope;
     long long *trace;          // debug: per-job clock stamps of cluster 0 (null in production)
     StackLayerDev L[kStkMaxLayers];
 };
 
+template <bool RELU>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kStkThreads, 1) stack_kernel(const __grid_constant__ StackParams p)
 {
     extern __shared__ uint8_t smem_raw[];
@@ -58,8 +68,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kStkThreads, 1) stac
     uint64_t *bars = (uint64_t *)(ring + p.stages * kStageBytes);
     uint64_t *w_full = bars, *w_empty = bars + 8, *pw_full = bars + 16;
     uint64_t *in_full = bars + 24, *pin_full = bars + 26, *in_free = bars + 28, *act_ready = bars + 30, *acc_full = bars + 32;
+    uint64_t *st_ready = bars + 36, *st_done = bars + 38;
     uint32_t *tmem_slot = (uint32_t *)(bars + 34);
-    float *vec_s = (float *)(bars + 36);                   // [layers][256]: biases (forward) or column sums (dgrad)
+    float *vec_s = (float *)(bars + 40);                   // [layers][256]: biases (forward) or column sums (dgrad)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -70,7 +81,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kStkThreads, 1) stac
     if (threadIdx.x == 0) {
         for (int i = 0; i < 8; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); mbar_init(&pw_full[i], 1); }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&in_full[i], 1); mbar_init(&pin_full[i], 1); mbar_init(&in_free[i], 16);
+            mbar_init(&in_full[i], 1); mbar_init(&pin_full[i], 1); mbar_init(&in_free[i], 17);
+            mbar_init(&st_ready[i], 16); mbar_init(&st_done[i], 1);
             mbar_init(&act_ready[i], 32); mbar_init(&acc_full[i], 1);
         }
         fence_barrier_init();
@@ -116,6 +128,39 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kStkThreads, 1) stac
                 }
             }
         }
+    } else if (warp == 2) {
+        // Stash writer: one thread moves finished activation tiles (layer outputs kept for the weight-gradient kernel) to
+        // HBM with TMA bulk stores, at most `store_depth` in flight.  Issuing all four 16 KB blocks of a job at once (from
+        // the epilogue groups) puts up to 2,000 cycles of store work ahead of the next weight load in the TMA unit's
+        // queue and the tensor pipe starves; metered, a weight load waits behind one or two blocks at most.
+        if (lane == 0) {
+            uint32_t sj = 0;
+            for (int64_t q = cluster_id; q < n_quads; q += n_clusters) {
+                for (int l = 0; l < L; ++l) {
+                    uint8_t *out = p.L[l].out_blocked;
+                    const bool stash = out != nullptr;
+                    const int ng = (p.L[l].N + 63) >> 6;
+                    for (int s = 0; s < 2; ++s) {
+                        if (stash) {
+                            mbar_wait(&st_ready[s], sj & 1);
+                            const int64_t tile = 4 * q + 2 * s + rank;
+                            if (tile < p.n_tiles) {
+                                for (int g = 0; g < ng; ++g) {
+                                    bulk_s2g(out + ((size_t)tile * ng + g) * kBlockBytes, act + s * kSlotBytes + g * kBlockBytes, kBlockBytes);
+                                    bulk_commit();
+                                    if (p.store_depth > 1) bulk_wait_read<1>(); else bulk_wait_read<0>();
+                                }
+                                bulk_wait_read<0>();
+                            }
+                            mbar_arrive(&st_done[s]);
+                        }
+                        if (l == L - 1) mbar_arrive(&in_free[s]);      // the producer may refill the slot
+                    }
+                    if (stash) ++sj;
+                }
+            }
+            bulk_wait<0>();
+        }
     } else if (warp == 3) {
         if (lane == 0 && rank == 1) {       // relay: tell the leader that this CTA's TMA data has landed
             int st = 0; uint32_t ph = 0; int64_t qi = 0;
@@ -133,47 +178,59 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kStkThreads, 1) stac
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && rank == 0) {
+        // The whole warp walks the job list so that every address and descriptor stays warp-uniform (uniform registers,
+        // no per-instruction register->uniform broadcast loops); lane 0 alone issues the MMAs and their commits.
+        if (rank == 0) {
             int st = 0; uint32_t ph = 0; int64_t qi = 0;
-            int64_t js[2] = {0, 0};
+            uint32_t jn = 0;
+            const uint32_t a_base = smem_u32(act), ring_base = smem_u32(ring);
             for (int64_t q = cluster_id; q < n_quads; q += n_clusters, ++qi) {
-                for (int l = 0; l < L; ++l) {
-                    const StackLayerDev &Ld = p.L[l];
-                    const uint32_t idesc = umma_idesc(256, Ld.N, false, false);
+                for (int l = 0; l < L; ++l, ++jn) {
+                    const int kblk = p.L[l].kblk, k_steps = p.L[l].k_steps;
+                    const uint32_t idesc = umma_idesc(256, p.L[l].N, false, false);
+#pragma unroll 1
                     for (int s = 0; s < 2; ++s) {
                         if (l == 0) {
                             mbar_wait(&in_full[s], (uint32_t)(qi & 1));
                             mbar_wait_cluster(&pin_full[s], (uint32_t)(qi & 1));
                         }
-                        if (js[s] > 0) mbar_wait_cluster(&act_ready[s], (uint32_t)((js[s] - 1) & 1));
+                        if (jn > 0) mbar_wait_cluster(&act_ready[s], (jn - 1) & 1);
                         tc_fence_after();
-                        if (p.trace && blockIdx.x == 0 && qi < 4) p.trace[((qi * 16 + l) * 2 + s) * 8 + 0] = clock64();
+                        if (p.trace && blockIdx.x == 0 && qi < 4 && lane == 0) p.trace[((qi * 16 + l) * 2 + s) * 8 + 0] = clock64();
                         const uint32_t d = tmem_base + s * 256;
-                        const uint64_t a_desc0 = umma_desc(smem_u32(act + s * kSlotBytes), 16, 1024);
+                        const uint64_t a_desc0 = umma_desc(a_base + s * kSlotBytes, 16, 1024);
                         uint32_t acc = 0;
-                        for (int kc = 0; kc < Ld.kblk; kc += 2) {
+#pragma unroll 1
+                        for (int kc = 0; kc < kblk; kc += 2) {
                             mbar_wait(&w_full[st], ph);
                             mbar_wait_cluster(&pw_full[st], ph);
                             tc_fence_after();
-                            const int nc = min(2, Ld.kblk - kc);
-                            // descriptors are built once per 64-wide block; a K step of 16 bf16 = 32 B = +2 in the address field
-                            uint64_t ad = a_desc0 + (uint64_t)(kc * (kBlockBytes >> 4));
-                            uint64_t bd = umma_desc(smem_u32(ring + st * kStageBytes), 16, 1024);
-                            for (int c = 0; c < nc; ++c) {
-                                const int nk = min(4, Ld.k_steps - 4 * (kc + c));
+                            // a K step of 16 bf16 = 32 B = +2 in the descriptor's address field; a 64-wide block = 16 KB
+                            const uint64_t ad = a_desc0 + (uint64_t)(kc * (kBlockBytes >> 4));
+                            const uint64_t bd = umma_desc(ring_base + st * kStageBytes, 16, 1024);
+                            const int nk = min(8, k_steps - 4 * kc);
+                            if (elect_one()) {
+                                if (nk == 8) {
 #pragma unroll
-                                for (int k = 0; k < 4; ++k) {
-                                    if (k < nk) { umma2_bf16(d, ad + 2 * k, bd + 2 * k, idesc, acc); acc = 1; }
+                                    for (int k = 0; k < 8; ++k) {
+                                        const uint32_t off = (uint32_t)((k >> 2) * (kBlockBytes >> 4) + 2 * (k & 3));
+                                        umma2_bf16(d, ad + off, bd + off, idesc, k ? 1u : acc);
+                                    }
+                                } else {
+                                    for (int k = 0; k < nk; ++k) {
+                                        const uint32_t off = (uint32_t)((k >> 2) * (kBlockBytes >> 4) + 2 * (k & 3));
+                                        umma2_bf16(d, ad + off, bd + off, idesc, k ? 1u : acc);
+                                    }
                                 }
-                                ad += kBlockBytes >> 4;
-                                bd += kBlockBytes >> 4;
+                                umma2_commit(&w_empty[st]);
                             }
-                            umma2_commit(&w_empty[st]);
+                            __syncwarp();
+                            acc = 1;
                             if (++st == p.stages) { st = 0; ph ^= 1; }
                         }
-                        umma2_commit(&acc_full[s]);
-                        if (p.trace && blockIdx.x == 0 && qi < 4) p.trace[((qi * 16 + l) * 2 + s) * 8 + 1] = clock64();
-                        ++js[s];
+                        if (elect_one()) umma2_commit(&acc_full[s]);
+                        __syncwarp();
+                        if (p.trace && blockIdx.x == 0 && qi < 4 && lane == 0) p.trace[((qi * 16 + l) * 2 + s) * 8 + 1] = clock64();
                     }
                 }
             }
@@ -184,116 +241,155 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kStkThreads, 1) stac
         const int ew = warp - 4;
         const int g = ew >> 2, quad = ew & 3;
         const int row = quad * 32 + lane;
-        const int sthr = quad * 32 + lane;                     // thread index within the group
+        const int sthr = row;                                  // thread index within the group
         const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
         const int bar_id = 1 + g;
-        int64_t je[2] = {0, 0};
-        bool store_pending[2] = {false, false};
+        const uint32_t blk0_s = smem_u32(act) + (uint32_t)g * kBlockBytes;     // my column block of slot 0 (shared window)
+        const uint32_t row_s = (uint32_t)row * 128u, sw = (uint32_t)row & 7u;
+        const uint32_t vec0_s = smem_u32(vec_s) + (uint32_t)g * 256u;          // my 64 bias / column-sum entries of layer 0
+        uint32_t jn = 0;                 // jobs finished per slot (both slots advance in lockstep)
+        uint32_t sj = 0;                 // stash jobs handed to the writer thread so far, per slot
+
+        // activation-derivative bits of the job after the current one are fetched one job ahead
+        auto fetch_bits = [&](int64_t q, int l, int s) -> uint64_t {
+            if (q >= n_quads) return 0;
+            const uint64_t *bi = p.L[l].bits_in;
+            const int ng = (p.L[l].N + 63) >> 6;
+            const int64_t tile = 4 * q + 2 * s + rank;
+            if (!bi || g >= ng || tile >= p.n_tiles) return 0;
+            return __ldg(bi + (tile * kTileRows + row) * ng + g);
+        };
+        uint64_t din_next = fetch_bits(cluster_id, 0, 0);
+
         for (int64_t q = cluster_id; q < n_quads; q += n_clusters) {
             const int64_t tq = (q - cluster_id) / n_clusters;
-            for (int l = 0; l < L; ++l) {
+            for (int l = 0; l < L; sj += p.L[l].out_blocked ? 1u : 0u, ++l, ++jn) {
                 const StackLayerDev Ld = p.L[l];
                 const int ngroups = (Ld.N + 63) >> 6;
                 const bool last = l == L - 1;
                 const bool to_act = !last || Ld.out_blocked != nullptr;
                 const bool mine = g < ngroups;
+                const bool fast = to_act && !Ld.out_f32 && (g + 1) * 64 <= Ld.N && (RELU || !Ld.bits_in);
                 float *vec = vec_s + l * 256;
-#pragma unroll
+                const uint32_t vec_sa = vec0_s + (uint32_t)l * 1024u;
+#pragma unroll 1
                 for (int s = 0; s < 2; ++s) {
                     const int64_t tile = 4 * q + 2 * s + rank;
                     const bool valid = tile < p.n_tiles;
                     const int64_t grow = tile * kTileRows + row;
                     const bool tr = p.trace && blockIdx.x < 2 && tq < 4 && ew == 0 && lane == 0;
-                    uint64_t din = 0;
-                    if (Ld.bits_in && valid && mine) din = Ld.bits_in[grow * ngroups + g];
-                    mbar_wait(&acc_full[s], (uint32_t)(je[s] & 1));
+                    const uint64_t din = din_next;
+                    {
+                        int ln = l + s;
+                        int64_t qn = q;
+                        if (ln == L) { ln = 0; qn += n_clusters; }
+                        din_next = fetch_bits(qn, ln, s ^ 1);
+                    }
+                    mbar_wait(&acc_full[s], jn & 1);
                     tc_fence_after();
                     if (tr) p.trace[((tq * 16 + l) * 2 + s) * 8 + 2 + 3 * rank] = clock64();
                     if (mine) {
-                        uint8_t *blk = act + s * kSlotBytes + g * kBlockBytes;
-                        if (store_pending[s] && to_act) {      // the TMA store issued from this block one job ago must have read it
-                            if (sthr == 0) bulk_wait_read<0>();
-                            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-                            store_pending[s] = false;
-                        }
+                        const uint32_t blk_s = blk0_s + (uint32_t)s * kSlotBytes;
+                        const uint32_t taddr = tmem_base + lane_base + s * 256 + g * 64;
+                        if (sj > 0 && to_act) mbar_wait(&st_done[s], (sj - 1) & 1);      // the writer has read this slot's last stashed tile
                         uint64_t dout = 0;
+                        if (fast) {
+                            // hidden layer, all 64 columns live: TMEM -> math -> bf16 -> this row's eight 16-byte chunks
 #pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const int col0 = g * 64 + h * 32;
-                            if (col0 >= Ld.N) {
+                            for (int h = 0; h < 2; ++h) {
+                                uint32_t v[32], w[16];
+                                tmem_ld32(taddr + h * 32, v);
+                                tmem_ld_wait();
+                                if (Ld.bits_in) {
+                                    mask_pack_relu32(v, (uint32_t)(din >> (32 * h)), w);
+                                } else if (RELU && Ld.act) {
+                                    uint32_t bits;
+                                    if (Ld.bits_out) bits = bias_relu_pack32<true>(v, vec_sa + h * 128, w);
+                                    else bits = bias_relu_pack32<false>(v, vec_sa + h * 128, w);
+                                    dout |= (uint64_t)bits << (32 * h);
+                                } else {
+                                    uint32_t bits = 0;
+                                    if (Ld.bits_out) epilogue_math32<EPI_BIAS_ACT_BITS, RELU>(v, vec_sa + h * 128, p.slope, 0, bits);
+                                    else if (Ld.act) epilogue_math32<EPI_BIAS_ACT, RELU>(v, vec_sa + h * 128, p.slope, 0, bits);
+                                    else if (Ld.bias) epilogue_math32<EPI_BIAS, RELU>(v, vec_sa + h * 128, p.slope, 0, bits);
+                                    dout |= (uint64_t)bits << (32 * h);
+#pragma unroll
+                                    for (int k = 0; k < 16; ++k) w[k] = pack_bf16(__uint_as_float(v[2 * k]), __uint_as_float(v[2 * k + 1]));
+                                }
+#pragma unroll
+                                for (int c = 0; c < 4; ++c)
+                                    sts_v4(blk_s + row_s + ((((uint32_t)(h * 4 + c)) ^ sw) << 4), w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+                            }
+                        } else {
+#pragma unroll 1
+                            for (int h = 0; h < 2; ++h) {
+                                const int col0 = g * 64 + h * 32;
+                                if (col0 >= Ld.N) {
+                                    if (to_act) {
+#pragma unroll
+                                        for (int c = 0; c < 4; ++c) sts_v4(blk_s + row_s + ((((uint32_t)(h * 4 + c)) ^ sw) << 4), 0, 0, 0, 0);
+                                    }
+                                    continue;
+                                }
+                                uint32_t v[32];
+                                tmem_ld32(taddr + h * 32, v);
+                                tmem_ld_wait();
+                                uint32_t bits = 0;
+                                const uint32_t dh = (uint32_t)(din >> (32 * h));
+                                if (Ld.bits_in) epilogue_math32<EPI_MASK, RELU>(v, vec_sa + h * 128, p.slope, dh, bits);
+                                else if (Ld.bits_out) epilogue_math32<EPI_BIAS_ACT_BITS, RELU>(v, vec_sa + h * 128, p.slope, 0, bits);
+                                else if (Ld.act) epilogue_math32<EPI_BIAS_ACT, RELU>(v, vec_sa + h * 128, p.slope, 0, bits);
+                                else if (Ld.bias) epilogue_math32<EPI_BIAS, RELU>(v, vec_sa + h * 128, p.slope, 0, bits);
+                                dout |= (uint64_t)bits << (32 * h);
+                                if (Ld.out_f32 && valid) {
+                                    float4 *dst = reinterpret_cast<float4 *>(Ld.out_f32 + grow * Ld.ld_f32 + col0);
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j)
+                                        dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                                }
                                 if (to_act) {
 #pragma unroll
                                     for (int c = 0; c < 4; ++c)
-                                        *reinterpret_cast<uint4 *>(blk + row * 128 + (((h * 4 + c) ^ (row & 7)) << 4)) = make_uint4(0, 0, 0, 0);
-                                }
-                                continue;
-                            }
-                            uint32_t v[32];
-                            tmem_ld32(tmem_base + lane_base + s * 256 + col0, v);
-                            tmem_ld_wait();
-                            uint32_t bits = 0;
-                            const uint32_t dh = (uint32_t)(din >> (32 * h));
-                            if (Ld.bits_in) epilogue_math<EPI_MASK>(v, vec, col0, p.slope, dh, bits);
-                            else if (Ld.bits_out) epilogue_math<EPI_BIAS_ACT_BITS>(v, vec, col0, p.slope, 0, bits);
-                            else if (Ld.act) epilogue_math<EPI_BIAS_ACT>(v, vec, col0, p.slope, 0, bits);
-                            else if (Ld.bias) epilogue_math<EPI_BIAS>(v, vec, col0, p.slope, 0, bits);
-                            dout |= (uint64_t)bits << (32 * h);
-                            if (Ld.out_f32 && valid) {
-                                float4 *dst = reinterpret_cast<float4 *>(Ld.out_f32 + grow * Ld.ld_f32 + col0);
-#pragma unroll
-                                for (int j = 0; j < 8; ++j)
-                                    dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-                            }
-                            if (to_act) {
-#pragma unroll
-                                for (int c = 0; c < 4; ++c) {
-                                    const uint4 qv = make_uint4(pack_bf16(__uint_as_float(v[8 * c]), __uint_as_float(v[8 * c + 1])),
-                                                                pack_bf16(__uint_as_float(v[8 * c + 2]), __uint_as_float(v[8 * c + 3])),
-                                                                pack_bf16(__uint_as_float(v[8 * c + 4]), __uint_as_float(v[8 * c + 5])),
-                                                                pack_bf16(__uint_as_float(v[8 * c + 6]), __uint_as_float(v[8 * c + 7])));
-                                    *reinterpret_cast<uint4 *>(blk + row * 128 + (((h * 4 + c) ^ (row & 7)) << 4)) = qv;
+                                        sts_v4(blk_s + row_s + ((((uint32_t)(h * 4 + c)) ^ sw) << 4),
+                                               pack_bf16(__uint_as_float(v[8 * c]), __uint_as_float(v[8 * c + 1])),
+                                               pack_bf16(__uint_as_float(v[8 * c + 2]), __uint_as_float(v[8 * c + 3])),
+                                               pack_bf16(__uint_as_float(v[8 * c + 4]), __uint_as_float(v[8 * c + 5])),
+                                               pack_bf16(__uint_as_float(v[8 * c + 6]), __uint_as_float(v[8 * c + 7])));
                                 }
                             }
                         }
                         if (Ld.bits_out && valid) Ld.bits_out[grow * ngroups + g] = dout;
                         if (to_act) fence_proxy_async();      // generic-proxy tile writes -> visible to tcgen05.mma / TMA store
-                        if (to_act && (Ld.out_blocked || Ld.colsum)) {
+                        if (to_act && Ld.colsum) {
                             asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-                            if (sthr == 0 && valid && Ld.out_blocked) {
-                                bulk_s2g(Ld.out_blocked + ((size_t)tile * ngroups + g) * kBlockBytes, blk, kBlockBytes);
-                                bulk_commit();
-                            }
-                            if (Ld.colsum && valid) {
-                                const int qq = sthr >> 5, ll = sthr & 31;
+                            if (valid) {
+                                // thread (qq, ll) adds up columns 2*ll, 2*ll+1 over rows [32*qq, 32*qq+32) of the bf16 tile
+                                const uint32_t qq = (uint32_t)sthr >> 5, ll = (uint32_t)sthr & 31u;
+                                const uint32_t cbase = blk_s + qq * 4096u + (ll & 3u) * 4u;
                                 float s0 = 0.f, s1 = 0.f;
 #pragma unroll 8
-                                for (int r = qq * 32; r < qq * 32 + 32; ++r) {
-                                    const uint32_t w2 = *reinterpret_cast<const uint32_t *>(blk + r * 128 + (((ll >> 2) ^ (r & 7)) << 4) + (ll & 3) * 4);
+                                for (uint32_t r = 0; r < 32; ++r) {
+                                    uint32_t w2;
+                                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w2) : "r"(cbase + r * 128u + (((ll >> 2) ^ (r & 7u)) << 4)));
                                     s0 += bf16_lo(w2); s1 += bf16_hi(w2);
                                 }
                                 atomicAdd(&vec[g * 64 + 2 * ll], s0);
                                 atomicAdd(&vec[g * 64 + 2 * ll + 1], s1);
                             }
-                            if (Ld.out_blocked) store_pending[s] = true;
                         }
                     }
                     if (tr) p.trace[((tq * 16 + l) * 2 + s) * 8 + 3 + 3 * rank] = clock64();
                     tc_fence_before();
-                    if (last && store_pending[s]) {            // the slot is about to be refilled by the producer
-                        if (sthr == 0) bulk_wait_read<0>();
-                        store_pending[s] = false;
-                    }
                     __syncwarp();
                     if (lane == 0) {
+                        if (Ld.out_blocked) mbar_arrive(&st_ready[s]);
                         if (last) mbar_arrive(&in_free[s]);
                         if (rank == 0) mbar_arrive(&act_ready[s]); else mbar_arrive_remote(&act_ready[s], 0);
                     }
                     if (tr) p.trace[((tq * 16 + l) * 2 + s) * 8 + 4 + 3 * rank] = clock64();
-                    ++je[s];
                 }
             }
         }
-        if (sthr == 0) bulk_wait<0>();
         asm volatile("bar.sync 5, 512;" ::: "memory");
         for (int i = threadIdx.x - 128; i < L * 256; i += 512) {
             const int l = i >> 8, c = i & 255;
@@ -322,6 +418,7 @@ extern "C" int papr_stack_bf16(const void *x, int K0, const papr_stack_layer *la
     StackParams p;
     p.x = (const uint8_t *)x; p.n_tiles = rows / kTileRows; p.n_layers = n_layers; p.kblk0 = (K0 + 63) / 64; p.slope = slope;
     p.any_stash = 0;
+    { static int depth = -1; if (depth < 0) { const char *e = getenv("PAPR_STACK_STORE_DEPTH"); depth = e ? atoi(e) : 2; } p.store_depth = depth; }
     p.trace = g_stack_trace;
     int K = K0;
     for (int l = 0; l < n_layers; ++l) {
@@ -350,11 +447,13 @@ extern "C" int papr_stack_bf16(const void *x, int K0, const papr_stack_layer *la
     const int smem = fixed + p.stages * kStageBytes;
     static bool attr_set = false;
     if (!attr_set) {
-        PAPR_CUDA_TRY(cudaFuncSetAttribute(stack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStkMaxSmem));
+        PAPR_CUDA_TRY(cudaFuncSetAttribute(stack_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStkMaxSmem));
+        PAPR_CUDA_TRY(cudaFuncSetAttribute(stack_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStkMaxSmem));
         attr_set = true;
     }
     const int64_t n_quads = (p.n_tiles + 3) / 4;
     const int grid = (int)(2 * (n_quads < kNumSMs / 2 ? n_quads : kNumSMs / 2));
-    stack_kernel<<<grid, kStkThreads, smem, (cudaStream_t)stream>>>(p);
+    if (slope == 0.f) stack_kernel<true><<<grid, kStkThreads, smem, (cudaStream_t)stream>>>(p);
+    else stack_kernel<false><<<grid, kStkThreads, smem, (cudaStream_t)stream>>>(p);
     return check_launch();
 }

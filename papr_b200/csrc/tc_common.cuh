@@ -78,6 +78,14 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols)
 {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
 }
+// one lane of the (fully active) warp; the compiler knows a single thread runs the guarded code, so register operands of
+// tcgen05.mma / cp.async.bulk move to uniform registers without a per-instruction broadcast loop
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred = 0;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\t@P mov.s32 %0, 1;\n\t}" : "+r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -200,20 +208,23 @@ __device__ __forceinline__ float4 lds_f4(uint32_t saddr)
 
 // 32 accumulator columns of one row: bias (from shared memory at bias_saddr), activation, sign bits / derivative mask.
 // RELU: negative slope is exactly 0 (max(t,0)); otherwise leaky with 0 <= slope <= 1 (max(t, slope*t)).
+// Sign bits: bit j = 1 when the pre-activation of column j has its IEEE sign bit clear (t > 0, or t == +0), gathered with
+// one funnel shift per element (columns walked from 31 down to 0, each pushing its sign into the low end).
 template <int EPI, bool RELU>
 __device__ __forceinline__ void epilogue_math32(uint32_t (&v)[32], uint32_t bias_saddr, float slope, uint32_t din, uint32_t &dout)
 {
     constexpr bool kBias = EPI == EPI_BIAS || EPI == EPI_BIAS_ACT || EPI == EPI_BIAS_ACT_BITS;
+    uint32_t neg = 0;
 #pragma unroll
-    for (int j4 = 0; j4 < 8; ++j4) {
+    for (int j4 = 7; j4 >= 0; --j4) {
         float b[4] = {0.f, 0.f, 0.f, 0.f};
         if (kBias) { const float4 q = lds_f4(bias_saddr + j4 * 16); b[0] = q.x; b[1] = q.y; b[2] = q.z; b[3] = q.w; }
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
+        for (int e = 3; e >= 0; --e) {
             const int j = j4 * 4 + e;
             float t = __uint_as_float(v[j]);
             if (kBias) t += b[e];
-            if (EPI == EPI_BIAS_ACT_BITS) { if (t > 0.f) dout |= 1u << j; }
+            if (EPI == EPI_BIAS_ACT_BITS) neg = __funnelshift_l(__float_as_uint(t), neg, 1);
             if (EPI == EPI_BIAS_ACT || EPI == EPI_BIAS_ACT_BITS) t = RELU ? fmaxf(t, 0.f) : fmaxf(t, t * slope);
             if (EPI == EPI_MASK) {
                 if (RELU) t = __uint_as_float(__float_as_uint(t) & (uint32_t)((int32_t)(din << (31 - j)) >> 31));
@@ -222,6 +233,7 @@ __device__ __forceinline__ void epilogue_math32(uint32_t (&v)[32], uint32_t bias
             v[j] = __float_as_uint(t);
         }
     }
+    if (EPI == EPI_BIAS_ACT_BITS) dout |= ~neg;
 }
 
 template <int EPI>
@@ -237,6 +249,57 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi)
 {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t *>(&v);
+}
+// two fp32 -> packed bf16 pair (lo in bits 0-15) with negative results clamped to +0: relu costs nothing extra
+__device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi)
+{
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+// hidden-layer forward epilogue for 32 columns, relu flavour: w[k] = bf16x2(relu(v[2k] + b[2k]), relu(v[2k+1] + b[2k+1]));
+// returns the sign-clear bits of the pre-activations (see epilogue_math32) when BITS
+template <bool BITS>
+__device__ __forceinline__ uint32_t bias_relu_pack32(const uint32_t (&v)[32], uint32_t bias_saddr, uint32_t (&w)[16])
+{
+    uint32_t neg = 0;
+#pragma unroll
+    for (int j4 = 7; j4 >= 0; --j4) {
+        const float4 q = lds_f4(bias_saddr + j4 * 16);
+        const float t0 = __uint_as_float(v[4 * j4]) + q.x, t1 = __uint_as_float(v[4 * j4 + 1]) + q.y;
+        const float t2 = __uint_as_float(v[4 * j4 + 2]) + q.z, t3 = __uint_as_float(v[4 * j4 + 3]) + q.w;
+        if (BITS) {
+            neg = __funnelshift_l(__float_as_uint(t3), neg, 1);
+            neg = __funnelshift_l(__float_as_uint(t2), neg, 1);
+            neg = __funnelshift_l(__float_as_uint(t1), neg, 1);
+            neg = __funnelshift_l(__float_as_uint(t0), neg, 1);
+        }
+        w[2 * j4] = pack_bf16_relu(t0, t1);
+        w[2 * j4 + 1] = pack_bf16_relu(t2, t3);
+    }
+    return ~neg;
+}
+__device__ __forceinline__ void sts_v4(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// relu'(.) mask applied to 32 columns while they are packed to bf16: w[k] = bf16x2(v[2k], v[2k+1]) with each half kept
+// where its bit of `din` is set and zeroed where it is clear.  Eight shifted copies of din put every bit at the top of
+// some byte; prmt's sign-replicate mode (selector bit 3) then expands two of those bytes into one 16|16-bit mask word.
+__device__ __forceinline__ void mask_pack_relu32(const uint32_t (&v)[32], uint32_t din, uint32_t (&w)[16])
+{
+    uint32_t sh[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) sh[t] = din << t;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const int j0 = 2 * k, j1 = 2 * k + 1;
+        const int t0 = 7 - (j0 & 7), m0 = j0 >> 3, t1 = 7 - (j1 & 7), m1 = j1 >> 3;
+        const uint32_t sel = (uint32_t)((8 | m0) * 0x11) | ((uint32_t)((8 | (4 + m1)) * 0x11) << 8);
+        uint32_t mask;
+        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(mask) : "r"(sh[t0]), "r"(sh[t1]), "r"(sel));
+        w[k] = pack_bf16(__uint_as_float(v[j0]), __uint_as_float(v[j1])) & mask;
+    }
 }
 __device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }

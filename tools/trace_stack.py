@@ -12,7 +12,7 @@ for i in range(L):
     w = torch.randn(256, 256, device="cuda") / 16
     layers.append(dict(w_image=ops.pack_weight(w, 256, 256, replicas=int(os.environ.get('REPS', 1))), N=256, bias=torch.zeros(256, device="cuda"), act=i < L - 1,
                        out_blocked=ops.Blocked(rows, 256, "cuda") if (stash or i == L - 1) else None))
-buf = torch.zeros(4 * 16 * 2 * 8 + 64, dtype=torch.int64, device="cuda")
+buf = torch.zeros(4096, dtype=torch.int64, device="cuda")
 h = lib(); fn = getattr(ctypes.CDLL(h._name), "papr_debug_stack_trace"); fn.argtypes = [ctypes.c_void_p]
 for _ in range(2): ops.stack_bf16(x, 256, layers)
 fn(buf.data_ptr())
@@ -21,11 +21,11 @@ e0.record(); ops.stack_bf16(x, 256, layers); e1.record(); torch.cuda.synchronize
 fn(None)
 ms = e0.elapsed_time(e1)
 print(f"kernel {ms:.3f} ms for {rows // 128 * L} tile-layers -> {ms * 1e-3 * 1.9e9 / (rows // 128 * L / 148):.0f} cycles/tile-layer/SM (at 1.9 GHz)")
-t = buf.cpu()[:1024].reshape(4, 16, 2, 8)
+t = buf.cpu()[:1024].reshape(4, 16, 2, 8); tw = buf.cpu()[2048:2048 + 256].reshape(4, 16, 2, 2); tc = buf.cpu()[3072:3072 + 128].reshape(4, 16, 2)
 t0 = int(t[0, 0, 0, 0])
 print("quad layer slot | mma_start mma_commit(issue) | L:epi_start epi_done arrived | P:epi_start epi_done arrived   (cycles since first MMA start)")
 for q in range(2):
     for l in range(L):
         for s in range(2):
             r = [int(v) - t0 if int(v) else -1 for v in t[q, l, s]]
-            print(f"{q} {l} {s} | {r[0]:7d} {r[1]:7d} | {r[2]:7d} {r[3]:7d} {r[4]:7d} | {r[5]:7d} {r[6]:7d} {r[7]:7d}")
+            print(f"{q} {l} {s} | {r[0]:7d} {r[1]:7d} | {r[2]:7d} {r[3]:7d} {r[4]:7d} | {r[5]:7d} {r[6]:7d} {r[7]:7d} | waits {int(tw[q, l, s, 0]):5d} mma-issue {int(tw[q, l, s, 1]):5d} commit {int(tc[q, l, s]):5d}")
