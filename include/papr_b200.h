@@ -83,7 +83,7 @@ int papr_pack_weight(const float *w, int64_t ld, int src_rows, int src_cols, int
  * One Linear layer, replaces nn.Linear + activation inside models/mlp.py:53-58 (and w_k/w_q of attn.py:217-218):
  *   Y = act(X W^T + bias)    X: tile-blocked bf16 [rows, ceil(K/64)*64];  fp32 accumulation in TMEM.
  * Outputs (any combination): y_blocked tile-blocked bf16 [rows, ceil(N/64)*64]; y_f32 fp32 row-major (ldy);
- * sign_bits_out [rows, ceil(N/64)] u64, bit j of word g = (pre-activation column 64g+j > 0);
+ * sign_bits_out [rows, ceil(N/64)] u64, bit j of word g = 1 when the pre-activation of column 64g+j has its sign bit clear (> 0, or exactly +0);
  * colsum[N] += column sums of the bf16 output (bias gradients).
  * Backward use (dgrad): X = dZ, weight image packed with transpose=1, sign_bits_in = the forward layer's sign bits:
  * output column j is multiplied by 1 (bit set) or `slope` (bit clear), i.e. by act'(.) of relu/leakyrelu.
