@@ -34,7 +34,8 @@ constexpr int kStkThreads = 640;     // 4 control warps + 2 x 8 epilogue warps
 constexpr int kStkMaxLayers = 8;
 constexpr int kSlotBytes = 4 * kBlockBytes;      // one 128 x 256 bf16 tile
 constexpr int kStkMaxSmem = 232448;
-constexpr int kStageBytes = 2 * kBlockBytes;    // weight-ring stage: K = 128 per barrier round trip (8 MMAs)
+constexpr int kStageBlocks = 1;                  // 64-wide K blocks per weight-ring stage (4 MMAs each)
+constexpr int kStageBytes = kStageBlocks * kBlockBytes;
 
 struct StackLayerDev {
     const uint8_t *w;          // weight image [kblk][N rows][128 B]
@@ -116,8 +117,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kStkThreads, 1) stac
                                          kBlockBytes, &in_full[s]);
                         }
                         const uint8_t *wsrc = Ld.w + (size_t)(cluster_id % Ld.w_reps) * Ld.w_rep_stride + (size_t)rank * chunk_bytes;
-                        for (int kc = 0; kc < Ld.kblk; kc += 2) {
-                            const int nc = min(2, Ld.kblk - kc);
+                        for (int kc = 0; kc < Ld.kblk; kc += kStageBlocks) {
+                            const int nc = min(kStageBlocks, Ld.kblk - kc);
                             mbar_wait(&w_empty[st], ph ^ 1);
                             mbar_arrive_expect_tx(&w_full[st], chunk_bytes * nc);
                             for (int c = 0; c < nc; ++c)
@@ -168,7 +169,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kStkThreads, 1) stac
                 for (int l = 0; l < L; ++l) {
                     for (int s = 0; s < 2; ++s) {
                         if (l == 0) { mbar_wait(&in_full[s], (uint32_t)(qi & 1)); mbar_arrive_remote(&pin_full[s], 0); }
-                        for (int kc = 0; kc < p.L[l].kblk; kc += 2) {
+                        for (int kc = 0; kc < p.L[l].kblk; kc += kStageBlocks) {
                             mbar_wait(&w_full[st], ph);
                             mbar_arrive_remote(&pw_full[st], 0);
                             if (++st == p.stages) { st = 0; ph ^= 1; }
@@ -201,18 +202,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kStkThreads, 1) stac
                         const uint64_t a_desc0 = umma_desc(a_base + s * kSlotBytes, 16, 1024);
                         uint32_t acc = 0;
 #pragma unroll 1
-                        for (int kc = 0; kc < kblk; kc += 2) {
+                        for (int kc = 0; kc < kblk; kc += kStageBlocks) {
                             mbar_wait(&w_full[st], ph);
                             mbar_wait_cluster(&pw_full[st], ph);
                             tc_fence_after();
                             // a K step of 16 bf16 = 32 B = +2 in the descriptor's address field; a 64-wide block = 16 KB
                             const uint64_t ad = a_desc0 + (uint64_t)(kc * (kBlockBytes >> 4));
                             const uint64_t bd = umma_desc(ring_base + st * kStageBytes, 16, 1024);
-                            const int nk = min(8, k_steps - 4 * kc);
+                            const int nk = min(4 * kStageBlocks, k_steps - 4 * kc);
                             if (elect_one()) {
-                                if (nk == 8) {
+                                if (nk == 4 * kStageBlocks) {
 #pragma unroll
-                                    for (int k = 0; k < 8; ++k) {
+                                    for (int k = 0; k < 4 * kStageBlocks; ++k) {
                                         const uint32_t off = (uint32_t)((k >> 2) * (kBlockBytes >> 4) + 2 * (k & 3));
                                         umma2_bf16(d, ad + off, bd + off, idesc, k ? 1u : acc);
                                     }
