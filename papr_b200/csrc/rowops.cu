@@ -346,7 +346,7 @@ __device__ __forceinline__ float half_sum(float v)      // sum over the 16 lanes
 
 // Each half-warp owns one (ray, candidate) row per iteration: 16 lanes x 8 columns cover the (<=128-wide) key input,
 // one 16-byte chunk per lane; the value input takes one or two chunks per lane.
-__global__ void __launch_bounds__(kRowThreads) attn_prologue_fwd_fast_kernel(const PrologueParams p)
+__global__ void __launch_bounds__(kRowThreads, 3) attn_prologue_fwd_fast_kernel(const PrologueParams p)
 {
     __shared__ float pe_s[kRowWarps][2][kMaxDk];
     __shared__ float geo_s[kRowWarps][32][9];
@@ -446,7 +446,7 @@ __global__ void __launch_bounds__(kRowThreads) attn_prologue_fwd_fast_kernel(con
     }
 }
 
-__global__ void __launch_bounds__(kRowThreads) attn_prologue_bwd_fast_kernel(const PrologueParams p)
+__global__ void __launch_bounds__(kRowThreads, 3) attn_prologue_bwd_fast_kernel(const PrologueParams p)
 {
     __shared__ float pe_s[kRowWarps][2][kMaxDk];      // pe values
     __shared__ float dpe_s[kRowWarps][2][kMaxDk];     // d pe (LayerNorm backward + value-stack gradient)
@@ -623,10 +623,18 @@ __global__ void __launch_bounds__(kRowThreads) score_blend_fwd_kernel(const Scor
         }
         const float cp = p.cprime[ray];
         float my_sc = 0.f;
+        // bf16 rows are fetched one candidate ahead (4 registers) so the HBM latency overlaps the three warp reductions
+        uint4 nxt = make_uint4(0, 0, 0, 0);
+        if (!p.h5_f32) nxt = *reinterpret_cast<const uint4 *>(p.h5 + blocked_chunk_offset(ray * p.K, lane, 4));
         for (int k = 0; k < p.K; ++k) {
             const int64_t row = ray * p.K + k;
             float h[8], s = 0.f;
-            load_row8(p, row, lane, h);
+            if (p.h5_f32) load_row8(p, row, lane, h);
+            else {
+                const uint4 cur = nxt;
+                if (k + 1 < p.K) nxt = *reinterpret_cast<const uint4 *>(p.h5 + blocked_chunk_offset(row + 1, lane, 4));
+                unpack8(cur, h);
+            }
 #pragma unroll
             for (int e = 0; e < 8; ++e) s += h[e];
             const float mean = warp_sum(s) * (1.f / 256.f);
@@ -751,12 +759,20 @@ __global__ void __launch_bounds__(kRowThreads) key_score_bwd_kernel(const ScoreP
         for (int e = 0; e < 8; ++e) { uas += ua[e]; zs[e] = 0.f; }
         const float ua_mean = warp_sum(uas) * (1.f / 256.f);
         float dss = 0.f;
+        uint4 nxt = make_uint4(0, 0, 0, 0);
+        if (!p.h5_f32) nxt = *reinterpret_cast<const uint4 *>(p.h5 + blocked_chunk_offset(ray * p.K, lane, 4));
+        float ds_n = p.d_score_in[ray * p.K], mean_n = p.stats[ray * p.K * 2], rstd_n = p.stats[ray * p.K * 2 + 1];
         for (int k = 0; k < p.K; ++k) {
             const int64_t row = ray * p.K + k;
-            const float ds = p.d_score_in[row];
-            const float mean = p.stats[row * 2], rstd = p.stats[row * 2 + 1];
+            const float ds = ds_n, mean = mean_n, rstd = rstd_n;
             float h[8], y[8], dot = 0.f;
-            load_row8(p, row, lane, h);
+            if (p.h5_f32) load_row8(p, row, lane, h);
+            else {
+                const uint4 cur = nxt;
+                if (k + 1 < p.K) nxt = *reinterpret_cast<const uint4 *>(p.h5 + blocked_chunk_offset(row + 1, lane, 4));
+                unpack8(cur, h);
+            }
+            if (k + 1 < p.K) { ds_n = p.d_score_in[row + 1]; mean_n = p.stats[row * 2 + 2]; rstd_n = p.stats[row * 2 + 3]; }
 #pragma unroll
             for (int e = 0; e < 8; ++e) { y[e] = (h[e] - mean) * rstd; dot += y[e] * ua[e]; }
             dot = warp_sum(dot);
