@@ -88,47 +88,58 @@ select_topk2_kernel(const float *__restrict__ rays_o, const float *__restrict__ 
         dx[j] = d[0]; dy[j] = d[1]; dz[j] = d[2];
         thr[j] = INF; lk[j] = INF; li[j] = -1;
     }
-    float wmax = 0.f;
+    float wmax = 0.f;                 // max |v|^2 over the points this thread staged (reduced over the block below)
 
     for (int base = 0; base < P; base += kSelTile) {
         const int count = min(kSelTile, P - base);
+        const int cpad = (count + 31) & ~31;
         __syncthreads();
-        for (int i = threadIdx.x; i < count; i += kSelThreads) {
-            const float *p = points + (int64_t)(base + i) * 3;
-            const float vx = __fsub_rn(p[0], ox), vy = __fsub_rn(p[1], oy), vz = __fsub_rn(p[2], oz);
-            tile[i] = make_float4(vx, vy, vz, fmaf(vz, vz, fmaf(vy, vy, vx * vx)));
+        for (int i = threadIdx.x; i < cpad; i += kSelThreads) {
+            if (i < count) {
+                const float *p = points + (int64_t)(base + i) * 3;
+                const float vx = __fsub_rn(p[0], ox), vy = __fsub_rn(p[1], oy), vz = __fsub_rn(p[2], oz);
+                const float w = fmaf(vz, vz, fmaf(vy, vy, vx * vx));
+                wmax = fmaxf(wmax, w);
+                tile[i] = make_float4(vx, vy, vz, eps * w);
+            } else {
+                tile[i] = make_float4(0.f, 0.f, 0.f, INF);         // padding: cheap key = +inf, never below a threshold
+            }
         }
         __syncthreads();
-        for (int c = 0; c < count; c += 32) {
-            const int pi = c + lane;
-            const bool valid = pi < count;
-            const float4 v = tile[valid ? pi : 0];
-            const int pidx = base + pi;
-            const float ew = eps * v.w;
-            wmax = fmaxf(wmax, v.w);
+        for (int c = 0; c < cpad; c += 32) {
+            const float4 v = tile[c + lane];
+            const int pidx = base + c + lane;
 #pragma unroll
             for (int j = 0; j < RPW; ++j) {
                 const float cx = fmaf(v.y, dz[j], -v.z * dy[j]);
                 const float cy = fmaf(v.z, dx[j], -v.x * dz[j]);
                 const float cz = fmaf(v.x, dy[j], -v.y * dx[j]);
-                float a = fmaf(cx, cx, fmaf(cy, cy, fmaf(cz, cz, ew)));
-                if (!valid) a = INF;
-                unsigned m = __ballot_sync(full, a < thr[j]);
-                while (m) {
-                    const int src = __ffs(m) - 1;
-                    m &= m - 1;
-                    const float ck = __shfl_sync(full, a, src);
-                    const int ci = __shfl_sync(full, pidx, src);
-                    if (ck < thr[j]) thr[j] = list_insert(lk[j], li[j], ck, ci, lane, 31);
+                const float a = fmaf(cx, cx, fmaf(cy, cy, fmaf(cz, cz, v.w)));
+                if (__any_sync(full, a < thr[j])) {
+                    unsigned m = __ballot_sync(full, a < thr[j]);
+                    while (m) {
+                        const int src = __ffs(m) - 1;
+                        m &= m - 1;
+                        const float ck = __shfl_sync(full, a, src);
+                        const int ci = __shfl_sync(full, pidx, src);
+                        if (ck < thr[j]) thr[j] = list_insert(lk[j], li[j], ck, ci, lane, 31);
+                    }
                 }
             }
         }
     }
-    wmax = fmaxf(wmax, __shfl_xor_sync(full, wmax, 16));
-    wmax = fmaxf(wmax, __shfl_xor_sync(full, wmax, 8));
-    wmax = fmaxf(wmax, __shfl_xor_sync(full, wmax, 4));
-    wmax = fmaxf(wmax, __shfl_xor_sync(full, wmax, 2));
-    wmax = fmaxf(wmax, __shfl_xor_sync(full, wmax, 1));
+    {
+        __shared__ float wred[kSelWarps];
+        wmax = fmaxf(wmax, __shfl_xor_sync(full, wmax, 16));
+        wmax = fmaxf(wmax, __shfl_xor_sync(full, wmax, 8));
+        wmax = fmaxf(wmax, __shfl_xor_sync(full, wmax, 4));
+        wmax = fmaxf(wmax, __shfl_xor_sync(full, wmax, 2));
+        wmax = fmaxf(wmax, __shfl_xor_sync(full, wmax, 1));
+        if (lane == 0) wred[warp] = wmax;
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < kSelWarps; ++i) wmax = fmaxf(wmax, wred[i]);
+    }
 
     // ---- phase 2: exact keys of the candidates, rank, safety test, (rare) exact rescan
 #pragma unroll
