@@ -741,7 +741,7 @@ __global__ void __launch_bounds__(kRowThreads) blend_bwd_kernel(const ScoreParam
         *reinterpret_cast<uint4 *>(p.dv + blocked_chunk_offset(M + i / (nblk * 8), (int)(i % (nblk * 8)), nblk)) = make_uint4(0, 0, 0, 0);
 }
 
-__global__ void __launch_bounds__(kRowThreads) key_score_bwd_kernel(const ScoreParams p)
+__global__ void __launch_bounds__(kRowThreads, 4) key_score_bwd_kernel(const ScoreParams p)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float acc_b5[8];
