@@ -446,6 +446,148 @@ __global__ void __launch_bounds__(kRowThreads, 3) attn_prologue_fwd_fast_kernel(
     }
 }
 
+// One (ray, candidate) row per LANE (the default shape L = 6, F = 64: 117-wide key input, 142-wide value input).  The
+// half-warp-per-row kernel above spends ~280 warp instructions per row because only 9 of 16 lanes build the positional
+// encoding and every column costs shuffles / shared-memory hops; here a lane carries its row in registers (9 sincos,
+// double-angle recurrences, one statistics pass, one emitting pass with compile-time column indices): ~55 warp
+// instructions per row.  A warp stages its 32 rows -- 32 x 128 B per 64-column block, already in the tile-blocked
+// swizzle -- in shared memory and copies each 4 KB piece out with fully coalesced 16-byte stores.
+template <int L, int F>
+__global__ void __launch_bounds__(kRowThreads, 1) attn_prologue_fwd_rows_kernel(const PrologueParams p)
+{
+    constexpr int S = 1 + 2 * L, DK = 9 * S, DPE = 6 * S, DV = DPE + F;
+    constexpr int NBK = (DK + 63) / 64, NBV = (DV + 63) / 64;
+    extern __shared__ __align__(16) uint8_t rows_stage[];
+    __shared__ float2 ab_s[DK];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int j = threadIdx.x; j < DK; j += kRowThreads) ab_s[j] = make_float2(p.a2[j], p.b2[j]);
+    __syncthreads();
+    const uint32_t wst = smem_u32(rows_stage) + (uint32_t)warp * (NBK + NBV) * 4096u;
+    const uint32_t my = wst + (uint32_t)lane * 128u;
+    const uint32_t sw = (uint32_t)lane & 7u;
+    const int64_t M = p.R * p.K, M_pad = (M + 127) / 128 * 128;
+
+    for (int64_t row0 = ((int64_t)blockIdx.x * kRowWarps + warp) * 32; row0 < M_pad; row0 += (int64_t)gridDim.x * kRowWarps * 32) {
+        const int64_t row = row0 + lane;
+        const bool live = row < M;
+        float g[9];
+        int pidx = 0;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) g[i] = 0.f;
+        if (live) {
+            const int64_t ray = row / p.K;
+            const int64_t view = ray / p.rays_per_view;
+            float u[3], den;
+            pidx = p.idx[row];
+            const Geometry geo = ray_point_geometry(p.points + (size_t)pidx * 3, p.rays_o + view * 3, p.rays_d + ray * 3, p.eps, u, &den);
+#pragma unroll
+            for (int i = 0; i < 9; ++i) g[i] = geo.g[i];
+        }
+        float s0[9], c0[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) sincosf(g[i], &s0[i], &c0[i]);
+        // statistics of the 117 key columns (model: mean, unbiased std)
+        float sum = 0.f, sq = 0.f;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            float s = s0[i], c = c0[i];
+            sum += g[i]; sq = fmaf(g[i], g[i], sq);
+#pragma unroll
+            for (int o = 0; o < L; ++o) {
+                sum += s + c; sq = fmaf(s, s, fmaf(c, c, sq));
+                const float s2 = 2.f * s * c, c2 = (c - s) * (c + s);
+                s = s2; c = c2;
+            }
+        }
+        const float mean = sum * (1.f / DK);
+        const float var = fmaxf(sq - (float)DK * mean * mean, 0.f) * (1.f / (DK - 1));
+        const float rstd = live ? 1.f / (sqrtf(var) + p.eps) : 0.f;
+        const float lv = live ? 1.f : 0.f;
+
+        // emit: columns in order; eight of them make one 16-byte chunk of the row
+        float kb[8], vb[8];
+        auto put_k = [&](int c) {        // key chunk c <- kb
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my + (uint32_t)(c >> 3) * 4096u + ((((uint32_t)c & 7u) ^ sw) << 4)),
+                         "r"(pack_bf16(kb[0], kb[1])), "r"(pack_bf16(kb[2], kb[3])), "r"(pack_bf16(kb[4], kb[5])), "r"(pack_bf16(kb[6], kb[7])) : "memory");
+        };
+        auto put_v = [&](int c) {        // value chunk c <- vb
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my + (uint32_t)(NBK + (c >> 3)) * 4096u + ((((uint32_t)c & 7u) ^ sw) << 4)),
+                         "r"(pack_bf16(vb[0], vb[1])), "r"(pack_bf16(vb[2], vb[3])), "r"(pack_bf16(vb[4], vb[5])), "r"(pack_bf16(vb[6], vb[7])) : "memory");
+        };
+#pragma unroll
+        for (int src = 0; src < 9; ++src) {
+            float s = s0[src], c = c0[src];
+#pragma unroll
+            for (int slot = 0; slot < S; ++slot) {
+                float val;
+                if (slot == 0) val = g[src];
+                else if (slot & 1) val = s;
+                else {
+                    val = c;
+                    const float s2 = 2.f * s * c, c2 = (c - s) * (c + s);
+                    s = s2; c = c2;
+                }
+                const int j = src * S + slot;
+                const float2 ab = ab_s[j];
+                kb[j & 7] = lv * fmaf((val - mean) * rstd, ab.x, ab.y);
+                if ((j & 7) == 7) put_k(j >> 3);
+                if (src >= 3) {
+                    const int jv = (src - 3) * S + slot;
+                    vb[jv & 7] = lv * val;
+                    if ((jv & 7) == 7) put_v(jv >> 3);
+                }
+            }
+        }
+        if (DK & 7) {
+#pragma unroll
+            for (int e = DK & 7; e < 8; ++e) kb[e] = 0.f;
+            put_k(DK >> 3);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) kb[e] = 0.f;
+#pragma unroll
+        for (int c = (DK + 7) >> 3; c < NBK * 8; ++c) put_k(c);
+        // point features follow the value-side encoding (model.py:396-437: cat(pe(geometry), pc_feats))
+        const float4 *fsrc = reinterpret_cast<const float4 *>(p.feats + (size_t)pidx * F);
+#pragma unroll
+        for (int f = 0; f < F; f += 4) {
+            float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (live) q = __ldg(fsrc + (f >> 2));
+            const float qq[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int jv = DPE + f + e;
+                vb[jv & 7] = qq[e];
+                if ((jv & 7) == 7) put_v(jv >> 3);
+            }
+        }
+        if (DV & 7) {
+#pragma unroll
+            for (int e = DV & 7; e < 8; ++e) vb[e] = 0.f;
+            put_v(DV >> 3);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) vb[e] = 0.f;
+#pragma unroll
+        for (int c = (DV + 7) >> 3; c < NBV * 8; ++c) put_v(c);
+        __syncwarp();
+        // copy out: the warp's 32 rows are 4 KB contiguous inside every 16 KB block of the tile
+        const int64_t tile = row0 >> 7;
+        const uint32_t roff = (uint32_t)(row0 & 127) * 128u + (uint32_t)lane * 16u;
+#pragma unroll
+        for (int b = 0; b < NBK + NBV; ++b) {
+            uint8_t *dst = (b < NBK ? p.kin + ((size_t)tile * NBK + b) * kBlockBytes : p.vin + ((size_t)tile * NBV + (b - NBK)) * kBlockBytes) + roff;
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                uint4 t;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w) : "r"(wst + (uint32_t)b * 4096u + (uint32_t)it * 512u + (uint32_t)lane * 16u));
+                *reinterpret_cast<uint4 *>(dst + it * 512) = t;
+            }
+        }
+        __syncwarp();
+    }
+}
+
 __global__ void __launch_bounds__(kRowThreads, 3) attn_prologue_bwd_fast_kernel(const PrologueParams p)
 {
     __shared__ float pe_s[kRowWarps][2][kMaxDk];      // pe values
@@ -926,7 +1068,16 @@ extern "C" int papr_attn_prologue_fwd(const float *rays_o, const float *rays_d, 
     p.nblk_k = dk_pad / 64; p.nblk_v = dv_pad / 64; p.eps = eps;
     p.kin = (uint8_t *)kin; p.vin = (uint8_t *)vin; p.kin_f32 = kin_f32; p.vin_f32 = vin_f32;
     if (kin_f32 || vin_f32) attn_prologue_fwd_kernel<<<row_grid(R), kRowThreads, 0, (cudaStream_t)stream>>>(p);
-    else attn_prologue_fwd_fast_kernel<<<row_grid(R), kRowThreads, 0, (cudaStream_t)stream>>>(p);
+    else if (L == 6 && F == 64 && p.nblk_k == 2 && p.nblk_v == 3 && !getenv("PAPR_PROLOGUE_HALFWARP")) {
+        constexpr int smem = kRowWarps * 5 * 4096;
+        static bool attr_set = false;
+        if (!attr_set) {
+            PAPR_CUDA_TRY(cudaFuncSetAttribute(attn_prologue_fwd_rows_kernel<6, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            attr_set = true;
+        }
+        const int64_t groups = ((R * K + 127) / 128 * 128 + kRowThreads - 1) / kRowThreads;
+        attn_prologue_fwd_rows_kernel<6, 64><<<(int)(groups < kNumSMs ? groups : kNumSMs), kRowThreads, smem, (cudaStream_t)stream>>>(p);
+    } else attn_prologue_fwd_fast_kernel<<<row_grid(R), kRowThreads, 0, (cudaStream_t)stream>>>(p);
     return check_launch();
 }
 
