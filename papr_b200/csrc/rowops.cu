@@ -719,6 +719,193 @@ __global__ void __launch_bounds__(kRowThreads, 3) attn_prologue_bwd_fast_kernel(
     }
 }
 
+// Backward of the prologue, one (ray, candidate) row per lane (default shape L = 6, F = 64), the counterpart of
+// attn_prologue_fwd_rows_kernel.  A warp brings its 32 rows of d kin / d vin into shared memory with coalesced loads; a lane
+// then walks its row's columns once for the LayerNorm statistics and once for everything else.  The chain through the
+// positional encoding is linear in the column gradients, so the six geometry gradients are accumulated as four running
+// sums per source (A = sum coef*gz, B = sum coef, C = sum coef*z, D = sum coef*gv) next to s1 = sum gz, s2 = sum gz*z and
+// combined at the end: t = rstd*A - rstd*s1*B - s2*C + D.  The LayerNorm-affine gradients need sums over rows, not
+// columns: d kin (for g_b2) and d kin * z (written back in place as bf16, for g_a2) are summed down the staged tile by
+// half-warps, 16 rows each, and kept in registers until the kernel ends.
+template <int L, int F>
+__global__ void __launch_bounds__(128, 2) attn_prologue_bwd_rows_kernel(const PrologueParams p)
+{
+    constexpr int S = 1 + 2 * L, DK = 9 * S, DPE = 6 * S, DV = DPE + F;
+    constexpr int NBK = (DK + 63) / 64, NBV = (DV + 63) / 64;
+    constexpr int kWarps = 4;
+    extern __shared__ __align__(16) uint8_t rows_stage[];
+    __shared__ float a2_s[DK];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int j = threadIdx.x; j < DK; j += 128) a2_s[j] = p.a2[j];
+    __syncthreads();
+    const uint32_t wst = smem_u32(rows_stage) + (uint32_t)warp * (NBK + NBV) * 4096u;
+    const uint32_t my = wst + (uint32_t)lane * 128u;
+    const uint32_t sw = (uint32_t)lane & 7u;
+    const int64_t M = p.R * p.K, M_pad = (M + 127) / 128 * 128;
+    // column-sum duty: chunk cq (8 key columns) over rows [16*half, 16*half + 16) of the warp's 32
+    const int cq = lane & 15, half = lane >> 4;
+    float acc_a2[8], acc_b2[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { acc_a2[e] = 0.f; acc_b2[e] = 0.f; }
+    auto column_sums = [&](float *acc, int64_t row0) {
+#pragma unroll 4
+        for (int r = half * 16; r < half * 16 + 16; ++r) {
+            if (row0 + r < M) {
+                uint4 q;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w)
+                             : "r"(wst + (uint32_t)(cq >> 3) * 4096u + (uint32_t)r * 128u + ((((uint32_t)cq & 7u) ^ ((uint32_t)r & 7u)) << 4)));
+                float f[8];
+                unpack8(q, f);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[e] += f[e];
+            }
+        }
+    };
+
+    for (int64_t row0 = ((int64_t)blockIdx.x * kWarps + warp) * 32; row0 < M_pad; row0 += (int64_t)gridDim.x * kWarps * 32) {
+        const int64_t row = row0 + lane;
+        const bool live = row < M;
+        // stage the 32 rows: 4 KB contiguous per 64-column block
+        {
+            const int64_t tile = row0 >> 7;
+            const uint32_t roff = (uint32_t)(row0 & 127) * 128u + (uint32_t)lane * 16u;
+#pragma unroll
+            for (int b = 0; b < NBK + NBV; ++b) {
+                const uint8_t *src = (b < NBK ? p.dkin + ((size_t)tile * NBK + b) * kBlockBytes : p.dvin + ((size_t)tile * NBV + (b - NBK)) * kBlockBytes) + roff;
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const uint4 t = *reinterpret_cast<const uint4 *>(src + it * 512);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(wst + (uint32_t)b * 4096u + (uint32_t)it * 512u + (uint32_t)lane * 16u),
+                                 "r"(t.x), "r"(t.y), "r"(t.z), "r"(t.w) : "memory");
+                }
+            }
+        }
+        float g[9], u[3] = {0.f, 0.f, 0.f}, den = 1.f;
+        int pidx = 0;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) g[i] = 0.f;
+        if (live) {
+            const int64_t ray = row / p.K;
+            const int64_t view = ray / p.rays_per_view;
+            pidx = p.idx[row];
+            const Geometry geo = ray_point_geometry(p.points + (size_t)pidx * 3, p.rays_o + view * 3, p.rays_d + ray * 3, p.eps, u, &den);
+#pragma unroll
+            for (int i = 0; i < 9; ++i) g[i] = geo.g[i];
+        }
+        float s0[9], c0[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) sincosf(g[i], &s0[i], &c0[i]);
+        float sum = 0.f, sq = 0.f;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            float s = s0[i], c = c0[i];
+            sum += g[i]; sq = fmaf(g[i], g[i], sq);
+#pragma unroll
+            for (int o = 0; o < L; ++o) {
+                sum += s + c; sq = fmaf(s, s, fmaf(c, c, sq));
+                const float s2 = 2.f * s * c, c2 = (c - s) * (c + s);
+                s = s2; c = c2;
+            }
+        }
+        const float mean = sum * (1.f / DK);
+        const float var = fmaxf(sq - (float)DK * mean * mean, 0.f) * (1.f / (DK - 1));
+        const float stdv = sqrtf(var);
+        const float rstd = 1.f / (stdv + p.eps);
+        const float lv = live ? 1.f : 0.f;
+        __syncwarp();
+        column_sums(acc_b2, row0);                   // g_b2 += sum over rows of d kin
+        __syncwarp();
+
+        float S1 = 0.f, S2 = 0.f, A[6], B[6], C[6], D[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { A[i] = 0.f; B[i] = 0.f; C[i] = 0.f; D[i] = 0.f; }
+        float go8[8], gv8[8], qb[8];
+        auto load_chunk = [&](int blk0, int c, float *f) {
+            uint4 q;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w)
+                         : "r"(my + (uint32_t)(blk0 + (c >> 3)) * 4096u + ((((uint32_t)c & 7u) ^ sw) << 4)));
+            unpack8(q, f);
+        };
+        auto put_q = [&](int c) {
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my + (uint32_t)(c >> 3) * 4096u + ((((uint32_t)c & 7u) ^ sw) << 4)),
+                         "r"(pack_bf16(qb[0], qb[1])), "r"(pack_bf16(qb[2], qb[3])), "r"(pack_bf16(qb[4], qb[5])), "r"(pack_bf16(qb[6], qb[7])) : "memory");
+        };
+#pragma unroll
+        for (int src = 0; src < 9; ++src) {
+            float s = s0[src], c = c0[src];
+#pragma unroll
+            for (int slot = 0; slot < S; ++slot) {
+                const int j = src * S + slot;
+                if ((j & 7) == 0) load_chunk(0, j >> 3, go8);
+                float val, coef;
+                if (slot == 0) { val = g[src]; coef = 1.f; }
+                else if (slot & 1) { val = s; coef = (float)(1 << ((slot - 1) >> 1)) * c; }
+                else { val = c; coef = -(float)(1 << ((slot - 1) >> 1)) * s; }
+                const float z = (val - mean) * rstd;
+                const float go = go8[j & 7];
+                const float gz = go * a2_s[j];
+                S1 += gz; S2 = fmaf(gz, z, S2);
+                qb[j & 7] = lv * go * z;
+                if ((j & 7) == 7) put_q(j >> 3);
+                if (src >= 3) {
+                    const int jv = (src - 3) * S + slot;
+                    if ((jv & 7) == 0 || (src == 3 && slot == 0)) load_chunk(NBK, jv >> 3, gv8);
+                    A[src - 3] = fmaf(coef, gz, A[src - 3]);
+                    B[src - 3] += coef;
+                    C[src - 3] = fmaf(coef, z, C[src - 3]);
+                    D[src - 3] = fmaf(coef, gv8[jv & 7], D[src - 3]);
+                }
+                if (slot && !(slot & 1)) {
+                    const float s2 = 2.f * s * c, c2 = (c - s) * (c + s);
+                    s = s2; c = c2;
+                }
+            }
+        }
+        if (DK & 7) {
+#pragma unroll
+            for (int e = DK & 7; e < 8; ++e) qb[e] = 0.f;
+            put_q(DK >> 3);
+        }
+        if (live) {
+            const float s1 = S1 * (1.f / DK);
+            const float s2 = S2 / ((float)(DK - 1) * stdv);
+            float dx[6];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) dx[i] = rstd * A[i] - rstd * s1 * B[i] - s2 * C[i] + D[i];
+            const float e0 = dx[0] - dx[3], e1 = dx[1] - dx[4], e2 = dx[2] - dx[5];
+            const float sd = (e0 * u[0] + e1 * u[1] + e2 * u[2]) / den;
+            atomicAdd(p.g_points + (size_t)pidx * 3 + 0, dx[3] + u[0] * sd);
+            atomicAdd(p.g_points + (size_t)pidx * 3 + 1, dx[4] + u[1] * sd);
+            atomicAdd(p.g_points + (size_t)pidx * 3 + 2, dx[5] + u[2] * sd);
+            // d feats = the tail of d vin (columns DPE .. DV-1)
+            float fv[F];
+#pragma unroll
+            for (int c = DPE >> 3; c <= (DV - 1) >> 3; ++c) {
+                float f8[8];
+                load_chunk(NBK, c, f8);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int f = c * 8 + e - DPE;
+                    if (f >= 0 && f < F) fv[f] = f8[e];
+                }
+            }
+            float *gf = p.g_feats + (size_t)pidx * F;
+#pragma unroll
+            for (int f = 0; f < F; f += 4) red_add_v4(gf + f, fv[f], fv[f + 1], fv[f + 2], fv[f + 3]);
+        }
+        __syncwarp();
+        column_sums(acc_a2, row0);                   // g_a2 += sum over rows of d kin * z (bf16 products staged in place)
+        __syncwarp();
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const float sa = acc_a2[e] + __shfl_xor_sync(0xffffffffu, acc_a2[e], 16);
+        const float sb = acc_b2[e] + __shfl_xor_sync(0xffffffffu, acc_b2[e], 16);
+        const int j = cq * 8 + e;
+        if (half == 0 && j < DK) { atomicAdd(p.g_a2 + j, sa); atomicAdd(p.g_b2 + j, sb); }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ score + blend
 struct ScoreParams {
     const uint8_t *h5;      // blocked bf16 [M_pad, 256] key stack output (before its LayerNorm)
@@ -1098,7 +1285,16 @@ extern "C" int papr_attn_prologue_bwd(const float *rays_o, const float *rays_d, 
     p.dkin = (const uint8_t *)dkin; p.dvin = (const uint8_t *)dvin; p.dkin_f32 = dkin_f32; p.dvin_f32 = dvin_f32;
     p.g_points = g_points; p.g_feats = g_feats; p.g_a2 = g_ln_a; p.g_b2 = g_ln_b;
     if (dkin_f32 || dvin_f32) attn_prologue_bwd_kernel<<<row_grid(R), kRowThreads, 0, (cudaStream_t)stream>>>(p);
-    else attn_prologue_bwd_fast_kernel<<<row_grid(R), kRowThreads, 0, (cudaStream_t)stream>>>(p);
+    else if (L == 6 && F == 64 && p.nblk_k == 2 && p.nblk_v == 3 && !getenv("PAPR_PROLOGUE_HALFWARP")) {
+        constexpr int smem = 4 * 5 * 4096;
+        static bool attr_set = false;
+        if (!attr_set) {
+            PAPR_CUDA_TRY(cudaFuncSetAttribute(attn_prologue_bwd_rows_kernel<6, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            attr_set = true;
+        }
+        const int64_t groups = ((R * K + 127) / 128 * 128 + 127) / 128;
+        attn_prologue_bwd_rows_kernel<6, 64><<<(int)(groups < 2 * kNumSMs ? groups : 2 * kNumSMs), 128, smem, (cudaStream_t)stream>>>(p);
+    } else attn_prologue_bwd_fast_kernel<<<row_grid(R), kRowThreads, 0, (cudaStream_t)stream>>>(p);
     return check_launch();
 }
 

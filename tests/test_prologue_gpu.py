@@ -1,0 +1,77 @@
+"""GPU: the three prologue kernel families agree -- exact fp32 (taps), half-warp-per-row bf16, row-per-lane bf16 -- forward
+(key / value stack inputs: models/model.py:285-310, 396-437; utils.py:232-257; attn.py:39-42) and backward."""
+import os
+import types
+
+import pytest
+import torch
+
+from papr_b200 import ops
+from papr_b200 import attention as A
+
+pytestmark = pytest.mark.gpu
+
+
+def _case(R=301, K=20, P=700, views=1, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    dev = "cuda"
+    sh = types.SimpleNamespace(R=R, rays_per_view=R // views, K=K, M=R * K, L=6, F=64, dk=117, dv=142,
+                               dk_pad=128, dv_pad=192, eps=1e-6)
+    rays_o = torch.randn(views, 3, device=dev, generator=g) * 3
+    rays_d = torch.nn.functional.normalize(torch.randn(R, 3, device=dev, generator=g), dim=-1)
+    points = torch.randn(P, 3, device=dev, generator=g)
+    feats = torch.randn(P, 64, device=dev, generator=g)
+    idx = torch.randint(0, P, (R, K), device=dev, generator=g, dtype=torch.int32)
+    ln_a = 1 + 0.1 * torch.randn(117, device=dev, generator=g)
+    ln_b = 0.1 * torch.randn(117, device=dev, generator=g)
+    return sh, rays_o, rays_d, points, feats, idx, ln_a, ln_b
+
+
+def _with_env(flag, fn):
+    if flag:
+        os.environ["PAPR_PROLOGUE_HALFWARP"] = "1"
+    try:
+        return fn()
+    finally:
+        os.environ.pop("PAPR_PROLOGUE_HALFWARP", None)
+
+
+@pytest.mark.parametrize("R,views", [(301, 1), (96, 2), (5, 1)])
+def test_prologue_forward_families_agree(R, views):
+    sh, rays_o, rays_d, points, feats, idx, ln_a, ln_b = _case(R=R, views=views)
+    _, _, k32, v32 = A._prologue_fwd(sh, rays_o, rays_d, points, feats, idx, ln_a, ln_b, taps=True)
+    outs = {}
+    for name, flag in (("halfwarp", True), ("rows", False)):
+        kin, vin, _, _ = _with_env(flag, lambda: A._prologue_fwd(sh, rays_o, rays_d, points, feats, idx, ln_a, ln_b))
+        outs[name] = (kin.to_f32(sh.M, sh.dk), vin.to_f32(sh.M, sh.dv), kin.to_f32(kin.rows_pad, kin.cols_pad),
+                      vin.to_f32(vin.rows_pad, vin.cols_pad))
+    for name, (k, v, kfull, vfull) in outs.items():
+        # bf16 rounding of the fp32 kernel's values: half an ulp = 2^-9 relative, plus 1e-5 absolute for the statistics
+        assert float(((k - k32).abs() - 4e-3 * k32.abs()).max()) <= 2e-5, name
+        assert float(((v - v32).abs() - 4e-3 * v32.abs()).max()) <= 2e-5, name
+        # padding rows / columns of the tile-blocked tensors are zero
+        assert float(kfull[sh.M:].abs().sum()) == 0.0 and float(vfull[sh.M:].abs().sum()) == 0.0, name
+        assert float(kfull[:, sh.dk:].abs().sum()) == 0.0 and float(vfull[:, sh.dv:].abs().sum()) == 0.0, name
+    # the two bf16 kernels differ only where a value sits on a rounding boundary
+    dk = (outs["rows"][0] - outs["halfwarp"][0]).abs()
+    assert float((dk > 0).float().mean()) < 0.02 and float((dk - 8e-3 * outs["rows"][0].abs()).max()) <= 1e-6
+    assert torch.equal(outs["rows"][1][:, 78:], outs["halfwarp"][1][:, 78:])       # gathered point features: copies
+
+
+@pytest.mark.parametrize("R,views", [(301, 1), (96, 2)])
+def test_prologue_backward_families_agree(R, views):
+    sh, rays_o, rays_d, points, feats, idx, ln_a, ln_b = _case(R=R, views=views, seed=1)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    dk32 = torch.randn(sh.M, sh.dk, device="cuda", generator=g)
+    dv32 = torch.randn(sh.M, sh.dv, device="cuda", generator=g)
+    dkin = ops.Blocked.from_f32(dk32, cols_pad=sh.dk_pad)
+    dvin = ops.Blocked.from_f32(dv32, cols_pad=sh.dv_pad)
+    # reference: the exact fp32 kernel fed with the bf16-rounded gradients the other two read
+    ref = A._prologue_bwd(sh, rays_o, rays_d, points, idx, ln_a, None, None,
+                          dkin.to_f32(sh.M, sh.dk), dvin.to_f32(sh.M, sh.dv), points.shape[0])
+    for name, flag in (("halfwarp", True), ("rows", False)):
+        got = _with_env(flag, lambda: A._prologue_bwd(sh, rays_o, rays_d, points, idx, ln_a, dkin, dvin, None, None, points.shape[0]))
+        for what, a, b in zip(("g_points", "g_feats", "g_a2", "g_b2"), got, ref):
+            scale = float(b.abs().max())
+            tol = 2e-2 if (what == "g_a2" and name == "rows") else 2e-3      # rows kernel sums bf16-rounded d kin * z products
+            assert float((a - b).abs().max()) <= tol * scale, (name, what, float((a - b).abs().max()), scale)
