@@ -916,7 +916,7 @@ struct ScoreParams {
     const int32_t *idx;     // [R,K]
     const float *v;         // fp32 [M_pad, ldv]
     int64_t R;
-    int K, C, ldv, score_relu, normalize;
+    int K, C, ldv, score_relu, normalize, sc_ready;
     float bkg_score, eps;
     float *fused, *attn, *sc, *stats;       // [R,C], [R,K+1], [M], [M,2]
     // backward
@@ -940,6 +940,84 @@ __device__ __forceinline__ void load_row8(const ScoreParams &p, int64_t row, int
     }
 }
 
+// Raw attention scores, one (ray, candidate) row per lane (bf16 h5, K >= 16): score = ua . z(h5) + c' with z the row's
+// LayerNorm-normalised key-stack output (attn.py:39-42, 117, 212-226 after the key-head fold of DESIGN.md section 3).
+// The warp-per-ray form spends three 5-stage shuffle reductions per row; here a lane owns its row's 256 columns (staged
+// through shared memory so the tile is read with coalesced 16-byte loads) and needs none.  Sums are taken about the row's
+// first element c0: mean = c0 + S/256, sum (h-mean)^2 = Q - S^2/256, ua.(h-mean) = T - (mean-c0) * sum(ua).
+__global__ void __launch_bounds__(kRowThreads, 1) score_rows_kernel(const ScoreParams p)
+{
+    extern __shared__ __align__(16) uint8_t rows_stage[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t wst = smem_u32(rows_stage) + (uint32_t)warp * 4u * 4096u;
+    const uint32_t my = wst + (uint32_t)lane * 128u;
+    const uint32_t sw = (uint32_t)lane & 7u;
+    const int64_t M = p.R * p.K, M_pad = (M + 127) / 128 * 128;
+    for (int64_t row0 = ((int64_t)blockIdx.x * kRowWarps + warp) * 32; row0 < M_pad; row0 += (int64_t)gridDim.x * kRowWarps * 32) {
+        if (row0 >= M) break;                                  // warp-uniform: only padding rows left
+        {
+            const int64_t tile = row0 >> 7;
+            const uint8_t *src = p.h5 + (size_t)tile * 4 * kBlockBytes + (uint32_t)(row0 & 127) * 128u + (uint32_t)lane * 16u;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const uint4 t = *reinterpret_cast<const uint4 *>(src + (size_t)b * kBlockBytes + it * 512);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(wst + (uint32_t)b * 4096u + (uint32_t)it * 512u + (uint32_t)lane * 16u),
+                                 "r"(t.x), "r"(t.y), "r"(t.z), "r"(t.w) : "memory");
+                }
+            }
+        }
+        const int64_t row = row0 + lane;
+        const bool live = row < M;
+        const int64_t ray = (live ? row : M - 1) / p.K;
+        // sum(ua) of the (at most three, K >= 16) rays this warp touches: one shuffle reduction each, then pick mine
+        const int64_t ray_a = row0 / p.K;
+        float usum = 0.f;
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            const int64_t rr = ray_a + t;
+            float part = 0.f;
+            if (rr < p.R) {
+                const float4 a = __ldg(reinterpret_cast<const float4 *>(p.ua + rr * 256 + lane * 8));
+                const float4 b = __ldg(reinterpret_cast<const float4 *>(p.ua + rr * 256 + lane * 8 + 4));
+                part = ((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w));
+            }
+            part = warp_sum(part);
+            if (ray == rr) usum = part;
+        }
+        __syncwarp();
+        const float4 *uap = reinterpret_cast<const float4 *>(p.ua + ray * 256);
+        float c0 = 0.f, S = 0.f, Q = 0.f, T = 0.f;
+#pragma unroll 4
+        for (int c = 0; c < 32; ++c) {
+            uint4 q;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w)
+                         : "r"(my + (uint32_t)(c >> 3) * 4096u + ((((uint32_t)c & 7u) ^ sw) << 4)));
+            float h[8];
+            unpack8(q, h);
+            if (c == 0) c0 = h[0];
+            const float4 u0 = __ldg(uap + 2 * c), u1 = __ldg(uap + 2 * c + 1);
+            const float uu[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float d = h[e] - c0;
+                S += d; Q = fmaf(d, d, Q); T = fmaf(d, uu[e], T);
+            }
+        }
+        if (live) {
+            const float dm = S * (1.f / 256.f);                      // mean - c0
+            const float sq = fmaxf(Q - S * dm, 0.f);
+            const float rstd = 1.f / (sqrtf(sq * (1.f / 255.f)) + p.eps);
+            float raw = (T - dm * usum) * rstd + p.cprime[ray];
+            if (p.score_relu) raw = fmaxf(raw, 0.f);
+            p.sc[row] = raw;
+            *reinterpret_cast<float2 *>(p.stats + row * 2) = make_float2(c0 + dm, rstd);
+        }
+        __syncwarp();
+    }
+}
+
 __global__ void __launch_bounds__(kRowThreads) score_blend_fwd_kernel(const ScoreParams p)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -952,6 +1030,9 @@ __global__ void __launch_bounds__(kRowThreads) score_blend_fwd_kernel(const Scor
         }
         const float cp = p.cprime[ray];
         float my_sc = 0.f;
+        if (p.sc_ready) {                    // raw scores and row statistics already written by score_rows_kernel
+            if (lane < p.K) my_sc = p.sc[ray * p.K + lane];
+        } else {
         // bf16 rows are fetched one candidate ahead (4 registers) so the HBM latency overlaps the three warp reductions
         uint4 nxt = make_uint4(0, 0, 0, 0);
         if (!p.h5_f32) nxt = *reinterpret_cast<const uint4 *>(p.h5 + blocked_chunk_offset(ray * p.K, lane, 4));
@@ -977,10 +1058,11 @@ __global__ void __launch_bounds__(kRowThreads) score_blend_fwd_kernel(const Scor
             if (lane == k) my_sc = raw;
             if (lane == 0) { p.stats[row * 2] = mean; p.stats[row * 2 + 1] = rstd; }
         }
+        }
         // model.py:524-533: influence scores, background token, softmax, top-K renormalisation
         float s = -INFINITY;
         if (lane < p.K) {
-            p.sc[ray * p.K + lane] = my_sc;
+            if (!p.sc_ready) p.sc[ray * p.K + lane] = my_sc;
             s = my_sc * __ldg(p.influ + p.idx[ray * p.K + lane]);
         } else if (lane == p.K) s = p.bkg_score;
         const float mx = warp_max(s);
@@ -1309,6 +1391,18 @@ extern "C" int papr_score_blend_fwd(const void *h5, const float *h5_f32, const f
     p.h5 = (const uint8_t *)h5; p.h5_f32 = h5_f32; p.ua = ua; p.cprime = cprime; p.influ = influ; p.idx = idx; p.v = v;
     p.R = R; p.K = K; p.C = C; p.ldv = (int)ldv; p.score_relu = score_relu; p.normalize = normalize;
     p.bkg_score = bkg_score; p.eps = eps; p.fused = fused; p.attn = attn; p.sc = sc; p.stats = stats;
+    if (h5 && !h5_f32 && K >= 16 && !getenv("PAPR_SCORE_WARP")) {
+        constexpr int smem = kRowWarps * 4 * 4096;
+        static bool attr_set = false;
+        if (!attr_set) {
+            PAPR_CUDA_TRY(cudaFuncSetAttribute(score_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            attr_set = true;
+        }
+        const int64_t groups = (R * K + kRowThreads - 1) / kRowThreads;
+        score_rows_kernel<<<(int)(groups < kNumSMs ? groups : kNumSMs), kRowThreads, smem, (cudaStream_t)stream>>>(p);
+        PAPR_CUDA_TRY(cudaGetLastError());
+        p.sc_ready = 1;
+    }
     score_blend_fwd_kernel<<<row_grid(R), kRowThreads, 0, (cudaStream_t)stream>>>(p);
     return check_launch();
 }

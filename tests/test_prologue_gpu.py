@@ -75,3 +75,39 @@ def test_prologue_backward_families_agree(R, views):
             scale = float(b.abs().max())
             tol = 2e-2 if (what == "g_a2" and name == "rows") else 2e-3      # rows kernel sums bf16-rounded d kin * z products
             assert float((a - b).abs().max()) <= tol * scale, (name, what, float((a - b).abs().max()), scale)
+
+
+@pytest.mark.parametrize("R,K,relu", [(301, 20, True), (77, 16, False), (40, 31, True)])
+def test_score_rows_kernel_matches_warp_per_ray(R, K, relu):
+    """Raw scores / LayerNorm statistics by the row-per-lane kernel against the warp-per-ray kernel (same bf16 h5) and
+    against a float64 evaluation of ua . LN(h5) + c' (attn.py:39-42, 212-226 after the key-head fold)."""
+    g = torch.Generator(device="cuda").manual_seed(R)
+    M, C, P = R * K, 32, 500
+    sh = types.SimpleNamespace(R=R, K=K, M=M, C=C, score_relu=relu, normalize=True, bkg_score=5.0, eps=1e-6)
+    h32 = torch.randn(M, 256, device="cuda", generator=g) * 2 + 0.5
+    h5 = ops.Blocked.from_f32(h32)
+    hq = h5.to_f32(M, 256).double()
+    ua = torch.randn(R, 256, device="cuda", generator=g) * 0.2
+    cprime = torch.randn(R, device="cuda", generator=g)
+    influ = torch.rand(P, device="cuda", generator=g)
+    idx = torch.randint(0, P, (R, K), device="cuda", generator=g, dtype=torch.int32)
+    v = torch.randn(ops.pad_rows(M), C, device="cuda", generator=g)
+    new = A._score_blend_fwd(sh, h5, None, ua, cprime, influ, idx, v)
+    os.environ["PAPR_SCORE_WARP"] = "1"
+    try:
+        old = A._score_blend_fwd(sh, h5, None, ua, cprime, influ, idx, v)
+    finally:
+        os.environ.pop("PAPR_SCORE_WARP", None)
+    mean = hq.mean(-1, keepdim=True)
+    std = hq.std(-1, keepdim=True)
+    z = (hq - mean) / (std + 1e-6)
+    raw = (z * ua.double().repeat_interleave(K, 0)).sum(-1) + cprime.double().repeat_interleave(K)
+    if relu:
+        raw = raw.clamp_min(0)
+    for name, out in (("rows", new), ("warp", old)):
+        fused, attn, sc, stats = out
+        assert float((sc.double() - raw).abs().max()) <= 2e-5 * max(1.0, float(raw.abs().max())), name
+        assert float((stats[:, 0].double() - mean[:, 0]).abs().max()) <= 1e-5, name
+        assert float((stats[:, 1].double() * (std[:, 0] + 1e-6) - 1).abs().max()) <= 1e-5, name
+    assert float((new[0] - old[0]).abs().max()) <= 1e-4 * float(old[0].abs().max())
+    assert float((new[1] - old[1]).abs().max()) <= 1e-5
