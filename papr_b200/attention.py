@@ -141,7 +141,8 @@ def _score_blend_fwd(sh, h5, h5_32, ua, cprime, influ, idx, v):
         _ptr(h5), _ptr(h5_32), ua.data_ptr(), cprime.data_ptr(), influ.data_ptr(), idx.data_ptr(), v.data_ptr(),
         v.stride(0), sh.R, sh.K, sh.C, int(sh.score_relu), int(sh.normalize), sh.bkg_score, sh.eps, fused.data_ptr(),
         attn.data_ptr(), sc.data_ptr(), stats.data_ptr(),
-        nbytes=sh.M * (512.0 + 4 * sh.C + 16) + sh.R * (1024.0 + 4 * sh.C))
+        nbytes=sh.M * (512.0 + 4 * sh.C + 16) + sh.R * (1024.0 + 4 * sh.C),
+        kernels=2 if (h5 is not None and h5_32 is None and sh.K >= 16) else 1)     # row scores, then per-ray softmax + blend
     return fused, attn, sc, stats
 
 

@@ -36,10 +36,11 @@ class LaunchStats:
 STATS = LaunchStats()
 
 
-def call(name, *args, flops=0.0, nbytes=0.0):
-    """Invoke one C-ABI entry point on the current stream (the stream pointer is appended)."""
+def call(name, *args, flops=0.0, nbytes=0.0, kernels=1):
+    """Invoke one C-ABI entry point on the current stream (the stream pointer is appended).  `kernels`: how many kernels
+    the entry point launches (for the launch count bench.py reports)."""
     fn = getattr(lib(), name)
-    STATS.count += 1
+    STATS.count += kernels
     if STATS.timing:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

@@ -21,7 +21,7 @@ def step():
     loss.backward(); model.step()
 for _ in range(2): step()
 torch.cuda.synchronize()
-with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU], record_shapes=True) as prof:
     step(); torch.cuda.synchronize()
 rows = []
 for e in prof.key_averages():
@@ -31,3 +31,13 @@ rows.sort(reverse=True)
 tot = sum(r[0] for r in rows)
 print(f"total device ms {tot:.1f}")
 for t, n, k in rows[:45]: print(f"{t:8.3f} ms x{n:4d} {k}")
+
+# which aten ops (with input shapes) own the torch-side device time
+ops_rows = []
+for e in prof.key_averages(group_by_input_shape=True):
+    t = getattr(e, "self_device_time_total", 0) or getattr(e, "self_cuda_time_total", 0)
+    if e.device_type.name == "CPU" and t > 50 and e.key.startswith("aten::"):
+        ops_rows.append((t / 1e3, e.count, e.key, str(e.input_shapes)[:120]))
+ops_rows.sort(reverse=True)
+print("aten ops by self device time:")
+for t, n, k, sh in ops_rows[:30]: print(f"{t:8.3f} ms x{n:4d} {k:28s} {sh}")
