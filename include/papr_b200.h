@@ -136,7 +136,7 @@ int papr_attn_prologue_bwd(const float *rays_o, const float *rays_d, const float
  * cprime (R) = (W_k^T q'/sqrt d) . b_2 + q'.b_k/sqrt d, with a_2,b_2 the key outnorm affine terms.
  *   h5 (M_pad,256) tile-blocked bf16 key-stack output (or fp32 tap h5_f32 (M,256)); v (M_pad, ldv) fp32 value-stack output
  *   fused (R,C); attn (R,K+1) softmax incl. background, un-renormalised (model.py:481/529);
- *   sc (M) activated scores before influence; stats (M,2) = LayerNorm mean and 1/(std+eps) (saved for backward)
+ *   sc (M) activated scores before influence; stats (M,4) = LayerNorm mean, 1/(std+eps), ua . z, 0 (saved for backward)
  */
 int papr_score_blend_fwd(const void *h5, const float *h5_f32, const float *ua, const float *cprime,
                          const float *influ, const int32_t *idx, const float *v, int64_t ldv, int64_t R, int K,

@@ -136,7 +136,7 @@ def _score_blend_fwd(sh, h5, h5_32, ua, cprime, influ, idx, v):
     fused = torch.empty((sh.R, sh.C), device=dev)
     attn = torch.empty((sh.R, sh.K + 1), device=dev)
     sc = torch.empty((sh.M,), device=dev)
-    stats = torch.empty((sh.M, 2), device=dev)
+    stats = torch.empty((sh.M, 4), device=dev)      # per row: LayerNorm mean, 1/(std+eps), ua . z, unused
     ops.call("papr_score_blend_fwd",
         _ptr(h5), _ptr(h5_32), ua.data_ptr(), cprime.data_ptr(), influ.data_ptr(), idx.data_ptr(), v.data_ptr(),
         v.stride(0), sh.R, sh.K, sh.C, int(sh.score_relu), int(sh.normalize), sh.bkg_score, sh.eps, fused.data_ptr(),

@@ -1009,10 +1009,11 @@ __global__ void __launch_bounds__(kRowThreads, 1) score_rows_kernel(const ScoreP
             const float dm = S * (1.f / 256.f);                      // mean - c0
             const float sq = fmaxf(Q - S * dm, 0.f);
             const float rstd = 1.f / (sqrtf(sq * (1.f / 255.f)) + p.eps);
-            float raw = (T - dm * usum) * rstd + p.cprime[ray];
+            const float dot = (T - dm * usum) * rstd;                // ua . z, kept for the backward kernel
+            float raw = dot + p.cprime[ray];
             if (p.score_relu) raw = fmaxf(raw, 0.f);
             p.sc[row] = raw;
-            *reinterpret_cast<float2 *>(p.stats + row * 2) = make_float2(c0 + dm, rstd);
+            *reinterpret_cast<float4 *>(p.stats + row * 4) = make_float4(c0 + dm, rstd, dot, 0.f);
         }
         __syncwarp();
     }
@@ -1056,7 +1057,7 @@ __global__ void __launch_bounds__(kRowThreads) score_blend_fwd_kernel(const Scor
             float raw = dot * rstd + cp;
             if (p.score_relu) raw = fmaxf(raw, 0.f);
             if (lane == k) my_sc = raw;
-            if (lane == 0) { p.stats[row * 2] = mean; p.stats[row * 2 + 1] = rstd; }
+            if (lane == 0) *reinterpret_cast<float4 *>(p.stats + row * 4) = make_float4(mean, rstd, dot * rstd, 0.f);
         }
         }
         // model.py:524-533: influence scores, background token, softmax, top-K renormalisation
@@ -1172,21 +1173,22 @@ __global__ void __launch_bounds__(kRowThreads, 4) key_score_bwd_kernel(const Sco
         float dss = 0.f;
         uint4 nxt = make_uint4(0, 0, 0, 0);
         if (!p.h5_f32) nxt = *reinterpret_cast<const uint4 *>(p.h5 + blocked_chunk_offset(ray * p.K, lane, 4));
-        float ds_n = p.d_score_in[ray * p.K], mean_n = p.stats[ray * p.K * 2], rstd_n = p.stats[ray * p.K * 2 + 1];
+        float ds_n = p.d_score_in[ray * p.K];
+        float4 st_n = *reinterpret_cast<const float4 *>(p.stats + ray * p.K * 4);
         for (int k = 0; k < p.K; ++k) {
             const int64_t row = ray * p.K + k;
-            const float ds = ds_n, mean = mean_n, rstd = rstd_n;
-            float h[8], y[8], dot = 0.f;
+            // mean, 1/(std+eps) and dot = ua . z come from the forward kernel: no reduction over the row is needed here
+            const float ds = ds_n, mean = st_n.x, rstd = st_n.y, dot = st_n.z;
+            float h[8], y[8];
             if (p.h5_f32) load_row8(p, row, lane, h);
             else {
                 const uint4 cur = nxt;
                 if (k + 1 < p.K) nxt = *reinterpret_cast<const uint4 *>(p.h5 + blocked_chunk_offset(row + 1, lane, 4));
                 unpack8(cur, h);
             }
-            if (k + 1 < p.K) { ds_n = p.d_score_in[row + 1]; mean_n = p.stats[row * 2 + 2]; rstd_n = p.stats[row * 2 + 3]; }
+            if (k + 1 < p.K) { ds_n = p.d_score_in[row + 1]; st_n = *reinterpret_cast<const float4 *>(p.stats + (row + 1) * 4); }
 #pragma unroll
-            for (int e = 0; e < 8; ++e) { y[e] = (h[e] - mean) * rstd; dot += y[e] * ua[e]; }
-            dot = warp_sum(dot);
+            for (int e = 0; e < 8; ++e) y[e] = (h[e] - mean) * rstd;
             const float sigma = 1.f / rstd - p.eps;
             const float coef = ds * dot / (255.f * sigma);
             float f[8];
