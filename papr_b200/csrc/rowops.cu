@@ -1101,7 +1101,15 @@ __global__ void __launch_bounds__(kRowThreads) blend_bwd_kernel(const ScoreParam
         if (lane < p.K) {
             const float *vr = p.v + (ray * p.K + lane) * p.ldv;
             const float *df = p.d_fused + ray * p.C;
-            for (int c = 0; c < p.C; ++c) dw += __ldg(df + c) * vr[c];
+            if (((p.C | p.ldv) & 3) == 0) {
+                for (int c = 0; c < p.C; c += 4) {
+                    const float4 a = __ldg(reinterpret_cast<const float4 *>(df + c));
+                    const float4 b = *reinterpret_cast<const float4 *>(vr + c);
+                    dw = fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, dw))));
+                }
+            } else {
+                for (int c = 0; c < p.C; ++c) dw += __ldg(df + c) * vr[c];
+            }
         }
         float da;                                   // d attn
         if (p.normalize) {
