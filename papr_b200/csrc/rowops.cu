@@ -453,7 +453,7 @@ __global__ void __launch_bounds__(kRowThreads, 3) attn_prologue_fwd_fast_kernel(
 // instructions per row.  A warp stages its 32 rows -- 32 x 128 B per 64-column block, already in the tile-blocked
 // swizzle -- in shared memory and copies each 4 KB piece out with fully coalesced 16-byte stores.
 template <int L, int F>
-__global__ void __launch_bounds__(kRowThreads, 1) attn_prologue_fwd_rows_kernel(const PrologueParams p)
+__global__ void __launch_bounds__(kRowThreads, 2) attn_prologue_fwd_rows_kernel(const PrologueParams p)
 {
     constexpr int S = 1 + 2 * L, DK = 9 * S, DPE = 6 * S, DV = DPE + F;
     constexpr int NBK = (DK + 63) / 64, NBV = (DV + 63) / 64;
@@ -462,7 +462,8 @@ __global__ void __launch_bounds__(kRowThreads, 1) attn_prologue_fwd_rows_kernel(
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int j = threadIdx.x; j < DK; j += kRowThreads) ab_s[j] = make_float2(p.a2[j], p.b2[j]);
     __syncthreads();
-    const uint32_t wst = smem_u32(rows_stage) + (uint32_t)warp * (NBK + NBV) * 4096u;
+    constexpr int NBS = NBK > NBV ? NBK : NBV;      // the key and the value rows are staged one after the other
+    const uint32_t wst = smem_u32(rows_stage) + (uint32_t)warp * NBS * 4096u;
     const uint32_t my = wst + (uint32_t)lane * 128u;
     const uint32_t sw = (uint32_t)lane & 7u;
     const int64_t M = p.R * p.K, M_pad = (M + 127) / 128 * 128;
@@ -511,7 +512,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) attn_prologue_fwd_rows_kernel(
                          "r"(pack_bf16(kb[0], kb[1])), "r"(pack_bf16(kb[2], kb[3])), "r"(pack_bf16(kb[4], kb[5])), "r"(pack_bf16(kb[6], kb[7])) : "memory");
         };
         auto put_v = [&](int c) {        // value chunk c <- vb
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my + (uint32_t)(NBK + (c >> 3)) * 4096u + ((((uint32_t)c & 7u) ^ sw) << 4)),
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my + (uint32_t)(c >> 3) * 4096u + ((((uint32_t)c & 7u) ^ sw) << 4)),
                          "r"(pack_bf16(vb[0], vb[1])), "r"(pack_bf16(vb[2], vb[3])), "r"(pack_bf16(vb[4], vb[5])), "r"(pack_bf16(vb[6], vb[7])) : "memory");
         };
 #pragma unroll
@@ -531,11 +532,6 @@ __global__ void __launch_bounds__(kRowThreads, 1) attn_prologue_fwd_rows_kernel(
                 const float2 ab = ab_s[j];
                 kb[j & 7] = lv * fmaf((val - mean) * rstd, ab.x, ab.y);
                 if ((j & 7) == 7) put_k(j >> 3);
-                if (src >= 3) {
-                    const int jv = (src - 3) * S + slot;
-                    vb[jv & 7] = lv * val;
-                    if ((jv & 7) == 7) put_v(jv >> 3);
-                }
             }
         }
         if (DK & 7) {
@@ -547,6 +543,41 @@ __global__ void __launch_bounds__(kRowThreads, 1) attn_prologue_fwd_rows_kernel(
         for (int e = 0; e < 8; ++e) kb[e] = 0.f;
 #pragma unroll
         for (int c = (DK + 7) >> 3; c < NBK * 8; ++c) put_k(c);
+        const int64_t tile = row0 >> 7;
+        const uint32_t roff = (uint32_t)(row0 & 127) * 128u + (uint32_t)lane * 16u;
+        auto copy_out = [&](uint8_t *base, int nb) {      // the warp's 32 rows are 4 KB contiguous inside every 16 KB block of the tile
+            __syncwarp();
+            for (int b = 0; b < nb; ++b) {
+                uint8_t *dst = base + ((size_t)tile * nb + b) * kBlockBytes + roff;
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    uint4 t;
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w) : "r"(wst + (uint32_t)b * 4096u + (uint32_t)it * 512u + (uint32_t)lane * 16u));
+                    *reinterpret_cast<uint4 *>(dst + it * 512) = t;
+                }
+            }
+            __syncwarp();
+        };
+        copy_out(p.kin, NBK);
+        // value side: the encodings of geometry scalars 3..8 again (unnormalised), then the point features
+#pragma unroll
+        for (int src = 3; src < 9; ++src) {
+            float s = s0[src], c = c0[src];
+#pragma unroll
+            for (int slot = 0; slot < S; ++slot) {
+                float val;
+                if (slot == 0) val = g[src];
+                else if (slot & 1) val = s;
+                else {
+                    val = c;
+                    const float s2 = 2.f * s * c, c2 = (c - s) * (c + s);
+                    s = s2; c = c2;
+                }
+                const int jv = (src - 3) * S + slot;
+                vb[jv & 7] = lv * val;
+                if ((jv & 7) == 7) put_v(jv >> 3);
+            }
+        }
         // point features follow the value-side encoding (model.py:396-437: cat(pe(geometry), pc_feats))
         const float4 *fsrc = reinterpret_cast<const float4 *>(p.feats + (size_t)pidx * F);
 #pragma unroll
@@ -570,21 +601,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) attn_prologue_fwd_rows_kernel(
         for (int e = 0; e < 8; ++e) vb[e] = 0.f;
 #pragma unroll
         for (int c = (DV + 7) >> 3; c < NBV * 8; ++c) put_v(c);
-        __syncwarp();
-        // copy out: the warp's 32 rows are 4 KB contiguous inside every 16 KB block of the tile
-        const int64_t tile = row0 >> 7;
-        const uint32_t roff = (uint32_t)(row0 & 127) * 128u + (uint32_t)lane * 16u;
-#pragma unroll
-        for (int b = 0; b < NBK + NBV; ++b) {
-            uint8_t *dst = (b < NBK ? p.kin + ((size_t)tile * NBK + b) * kBlockBytes : p.vin + ((size_t)tile * NBV + (b - NBK)) * kBlockBytes) + roff;
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-                uint4 t;
-                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w) : "r"(wst + (uint32_t)b * 4096u + (uint32_t)it * 512u + (uint32_t)lane * 16u));
-                *reinterpret_cast<uint4 *>(dst + it * 512) = t;
-            }
-        }
-        __syncwarp();
+        copy_out(p.vin, NBV);
     }
 }
 
@@ -1348,14 +1365,14 @@ extern "C" int papr_attn_prologue_fwd(const float *rays_o, const float *rays_d, 
     p.kin = (uint8_t *)kin; p.vin = (uint8_t *)vin; p.kin_f32 = kin_f32; p.vin_f32 = vin_f32;
     if (kin_f32 || vin_f32) attn_prologue_fwd_kernel<<<row_grid(R), kRowThreads, 0, (cudaStream_t)stream>>>(p);
     else if (L == 6 && F == 64 && p.nblk_k == 2 && p.nblk_v == 3 && !getenv("PAPR_PROLOGUE_HALFWARP")) {
-        constexpr int smem = kRowWarps * 5 * 4096;
+        constexpr int smem = kRowWarps * 3 * 4096;
         static bool attr_set = false;
         if (!attr_set) {
             PAPR_CUDA_TRY(cudaFuncSetAttribute(attn_prologue_fwd_rows_kernel<6, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             attr_set = true;
         }
         const int64_t groups = ((R * K + 127) / 128 * 128 + kRowThreads - 1) / kRowThreads;
-        attn_prologue_fwd_rows_kernel<6, 64><<<(int)(groups < kNumSMs ? groups : kNumSMs), kRowThreads, smem, (cudaStream_t)stream>>>(p);
+        attn_prologue_fwd_rows_kernel<6, 64><<<(int)(groups < 2 * kNumSMs ? groups : 2 * kNumSMs), kRowThreads, smem, (cudaStream_t)stream>>>(p);
     } else attn_prologue_fwd_fast_kernel<<<row_grid(R), kRowThreads, 0, (cudaStream_t)stream>>>(p);
     return check_launch();
 }
