@@ -22,6 +22,21 @@ inline int check_launch()
         if (_e != cudaSuccess) { papr::set_last_cuda_error(_e); return PAPR_ERR_CUDA; } \
     } while (0)
 
+// Opt-in to more than 48 KB of dynamic shared memory is a per-device function attribute: set it once per (kernel, device).
+struct SmemAttrOnce { bool done[64] = {}; };
+template <typename Kernel>
+inline cudaError_t ensure_dyn_smem(SmemAttrOnce &once, Kernel kernel, int bytes)
+{
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const bool tracked = dev >= 0 && dev < 64;
+    if (tracked && once.done[dev]) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess && tracked) once.done[dev] = true;
+    return e;
+}
+
 constexpr int kNumSMs = 148;   // B200
 
 }  // namespace papr

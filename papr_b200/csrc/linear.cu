@@ -233,11 +233,8 @@ __global__ void __launch_bounds__(kLinThreads, 1) linear_kernel(const LinearPara
 template <int EPI>
 static int launch_linear(const LinearParams &p, int smem, cudaStream_t stream)
 {
-    static bool attr_set = false;
-    if (!attr_set) {
-        PAPR_CUDA_TRY(cudaFuncSetAttribute(linear_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-        attr_set = true;
-    }
+    static SmemAttrOnce once;
+    PAPR_CUDA_TRY(ensure_dyn_smem(once, linear_kernel<EPI>, kMaxSmem));
     const int grid = (int)(p.n_tiles < kNumSMs ? p.n_tiles : kNumSMs);
     linear_kernel<EPI><<<grid, kLinThreads, smem, stream>>>(p);
     return check_launch();

@@ -1366,11 +1366,8 @@ extern "C" int papr_attn_prologue_fwd(const float *rays_o, const float *rays_d, 
     if (kin_f32 || vin_f32) attn_prologue_fwd_kernel<<<row_grid(R), kRowThreads, 0, (cudaStream_t)stream>>>(p);
     else if (L == 6 && F == 64 && p.nblk_k == 2 && p.nblk_v == 3 && !getenv("PAPR_PROLOGUE_HALFWARP")) {
         constexpr int smem = kRowWarps * 3 * 4096;
-        static bool attr_set = false;
-        if (!attr_set) {
-            PAPR_CUDA_TRY(cudaFuncSetAttribute(attn_prologue_fwd_rows_kernel<6, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            attr_set = true;
-        }
+        static SmemAttrOnce once;
+        PAPR_CUDA_TRY(ensure_dyn_smem(once, attn_prologue_fwd_rows_kernel<6, 64>, smem));
         const int64_t groups = ((R * K + 127) / 128 * 128 + kRowThreads - 1) / kRowThreads;
         attn_prologue_fwd_rows_kernel<6, 64><<<(int)(groups < 2 * kNumSMs ? groups : 2 * kNumSMs), kRowThreads, smem, (cudaStream_t)stream>>>(p);
     } else attn_prologue_fwd_fast_kernel<<<row_grid(R), kRowThreads, 0, (cudaStream_t)stream>>>(p);
@@ -1396,11 +1393,8 @@ extern "C" int papr_attn_prologue_bwd(const float *rays_o, const float *rays_d, 
     if (dkin_f32 || dvin_f32) attn_prologue_bwd_kernel<<<row_grid(R), kRowThreads, 0, (cudaStream_t)stream>>>(p);
     else if (L == 6 && F == 64 && p.nblk_k == 2 && p.nblk_v == 3 && !getenv("PAPR_PROLOGUE_HALFWARP")) {
         constexpr int smem = 4 * 5 * 4096;
-        static bool attr_set = false;
-        if (!attr_set) {
-            PAPR_CUDA_TRY(cudaFuncSetAttribute(attn_prologue_bwd_rows_kernel<6, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            attr_set = true;
-        }
+        static SmemAttrOnce once;
+        PAPR_CUDA_TRY(ensure_dyn_smem(once, attn_prologue_bwd_rows_kernel<6, 64>, smem));
         const int64_t groups = ((R * K + 127) / 128 * 128 + 127) / 128;
         attn_prologue_bwd_rows_kernel<6, 64><<<(int)(groups < 2 * kNumSMs ? groups : 2 * kNumSMs), 128, smem, (cudaStream_t)stream>>>(p);
     } else attn_prologue_bwd_fast_kernel<<<row_grid(R), kRowThreads, 0, (cudaStream_t)stream>>>(p);
@@ -1420,11 +1414,8 @@ extern "C" int papr_score_blend_fwd(const void *h5, const float *h5_f32, const f
     p.bkg_score = bkg_score; p.eps = eps; p.fused = fused; p.attn = attn; p.sc = sc; p.stats = stats;
     if (h5 && !h5_f32 && K >= 16 && !getenv("PAPR_SCORE_WARP")) {
         constexpr int smem = kRowWarps * 4 * 4096;
-        static bool attr_set = false;
-        if (!attr_set) {
-            PAPR_CUDA_TRY(cudaFuncSetAttribute(score_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            attr_set = true;
-        }
+        static SmemAttrOnce once;
+        PAPR_CUDA_TRY(ensure_dyn_smem(once, score_rows_kernel, smem));
         const int64_t groups = (R * K + kRowThreads - 1) / kRowThreads;
         score_rows_kernel<<<(int)(groups < kNumSMs ? groups : kNumSMs), kRowThreads, smem, (cudaStream_t)stream>>>(p);
         PAPR_CUDA_TRY(cudaGetLastError());

@@ -446,12 +446,10 @@ extern "C" int papr_stack_bf16(const void *x, int K0, const papr_stack_layer *la
     if (p.stages > 8) p.stages = 8;
     if (p.stages < 2) return PAPR_ERR_INVALID_ARGUMENT;
     const int smem = fixed + p.stages * kStageBytes;
-    static bool attr_set = false;
-    if (!attr_set) {
-        PAPR_CUDA_TRY(cudaFuncSetAttribute(stack_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStkMaxSmem));
-        PAPR_CUDA_TRY(cudaFuncSetAttribute(stack_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStkMaxSmem));
-        attr_set = true;
-    }
+    static SmemAttrOnce once;
+    PAPR_CUDA_TRY(ensure_dyn_smem(once, stack_kernel<true>, kStkMaxSmem));
+    static SmemAttrOnce once1;
+    PAPR_CUDA_TRY(ensure_dyn_smem(once1, stack_kernel<false>, kStkMaxSmem));
     const int64_t n_quads = (p.n_tiles + 3) / 4;
     const int grid = (int)(2 * (n_quads < kNumSMs / 2 ? n_quads : kNumSMs / 2));
     if (slope == 0.f) stack_kernel<true><<<grid, kStkThreads, smem, (cudaStream_t)stream>>>(p);

@@ -134,11 +134,8 @@ extern "C" int papr_wgrad_bf16(const void *a_blocked, int a_cols, const void *b_
     p.stages = (232448 - 1024 - 1024) / stage_bytes;
     if (p.stages > 8) p.stages = 8;
     const int smem = 1024 + p.stages * stage_bytes + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
-        PAPR_CUDA_TRY(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-        attr_set = true;
-    }
+    static SmemAttrOnce once;
+    PAPR_CUDA_TRY(ensure_dyn_smem(once, wgrad_kernel, 232448));
     const int grid = (int)(p.n_units < kNumSMs ? p.n_units : kNumSMs);
     wgrad_kernel<<<grid, kWgThreads, smem, (cudaStream_t)stream>>>(p);
     return check_launch();
