@@ -13,7 +13,7 @@ from papr_b200.config import Config, make_config, merge
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_abi_library_exports_every_declared_symbol():
+def test_abi_library_exports_every_declared_symbol(built_library):
     from papr_b200 import _lib
     header = open(os.path.join(ROOT, "include", "papr_b200.h")).read()
     declared = set(re.findall(r"^(?:int|const char \*)\s*(papr_[a-z0-9_]+)\s*\(", header, re.M))
