@@ -15,8 +15,9 @@ The key stack's output LayerNorm, w_k and the dot with the query are folded alge
   score = q'.(W_k LN(h5) + b_k)/sqrt d = ua . z(h5) + c'   with z the normalised h5,
 which removes one 256x256 GEMM per row; its parameters therefore get their gradients through ua and c' (autograd).
 
-precision="fp32" keeps every CUDA-core kernel but routes the GEMMs through torch fp32 matmuls; it exists for the
-1e-5 parity tests, the bf16 tensor-core path is the product.
+precision="fp32" is the parity mode: the same CUDA-core kernels (fp32 taps instead of bf16 tiles) and every GEMM on the
+library's own tensor-core kernels at fp32 accuracy through a three-way bf16 split (papr_b200/split_gemm.py), so the
+1e-5 assertions of the tests exercise linear_kernel / wgrad_kernel themselves.  The bf16 path is the product.
 """
 import math
 
@@ -24,8 +25,12 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import ops
+from . import ops, split_gemm
 from .nn import AttentionLayer, Embeddings, activation_slope
+
+#: GEMM engine of precision="fp32": "split" = the library's tensor-core kernels (three-way bf16 split); "torch" = torch
+#: fp32 matmuls, kept only to A/B the split path in tests/test_tc_gpu.py
+FP32_GEMM = "split"
 
 
 def posenc(x, L, factor=2.0, mult=1.0):
@@ -80,11 +85,18 @@ class _LinearBf16Fn(torch.autograd.Function):
 
 def _linear(x, lin, slope, precision):
     if precision == "fp32":
+        if FP32_GEMM == "split":
+            return split_gemm.linear(x, lin, slope)
         y = F.linear(x, lin.weight, lin.bias)
         if slope is not None:
             y = F.leaky_relu(y, slope) if slope else F.relu(y)
         return y
     return _LinearBf16Fn.apply(x, lin.weight, lin.bias, slope)
+
+
+def _mlp_fp32(mlp, x):
+    """An MLP stack in the fp32 parity mode."""
+    return split_gemm.mlp_forward(mlp, x) if FP32_GEMM == "split" else mlp(x)
 
 
 class _Shape:
@@ -101,6 +113,9 @@ class _Shape:
         self.score_relu, self.normalize, self.bkg_score = attn.score_relu, attn.normalize, attn.bkg_score
         self.k_skip = tuple(attn.embed.embed_k.mlp.skip_layers)
         self.v_skip = tuple(attn.embed.embed_v.mlp.skip_layers)
+        # grad mode of the CALLER: inside autograd.Function.forward it always reads False, and ctx.needs_input_grad
+        # mirrors requires_grad regardless of torch.no_grad(), so this is what decides whether a backward stash is kept
+        self.grad = torch.is_grad_enabled()
 
 
 def _prologue_fwd(sh, rays_o, rays_d, points, feats, idx, ln_a, ln_b, taps=False):
@@ -172,6 +187,35 @@ def _key_score_bwd(sh, d_score, h5, h5_32, stats, ua, tap=False):
         dh5.data_ptr(), _ptr(dh5_32), zsum.data_ptr(), dssum.data_ptr(), g_b5.data_ptr(),
         nbytes=sh.M * (1024.0 + 12) + sh.R * 2048.0)
     return dh5, dh5_32, zsum, dssum, g_b5
+
+
+def _stash_pack(seq):
+    """Flatten a list of Blocked / tensor / None into (tensors for ctx.save_for_backward, python spec).  The big buffers
+    have to go through save_for_backward: that is what torch.utils.checkpoint's saved-tensor hooks intercept, so a
+    checkpointed ray chunk really drops its stash after the forward and rebuilds it during backward."""
+    tensors, spec = [], []
+    for it in seq:
+        if it is None:
+            spec.append(None)
+        elif isinstance(it, ops.Blocked):
+            spec.append((it.rows, it.cols, it.cols_pad))
+            tensors.append(it.buf)
+        else:
+            spec.append("t")
+            tensors.append(it)
+    return tensors, spec
+
+
+def _stash_unpack(tensors, spec):
+    out, it = [], iter(tensors)
+    for sp in spec:
+        if sp is None:
+            out.append(None)
+        elif sp == "t":
+            out.append(next(it))
+        else:
+            out.append(ops.Blocked.wrap(next(it), *sp))
+    return out
 
 
 def _pad_bias(b, N):
@@ -319,30 +363,31 @@ class _StackBf16Fn(torch.autograd.Function):
     layers, sign bits drive the dgrad masks and the dgrad epilogues produce the bias gradients."""
 
     @staticmethod
-    def forward(ctx, x, slope, n, *wb):
+    def forward(ctx, x, slope, n, grad, *wb):
         ws, bs = wb[:n], wb[n:]
         xb = ops.Blocked.from_f32(x)
-        save = any(ctx.needs_input_grad)
+        save = grad and any(ctx.needs_input_grad)
         inputs, bits, y = _stack_forward(xb, [w.detach() for w in ws], bs, slope, x.shape[1], save, last_f32=True)
         n_out = ws[-1].shape[0]
         if save:
-            ctx.blocked = (inputs, bits)
+            tensors, ctx.spec = _stash_pack(list(inputs) + list(bits))
             ctx.slope, ctx.n, ctx.rows, ctx.n_in = slope, n, x.shape[0], x.shape[1]
-            ctx.save_for_backward(*ws)
+            ctx.save_for_backward(*ws, *tensors)
         return y[: x.shape[0], :n_out]
 
     @staticmethod
     def backward(ctx, gy):
-        ws = ctx.saved_tensors
-        inputs, bits = ctx.blocked
+        saved = ctx.saved_tensors
+        ws = saved[:ctx.n]
+        stash = _stash_unpack(saved[ctx.n:], ctx.spec)
+        inputs, bits = stash[:ctx.n], stash[ctx.n:]
         n_out = ws[-1].shape[0]
         g = gy.contiguous()
         dz = ops.Blocked.from_f32(g, cols_pad=max(ops.pad_cols(n_out), 128))
         gb_last = g.sum(0)
         in_pad = ops.pad_cols(ctx.n_in)
         dx, gWs, gbs = _stack_backward(dz, inputs, bits, ws, ctx.slope, gb_last, ctx.n_in, in_pad)
-        ctx.blocked = None
-        return (dx.to_f32(ctx.rows, ctx.n_in), None, None, *gWs, *gbs)
+        return (dx.to_f32(ctx.rows, ctx.n_in), None, None, None, *gWs, *gbs)
 
 
 class _QueryTailFn(torch.autograd.Function):
@@ -394,7 +439,7 @@ class RowAttentionFn(torch.autograd.Function):
         kw, kb = wb[:nk], wb[nk:2 * nk]
         nv = (len(wb) - 2 * nk) // 2
         vw, vb = wb[2 * nk:2 * nk + nv], wb[2 * nk + nv:]
-        save = any(ctx.needs_input_grad)
+        save = sh.grad and any(ctx.needs_input_grad)
         pts = points.detach().contiguous()
         fts = feats.detach().contiguous() if feats is not None else None
         kin, vin, _, _ = _prologue_fwd(sh, rays_o, rays_d, pts, fts, idx, ln_a.detach(), ln_b.detach())
@@ -406,8 +451,9 @@ class RowAttentionFn(torch.autograd.Function):
                                                   infl, idx, v)
         if save:
             ctx.sh, ctx.nk, ctx.nv = sh, nk, nv
-            ctx.blocked = (k_in, k_bits, h5, v_in, v_bits)
-            ctx.save_for_backward(rays_o, rays_d, idx, pts, infl, ua.detach(), ln_a.detach(), v, attn, sc, stats, *wb)
+            tensors, ctx.spec = _stash_pack(list(k_in) + list(k_bits) + [h5] + list(v_in) + list(v_bits))
+            ctx.save_for_backward(rays_o, rays_d, idx, pts, infl, ua.detach(), ln_a.detach(), v, attn, sc, stats, *wb,
+                                  *tensors)
         return fused, attn
 
     @staticmethod
@@ -415,9 +461,12 @@ class RowAttentionFn(torch.autograd.Function):
         sh, nk, nv = ctx.sh, ctx.nk, ctx.nv
         saved = ctx.saved_tensors           # one access only (non-reentrant checkpointing unpacks on access)
         rays_o, rays_d, idx, pts, infl, ua, ln_a, v, attn, sc, stats = saved[:11]
-        wb = saved[11:]
+        n_wb = 2 * nk + 2 * nv
+        wb = saved[11:11 + n_wb]
         kw, vw = wb[:nk], wb[2 * nk:2 * nk + nv]
-        k_in, k_bits, h5, v_in, v_bits = ctx.blocked
+        st = _stash_unpack(saved[11 + n_wb:], ctx.spec)
+        k_in, k_bits, h5 = st[:nk], st[nk:2 * nk], st[2 * nk]
+        v_in, v_bits = st[2 * nk + 1:2 * nk + 1 + nv], st[2 * nk + 1 + nv:]
         P = pts.shape[0]
         d_attn_c = d_attn.contiguous() if d_attn is not None else None
         dv, d_score, g_influ, g_bv = _blend_bwd(sh, d_fused.contiguous(), d_attn_c, attn, sc, infl, idx, v, P)
@@ -425,7 +474,6 @@ class RowAttentionFn(torch.autograd.Function):
         dh5, _, zsum, dssum, g_b5 = _key_score_bwd(sh, d_score, h5, None, stats, ua)
         d_kin, gkW, gkb = _stack_backward(dh5, k_in, k_bits, kw, sh.k_slope, g_b5, sh.dk, sh.dk_pad, sh.k_skip)
         g_points, g_feats, g_a, g_b = _prologue_bwd(sh, rays_o, rays_d, pts, idx, ln_a, d_kin, d_vin, None, None, P)
-        ctx.blocked = None
         return (None, None, None, None, g_points, g_feats, g_influ.reshape(-1, 1), zsum, dssum, g_a, g_b, None,
                 *gkW, *gkb, *gvW, *gvb)
 
@@ -434,8 +482,8 @@ class _PrologueFp32Fn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, sh, rays_o, rays_d, idx, points, feats, ln_a, ln_b):
         pts = points.detach().contiguous()
-        _, _, kin32, vin32 = _prologue_fwd(sh, rays_o, rays_d, pts, feats.detach().contiguous(), idx, ln_a.detach(),
-                                           ln_b.detach(), taps=True)
+        fts = feats.detach().contiguous() if feats is not None else None
+        _, _, kin32, vin32 = _prologue_fwd(sh, rays_o, rays_d, pts, fts, idx, ln_a.detach(), ln_b.detach(), taps=True)
         ctx.sh = sh
         ctx.save_for_backward(rays_o, rays_d, idx, pts, ln_a.detach())
         return kin32, vin32
@@ -498,6 +546,9 @@ class ProximityAttention(nn.Module):
             raise NotImplementedError("the B200 score kernel is specialised to d_model = key/query width = 256")
         if E.key.norm != "layernorm" or E.query.norm != "layernorm" or E.value.norm != "none":
             raise NotImplementedError("only key/query layernorm + value none (the shipped setting) is supported")
+        for part in (E.key, E.query, E.value):
+            if part.ff_last_act != "none":
+                raise NotImplementedError("ff_last_act other than 'none' is not used by any shipped config")
         self.k_slope = activation_slope(E.key.ff_act)
         self.v_slope = activation_slope(E.value.ff_act)
         self.q_slope = activation_slope(E.query.ff_act)
@@ -517,20 +568,22 @@ class ProximityAttention(nn.Module):
         q = fq.innorm(q)
         lins = fq.mlp.linears()
         if precision == "fp32":
-            q = fq.mlp(q)
+            q = _mlp_fp32(fq.mlp, q)
         elif fq.mlp.skip_layers:
             raise NotImplementedError("skip_layers in the query stack are not used by any shipped config")
         else:
-            q = _StackBf16Fn.apply(q, self.q_slope, len(lins), *[l.weight for l in lins], *[l.bias for l in lins])
+            q = _StackBf16Fn.apply(q, self.q_slope, len(lins), torch.is_grad_enabled(), *[l.weight for l in lins],
+                                   *[l.bias for l in lins])
         al = self.attention_layer
         scale = 1.0 / math.sqrt(self.d_model)
         on = self.embed.embed_k.outnorm
         if precision == "fp32":
             q = fq.outnorm(q)
             qp = _linear(q, al.w_q, None, precision)                           # q' (R,256)
-            u = (qp @ al.w_k.weight) * scale
+            wk_t = al.w_k.weight.t()
+            u = (split_gemm.matmul_t(qp, wk_t) if FP32_GEMM == "split" else qp @ al.w_k.weight) * scale
             ua = u * on.a_2
-            cprime = (u * on.b_2).sum(-1) + (qp @ al.w_k.bias) * scale
+            cprime = (u * on.b_2).sum(-1) + (qp * al.w_k.bias).sum(-1) * scale
             return ua, cprime
         # Everything after the normalisation z = (q - mean)/(std + eps) is linear in z (attn.py:39-42, 217-218, 53-54):
         #   q' = W_q (a_q z + b_q) + c_q ;  u = W_k^T q' / sqrt(d) ;  ua = u a_k ;  c' = u . b_k2 + q' . c_k / sqrt(d)
@@ -555,16 +608,18 @@ class ProximityAttention(nn.Module):
         fk, fv = self.embed.embed_k, self.embed.embed_v
         if precision == "fp32":
             kin, vin = _PrologueFp32Fn.apply(sh, rays_o, rd, idx, points, feats, fk.innorm.a_2, fk.innorm.b_2)
-            h5 = fk.mlp(kin)
-            v = fv.mlp(vin)
+            h5 = _mlp_fp32(fk.mlp, kin)
+            v = _mlp_fp32(fv.mlp, vin)
             return _ScoreBlendFp32Fn.apply(sh, idx, h5, v, ua, cprime, influ)
         klin, vlin = fk.mlp.linears(), fv.mlp.linears()
         wb = [l.weight for l in klin] + [l.bias for l in klin] + [l.weight for l in vlin] + [l.bias for l in vlin]
         return RowAttentionFn.apply(sh, rays_o, rd, idx, points, feats, influ, ua, cprime, fk.innorm.a_2, fk.innorm.b_2,
                                     len(klin), *wb)
 
-    #: bytes of backward stash per (ray, candidate) row in the bf16 path (layer inputs, sign bits, row statistics)
+    #: bytes per (ray, candidate) row alive at the peak of a call in the bf16 path: with the backward stash (layer
+    #: inputs, sign bits, row statistics) and without it (inference: kin, vin, h5, v only)
     STASH_BYTES_PER_ROW = 8192
+    INFER_BYTES_PER_ROW = 1536
 
     def forward(self, rays_o, rays_d, idx, points, feats, influ, precision=None, ray_chunk=None):
         """rays_o (N,3), rays_d (N,H,W,3), idx int32 (N,H,W,K) -> fused (R,C), attn (R,K+1); differentiable.
@@ -572,7 +627,8 @@ class ProximityAttention(nn.Module):
         ray_chunk: process at most that many rays of one view at a time.  Under autograd each chunk is checkpointed
         (its forward is recomputed during backward), so the backward stash is bounded by one chunk instead of growing
         with the frame -- the replacement for the reference's fixed 160x160 training patches when a whole frame (or a
-        1920x1080 one) is trained on at once.  None = automatic: chunk only if the stash would not fit in free memory."""
+        1920x1080 one) is trained on at once.  None = automatic: chunk only if the working set would not fit in free
+        memory (with or without grad)."""
         precision = precision or self.precision
         N, H, W, _ = rays_d.shape
         K = idx.shape[-1]
@@ -582,24 +638,28 @@ class ProximityAttention(nn.Module):
         rd = rays_d.detach().float().contiguous().reshape(N, H * W, 3)
         idx = idx.reshape(N, H * W, K).contiguous()
         grad = torch.is_grad_enabled()
-        if ray_chunk is None and grad and rd.is_cuda:
+        if ray_chunk is None and rd.is_cuda:
             free, _ = torch.cuda.mem_get_info(rd.device)
             free += torch.cuda.memory_reserved(rd.device) - torch.cuda.memory_allocated(rd.device)
-            need = N * H * W * K * self.STASH_BYTES_PER_ROW
+            per_row = self.STASH_BYTES_PER_ROW if grad else self.INFER_BYTES_PER_ROW
+            if precision == "fp32":
+                per_row *= 6
+            need = N * H * W * K * per_row
             if need > 0.8 * free:
-                ray_chunk = max(4096, int(0.4 * free / (K * self.STASH_BYTES_PER_ROW)) // 128 * 128)
-        if not ray_chunk or (N == 1 and H * W <= ray_chunk) or (N * H * W <= ray_chunk):
-            return self._rows(rays_o, rd.reshape(-1, 3), idx.reshape(-1, K), points, feats, influ, precision, N, H * W)
-        from torch.utils.checkpoint import checkpoint
-        fused, attn = [], []
-        for v in range(N):
-            for r0 in range(0, H * W, ray_chunk):
-                r1 = min(r0 + ray_chunk, H * W)
-                args = (rays_o[v:v + 1], rd[v, r0:r1], idx[v, r0:r1], points, feats, influ, precision, 1, r1 - r0)
-                if grad:
-                    f, a = checkpoint(self._rows, *args, use_reentrant=False)
-                else:
-                    f, a = self._rows(*args)
-                fused.append(f)
-                attn.append(a)
-        return torch.cat(fused), torch.cat(attn)
+                ray_chunk = max(4096, int(0.4 * free / (K * per_row)) // 128 * 128)
+        with torch.cuda.device(rd.device):      # the C ABI launches on the current device
+            if not ray_chunk or (N == 1 and H * W <= ray_chunk) or (N * H * W <= ray_chunk):
+                return self._rows(rays_o, rd.reshape(-1, 3), idx.reshape(-1, K), points, feats, influ, precision, N, H * W)
+            from torch.utils.checkpoint import checkpoint
+            fused, attn = [], []
+            for v in range(N):
+                for r0 in range(0, H * W, ray_chunk):
+                    r1 = min(r0 + ray_chunk, H * W)
+                    args = (rays_o[v:v + 1], rd[v, r0:r1], idx[v, r0:r1], points, feats, influ, precision, 1, r1 - r0)
+                    if grad:
+                        f, a = checkpoint(self._rows, *args, use_reentrant=False)
+                    else:
+                        f, a = self._rows(*args)
+                    fused.append(f)
+                    attn.append(a)
+            return torch.cat(fused), torch.cat(attn)

@@ -24,7 +24,7 @@ from .attention import ProximityAttention
 from .bookkeeping import add_points_knn
 from .nn import MappingMLP, make_activation
 from .renderer import get_generator
-from .schedule import create_learning_rate_fn
+from .schedule import create_learning_rate_fn, reposition
 
 
 def count_parameters(model):
@@ -245,7 +245,10 @@ class PAPR(nn.Module):
 
     # ------------------------------------------------------------------ the hot path (model.py:462-560)
     def _attend(self, rays_o, rays_d, c2w, step):
-        idx = self._get_points(rays_o, rays_d, c2w, step)
+        if not rays_d.is_cuda:
+            raise RuntimeError("papr_b200 needs CUDA tensors: there is no CPU path (and no fallback)")
+        with torch.cuda.device(rays_d.device):      # the C ABI launches on the current device
+            idx = self._get_points(rays_o, rays_d, c2w, step)
         feats = self.pc_feats if self.use_pc_feats else None
         return self.proximity_attn(rays_o, rays_d, idx, self.points, feats, self.points_influ_scores,
                                    precision=self.precision, ray_chunk=self.ray_chunk)
@@ -295,8 +298,15 @@ class PAPR(nn.Module):
                     optimizer.load_state_dict(osd[name])
             ssd = torch.load(os.path.join(load_dir, "schedulers.pth"))
             for name, scheduler in self.schedulers.items():
-                if scheduler is not None:
-                    scheduler.load_state_dict(ssd[name])
+                if scheduler is None:
+                    continue
+                sd = ssd[name]
+                if "lr_lambdas" in sd:
+                    scheduler.load_state_dict(sd)
+                else:
+                    # a reference checkpoint (SequentialLR state): our schedule is a closed form of the step count,
+                    # so repositioning it at the saved step reproduces the same learning rates
+                    reposition(scheduler, int(sd["last_epoch"]))
         spath = os.path.join(load_dir, "scaler.pth")
         if os.path.exists(spath):
             sd = torch.load(spath)
@@ -325,6 +335,7 @@ class PAPR(nn.Module):
                                                     requires_grad=self.points_influ_scores.requires_grad)
         if self.use_pc_feats:
             self.pc_feats = nn.Parameter(state_dict["pc_feats"].data.to(dev), requires_grad=self.pc_feats.requires_grad)
+        self._select_k = int(self.select_k)      # the buffer may just have been overwritten (e.g. a K=30 checkpoint)
         self._idx32 = None
 
 

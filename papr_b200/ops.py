@@ -154,6 +154,15 @@ class Blocked:
         return self.buf.data_ptr()
 
     @staticmethod
+    def wrap(buf, rows, cols, cols_pad):
+        """A Blocked view of existing storage (the inverse of handing .buf to ctx.save_for_backward)."""
+        out = Blocked.__new__(Blocked)
+        out.rows, out.cols, out.cols_pad = rows, cols, cols_pad
+        out.rows_pad = pad_rows(rows)
+        out.buf = buf
+        return out
+
+    @staticmethod
     def from_f32(t, cols_pad=None):
         t = _f32c(t)
         out = Blocked(t.shape[0], t.shape[1], t.device)

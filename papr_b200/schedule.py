@@ -46,15 +46,21 @@ class WarmupDecay:
         raise NotImplementedError(self.kind)
 
 
+def reposition(sched, step):
+    """Jump a closed-form scheduler to `step` in O(1) (the reference calls .step() `step` times)."""
+    if step <= 0:
+        return
+    sched.last_epoch = step - 1
+    sched._step_count = step
+    sched.optimizer._opt_called = True     # silence the "scheduler before optimizer" warning on the jump
+    sched.step()
+
+
 def create_learning_rate_fn(optimizer, max_steps, args, start_step=0):
     """Scheduler positioned at `start_step` (reference: create + step() x start_step)."""
     if args.type == "none":
         return None
     fn = WarmupDecay(args.type, args.warmup, max_steps, args.get("gamma", 1.0))
     sched = lr_scheduler.LambdaLR(optimizer, lr_lambda=fn)
-    if start_step > 0:
-        sched.last_epoch = start_step - 1
-        sched._step_count = start_step
-        optimizer._opt_called = True     # silence the "scheduler before optimizer" warning on the jump
-        sched.step()
+    reposition(sched, start_step)
     return sched

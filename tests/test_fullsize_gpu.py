@@ -83,3 +83,87 @@ def test_fullsize_tiles_equal_full_frame(frame):
     assert torch.equal(m._idx32, frame["idx"][:, 300:400, 500:600])
     assert float((f - frame["fused"][:, 300:400, 500:600]).abs().max()) == 0.0
     assert float((a - frame["attn"][:, 300:400, 500:600]).abs().max()) == 0.0
+
+
+# ----------------------------------------------------------------------------- RGB and gradients at the full size
+TILE = (352, 416, 384, 448)      # interior rows/cols of the checked tile (64 x 64), away from the frame border
+HALO = 16                        # UNet influence radius is 13 px: tile + halo reproduces the full frame
+
+
+def _tile_oracle(frame, with_grad):
+    """The CPU oracle on tile + halo (96 x 96 rays of the 800x800 frame, all 30,000 points).  The loss is the MSE over the
+    tile interior only, so its gradients equal those of the same masked loss on the whole frame."""
+    r0, r1, c0, c1 = TILE
+    rd = frame["rays_d"][:, r0 - HALO:r1 + HALO, c0 - HALO:c1 + HALO].contiguous()
+    tgt = torch.rand(1, r1 - r0, c1 - c0, 3, generator=torch.Generator().manual_seed(11))
+    params = {k: v.clone().requires_grad_(with_grad and v.dtype.is_floating_point and k != "bkg_feats")
+              for k, v in frame["params"].items()}
+    with torch.set_grad_enabled(with_grad):
+        out = O.forward(params, frame["cfg"], frame["rays_o"], rd)
+        rgb = out["rgb"][:, HALO:-HALO, HALO:-HALO]
+        loss = ((rgb - tgt) ** 2).mean()
+        if with_grad:
+            loss.backward()
+    grads = {k: params[k].grad for k in ("points", "points_influ_scores", "pc_feats")} if with_grad else None
+    return rd, tgt, rgb.detach(), float(loss), grads, out["fused"].detach(), out["attn"].detach()
+
+
+@pytest.fixture(scope="module")
+def tile_truth(frame):
+    return _tile_oracle(frame, with_grad=True)
+
+
+def test_fullsize_rgb_and_gradients_bf16_whole_frame(frame, tile_truth):
+    """Product path on the WHOLE 800x800 frame (P=30k): forward + backward of a loss masked to the tile; RGB on the tile
+    and the point / feature / influence gradients against the CPU oracle (stated bf16 tolerances, tests/test_model_gpu.py)."""
+    from tests.parity import rel_err
+    r0, r1, c0, c1 = TILE
+    _, tgt, want_rgb, want_loss, want_g, _, _ = tile_truth
+    m = frame["model"]
+    m.clear_grad()
+    rgb = m(frame["rays_o"].cuda(), frame["rays_d"].cuda(), None)
+    tile = rgb[:, r0:r1, c0:c1]
+    loss = ((tile - tgt.cuda()) ** 2).mean()
+    loss.backward()
+    e_rgb = float((tile.detach().cpu() - want_rgb).abs().max())
+    print(f"full frame bf16: tile rgb max-abs err {e_rgb:.2e}, loss {loss.item():.6f} vs {want_loss:.6f}")
+    assert e_rgb <= 1.5e-2
+    assert abs(loss.item() - want_loss) <= 2e-3
+    for attr in ("points", "points_influ_scores", "pc_feats"):
+        got, want = getattr(m, attr).grad.cpu(), want_g[attr]
+        l2 = float((got - want).double().norm()) / float(want.double().norm())
+        cos = float(torch.nn.functional.cosine_similarity(got.flatten().double(), want.flatten().double(), dim=0))
+        print(f"   {attr}: relative L2 {l2:.3e} cosine {cos:.5f} max-abs/max {rel_err(got, want):.3e}")
+        assert l2 <= 0.2 and cos >= 0.98, (attr, l2, cos)
+        assert int((got != 0).sum()) > 0 and bool(((want != 0) | (got.abs() <= 1e-3 * float(want.abs().max()))).all()), \
+            "a point outside the tile's receptive field received a gradient"
+    m.clear_grad()
+
+
+def test_fullsize_rgb_and_gradients_fp32_tile(frame, tile_truth):
+    """Parity mode (fp32-accurate GEMMs on the library's own tensor-core kernels) on the same tile + halo rays: attention
+    weights / features 1e-5, RGB 1e-4 (north star: 1e-3), gradients within the reference's own fp32 noise."""
+    from papr_b200.model import PAPR
+    from tests.parity import rel_err
+    rd, tgt, want_rgb, want_loss, want_g, want_fused, want_attn = tile_truth
+    cfg = frame["cfg"]
+    m = PAPR(cfg, device="cuda", precision="fp32").cuda()
+    m.load_my_state_dict({k: v.clone() for k, v in frame["params"].items()})
+    m.clear_grad()
+    rgb = m(frame["rays_o"].cuda(), rd.cuda(), None)
+    tile = rgb[:, HALO:-HALO, HALO:-HALO]
+    loss = ((tile - tgt.cuda()) ** 2).mean()
+    loss.backward()
+    with torch.no_grad():
+        fused, attn = m.evaluate(frame["rays_o"].cuda(), rd.cuda(), None)
+    e_rgb = float((tile.detach().cpu() - want_rgb).abs().max())
+    e_attn = float((attn.squeeze(-1).cpu() - want_attn).abs().max())
+    e_fused = rel_err(fused.squeeze(-2).cpu(), want_fused)
+    print(f"tile fp32: rgb {e_rgb:.2e} attn {e_attn:.2e} fused {e_fused:.2e} loss {loss.item():.7f} vs {want_loss:.7f}")
+    assert e_attn <= 1e-5 and e_fused <= 1e-5 and e_rgb <= 1e-4
+    assert abs(loss.item() - want_loss) <= 1e-5
+    for attr in ("points", "points_influ_scores", "pc_feats"):
+        got, want = getattr(m, attr).grad.cpu(), want_g[attr]
+        e = rel_err(got, want)
+        print(f"   {attr}: max-abs/max vs reference fp32 {e:.3e}")
+        assert e <= 5e-3, (attr, e)

@@ -110,3 +110,37 @@ def test_linear_addend_split_k():
     pre = _bf(torch.cat([h, inp], 1)) @ _bf(w).t() + b
     want = torch.where(pre > 0, pre, 0.2 * pre)
     assert (y[:rows] - want).abs().max().item() < 3e-3
+
+
+# ----------------------------------------------------------------------------- fp32 parity mode on the same kernels
+@pytest.mark.parametrize("n_in,n_out,slope", [(117, 256, 0.0), (256, 256, 0.2), (398, 256, None), (256, 32, None),
+                                              (39, 256, 0.0), (256, 3, None)])
+def test_split_linear_is_fp32_accurate(n_in, n_out, slope):
+    """papr_b200.split_gemm: three-way bf16 split through papr_linear_bf16 / papr_wgrad_bf16 == fp32 Linear (forward,
+    data gradient, weight gradient, bias gradient), judged against a float64 evaluation and against torch's own fp32."""
+    from papr_b200 import split_gemm
+    g = torch.Generator(device="cuda").manual_seed(n_in * 3 + n_out)
+    rows = 1000
+    x = (torch.randn(rows, n_in, device="cuda", generator=g) * 3).requires_grad_(True)
+    w = (torch.randn(n_out, n_in, device="cuda", generator=g) / n_in ** 0.5).requires_grad_(True)
+    b = torch.randn(n_out, device="cuda", generator=g).requires_grad_(True)
+    gy = torch.randn(rows, n_out, device="cuda", generator=g)
+
+    def act(t):
+        return t if slope is None else torch.nn.functional.leaky_relu(t, slope)
+
+    y = split_gemm.SplitLinearFn.apply(x, w, b, slope)
+    y.backward(gy)
+    got = [y.detach(), x.grad.clone(), w.grad.clone(), b.grad.clone()]
+    outs = {}
+    for dt in (torch.float64, torch.float32):
+        xd, wd, bd = (t.detach().to(dt).requires_grad_(True) for t in (x, w, b))
+        yd = act(xd @ wd.t() + bd)
+        yd.backward(gy.to(dt))
+        outs[dt] = [yd.detach(), xd.grad, wd.grad, bd.grad]
+    for name, a, t64, t32 in zip(("y", "gx", "gw", "gb"), got, outs[torch.float64], outs[torch.float32]):
+        scale = float(t64.abs().max())
+        e_ours = float((a.double() - t64).abs().max()) / scale
+        e_torch = float((t32.double() - t64).abs().max()) / scale
+        print(f"split {n_in}->{n_out} {name}: ours {e_ours:.2e}  torch fp32 {e_torch:.2e}")
+        assert e_ours <= max(2e-6, 4 * e_torch), (name, e_ours, e_torch)

@@ -119,3 +119,58 @@ def test_ray_chunking_with_checkpointing_matches_unchunked():
     for n in g_a:
         denom = max(float(g_a[n].abs().max()), 1e-12)
         assert float((g_a[n] - g_b[n]).abs().max()) / denom < 2e-2, n     # atomics + bf16 column sums reorder slightly
+
+
+def test_checkpointed_chunks_bound_the_backward_stash():
+    """The stash of a checkpointed chunk goes through save_for_backward, so peak memory follows ray_chunk, not the frame
+    (it used to live in a Python attribute that checkpoint could not drop)."""
+    model, cfg = _model()
+    b = _batch(cfg, 96, 128, views=1)          # 12,288 rays x K=20 = 245,760 rows -> ~1.9 GB of stash unchunked
+    tgt = torch.rand_like(b["target"])
+
+    def peak(chunk):
+        model.ray_chunk = chunk
+        model.clear_grad()
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+        torch.cuda.reset_peak_memory_stats()
+        base = torch.cuda.memory_allocated()
+        out = model(b["rays_o"], b["rays_d"], b["c2w"])
+        torch.mean((out - tgt) ** 2).backward()
+        torch.cuda.synchronize()
+        return torch.cuda.max_memory_allocated() - base
+
+    full = peak(10 ** 9)
+    eighth = peak(96 * 128 // 8)
+    print(f"peak bytes above baseline: unchunked {full / 2**20:.0f} MiB, 8 chunks {eighth / 2**20:.0f} MiB")
+    assert eighth < 0.4 * full, (full, eighth)
+
+
+def test_inference_keeps_no_backward_stash():
+    """Under torch.no_grad() the stacks must not write layer inputs / sign bits (needs_input_grad is True
+    there); peak memory of evaluate() stays near the 1.5 KB/row working set instead of the 8 KB/row stash."""
+    model, cfg = _model()
+    b = _batch(cfg, 96, 128, views=1)
+    rows = 96 * 128 * 20
+
+    def peak(fn):
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+        torch.cuda.reset_peak_memory_stats()
+        base = torch.cuda.memory_allocated()
+        fn()
+        torch.cuda.synchronize()
+        return torch.cuda.max_memory_allocated() - base
+
+    def infer():
+        with torch.no_grad():
+            model.evaluate(b["rays_o"], b["rays_d"], b["c2w"])
+
+    def train_fwd():
+        model.clear_grad()
+        out = model(b["rays_o"], b["rays_d"], b["c2w"])
+        out.sum().backward()
+
+    p_inf, p_trn = peak(infer), peak(train_fwd)
+    print(f"bytes/row: inference {p_inf / rows:.0f}, training {p_trn / rows:.0f}")
+    assert p_inf / rows < 2600 and p_inf < 0.5 * p_trn
