@@ -79,10 +79,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kStkThreads, 1) stac
     const int64_t n_quads = (p.n_tiles + 3) >> 2;
     const int L = p.n_layers;
 
+    // The stash writer takes part in releasing a slot only when it has to read the LAST layer's tile out of it.  (It must
+    // not arrive otherwise: with nothing to wait for it would run whole quads ahead of the epilogue warps and its early
+    // arrivals would complete in_free phases that the epilogue has not reached -- a hang at scale, inference only.)
+    const bool writer_on_last = p.L[L - 1].out_blocked != nullptr;
     if (threadIdx.x == 0) {
         for (int i = 0; i < 8; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); mbar_init(&pw_full[i], 1); }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&in_full[i], 1); mbar_init(&pin_full[i], 1); mbar_init(&in_free[i], 17);
+            mbar_init(&in_full[i], 1); mbar_init(&pin_full[i], 1); mbar_init(&in_free[i], writer_on_last ? 17 : 16);
             mbar_init(&st_ready[i], 16); mbar_init(&st_done[i], 1);
             mbar_init(&act_ready[i], 32); mbar_init(&acc_full[i], 1);
         }
@@ -155,7 +159,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kStkThreads, 1) stac
                             }
                             mbar_arrive(&st_done[s]);
                         }
-                        if (l == L - 1) mbar_arrive(&in_free[s]);      // the producer may refill the slot
+                        if (l == L - 1 && stash) mbar_arrive(&in_free[s]);      // the producer may refill the slot
                     }
                     if (stash) ++sj;
                 }

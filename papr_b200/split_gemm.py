@@ -40,8 +40,9 @@ def split_linear(x, w, bias=None, slope=None):
     slope: None = no activation, 0.0 = relu, > 0 = leaky relu."""
     M, n_in = x.shape
     n_out = w.shape[0]
-    if n_out > 256:
-        raise NotImplementedError("split_linear: at most 256 output features")
+    if n_out > _KMAX:       # e.g. the data gradient of a skip layer (398 inputs): one pass per 256 output features
+        return torch.cat([split_linear(x, w[o0:o1], None if bias is None else bias[o0:o1], slope)
+                          for o0, o1 in _chunks(n_out)], dim=1)
     N = (n_out + 31) // 32 * 32
     act = slope is not None
     b = None

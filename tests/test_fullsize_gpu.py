@@ -63,9 +63,9 @@ def test_fullsize_attention_matches_oracle_on_sampled_rays(frame):
         want = O.attention_features(frame["params"], frame["cfg"], frame["rays_o"], rd, idx=idx)
     got_fused = frame["fused"].reshape(-1, 32)[pick.cuda()].cpu()
     got_attn = frame["attn"].reshape(-1, 21)[pick.cuda()].cpu()
-    assert float((got_attn - want["attn"].reshape(-1, 21)).abs().max()) <= 2e-2
+    assert float((got_attn - want["attn"].reshape(-1, 21)).abs().max()) <= 7e-3      # stated bf16 tolerance (test_model_gpu.py)
     scale = float(want["fused"].abs().max())
-    assert float((got_fused - want["fused"].reshape(-1, 32)).abs().max()) <= 4e-2 * scale
+    assert float((got_fused - want["fused"].reshape(-1, 32)).abs().max()) <= 1.5e-2 * scale
 
 
 def test_fullsize_attention_weights_are_a_distribution(frame):
@@ -127,14 +127,14 @@ def test_fullsize_rgb_and_gradients_bf16_whole_frame(frame, tile_truth):
     loss.backward()
     e_rgb = float((tile.detach().cpu() - want_rgb).abs().max())
     print(f"full frame bf16: tile rgb max-abs err {e_rgb:.2e}, loss {loss.item():.6f} vs {want_loss:.6f}")
-    assert e_rgb <= 1.5e-2
-    assert abs(loss.item() - want_loss) <= 2e-3
+    assert e_rgb <= 9e-3             # stated bf16 tolerance; measured 1.5e-3 here
+    assert abs(loss.item() - want_loss) <= 5e-4
     for attr in ("points", "points_influ_scores", "pc_feats"):
         got, want = getattr(m, attr).grad.cpu(), want_g[attr]
         l2 = float((got - want).double().norm()) / float(want.double().norm())
         cos = float(torch.nn.functional.cosine_similarity(got.flatten().double(), want.flatten().double(), dim=0))
         print(f"   {attr}: relative L2 {l2:.3e} cosine {cos:.5f} max-abs/max {rel_err(got, want):.3e}")
-        assert l2 <= 0.2 and cos >= 0.98, (attr, l2, cos)
+        assert l2 <= 0.1 and cos >= 0.995, (attr, l2, cos)     # measured: L2 <= 4.6e-2, cosine >= 0.9989
         assert int((got != 0).sum()) > 0 and bool(((want != 0) | (got.abs() <= 1e-3 * float(want.abs().max()))).all()), \
             "a point outside the tile's receptive field received a gradient"
     m.clear_grad()

@@ -7,10 +7,14 @@ Two precisions are checked:
          is 2.7e-3 away from a float64 evaluation on chair_12x12_p800: the PE derivative multiplies by 2^5 and
          cancels), so they are checked two ways: within 5e-3 of the reference's fp32 values, and no further from a
          float64 evaluation of the oracle than max(1e-3, 3x the reference's own fp32 distance from it).
-  bf16 : the product path (tcgen05 bf16 GEMMs, fp32 accumulation).  Stated bf16 tolerance: attention weights 2e-2
-         absolute, aggregated features 4e-2 relative to their scale, RGB 3e-2 max-abs; gradients: relative L2 error
-         <= 0.2 and cosine similarity >= 0.98 against the reference (measured: L2 0.004-0.15, cosine >= 0.99); the worst
-         single entry may be off by up to 0.35 of the gradient's max-abs (measured 0.03-0.27 on these tiny fixtures).
+  bf16 : the product path (tcgen05 bf16 GEMMs, fp32 accumulation).  Stated bf16 tolerance = 2x the worst error measured
+         over all fixtures on B200 (tools/error_budget.py, profiles/r02_error_budget.md): candidate attention weights
+         2e-3 absolute (measured 8.3e-4), background weight 7e-3 (3.2e-3), aggregated features 1.5e-2 relative to their
+         scale (7.5e-3), RGB 9e-3 max-abs (4.3e-3).  The RGB error is owed to the bf16 key stack (a 3e-3 error of the
+         background weight multiplies the colour); the bf16 UNet alone contributes <= 8.7e-4.  Gradients: relative L2
+         error <= 0.2 and cosine similarity >= 0.98 against the reference (measured: L2 0.004-0.15, cosine >= 0.99); the
+         worst single entry may be off by up to 0.35 of the gradient's max-abs (measured 0.03-0.27 on these tiny fixtures).
+  The fp32 mode's GEMMs run on the library's own tensor-core kernels (papr_b200/split_gemm.py), not on torch.matmul.
 """
 import pytest
 import torch
@@ -86,7 +90,7 @@ def test_forward_and_evaluate_match_reference(golden_dir, name, precision):
     if precision == "fp32":
         assert e_attn <= 1e-5 and e_bkg <= 1e-5 and e_fused <= 1e-5 and e_rgb <= 1e-4
     else:
-        assert e_attn <= 2e-2 and e_bkg <= 2e-2 and e_fused <= 4e-2 and e_rgb <= 3e-2
+        assert e_attn <= 2e-3 and e_bkg <= 7e-3 and e_fused <= 1.5e-2 and e_rgb <= 9e-3
 
 
 @pytest.mark.parametrize("name", GOLDEN_CASES)
@@ -162,7 +166,7 @@ def test_against_oracle_medium(precision):
     if precision == "fp32":
         assert e_attn <= 1e-5 and e_fused <= 1e-5 and e_rgb <= 1e-4
     else:
-        assert e_attn <= 2e-2 and e_fused <= 4e-2 and e_rgb <= 3e-2
+        assert e_attn <= 7e-3 and e_fused <= 1.5e-2 and e_rgb <= 9e-3
 
 
 @pytest.mark.parametrize("K,P", [(1, 50), (31, 200), (20, 21)])

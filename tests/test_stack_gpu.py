@@ -89,3 +89,43 @@ def test_stack_dgrad_matches_per_layer(rows):
         assert torch.equal(outs[j].to_f32(), ref[j].to_f32()), f"dgrad step {j}"
         if css[j] is not None:
             assert (css[j] - ref_cs[j]).abs().max().item() <= 1e-3 * max(1.0, ref_cs[j].abs().max().item())
+
+
+@pytest.mark.parametrize("rows", [128 * 5, 128 * 4 * 74 * 9 + 77])
+@pytest.mark.parametrize("dims,last_f32", [((142, 256, 256, 256, 256, 256, 256, 256, 32), True), ((117, 256, 256, 256, 256, 256), False),
+                                           ((39, 256, 256, 256), True)])
+def test_stack_inference_mode_at_scale(rows, dims, last_f32):
+    """Inference form of the fused stack: nothing leaves the SM except the last layer's output (fp32 row-major for the
+    value / query stacks, a tile for the key stack), over many quads per cluster.  Round 1 only ever ran this form with a
+    tile output on the last layer; with a pure fp32 output the stash-writer thread had nothing to wait for, ran ahead and
+    broke the slot-release barrier (a hang at full frame size).  Must equal the per-layer kernels bit for bit."""
+    from papr_b200 import ops
+    ws, bs = _weights(dims, rows % 1000 + len(dims))
+    g = torch.Generator(device="cuda").manual_seed(2)
+    x = ops.Blocked.from_f32(torch.randn(rows, dims[0], device="cuda", generator=g))
+    n = len(ws)
+    K0 = (dims[0] + 15) // 16 * 16
+    h = x
+    for i, (w, b) in enumerate(zip(ws, bs)):
+        last = i == n - 1
+        N, K = (w.shape[0] + 31) // 32 * 32, (w.shape[1] + 15) // 16 * 16
+        yb, yf, _ = ops.linear_bf16(h, ops.pack_weight(w, N, K), N, K, bias=b, act=not last, slope=0.0,
+                                    out_blocked=not (last and last_f32), out_f32=last and last_f32)
+        h = yb
+    layers = []
+    for i, (w, b) in enumerate(zip(ws, bs)):
+        last = i == n - 1
+        N, K = (w.shape[0] + 31) // 32 * 32, (w.shape[1] + 15) // 16 * 16
+        spec = dict(w_image=ops.pack_weight(w, N, K, replicas=ops.WEIGHT_REPLICAS), N=N, bias=b, act=not last)
+        if last and last_f32:
+            spec["out_f32"] = torch.zeros((x.rows_pad, N), device="cuda")
+        elif last:
+            spec["out_blocked"] = ops.Blocked(rows, N, "cuda")
+        layers.append(spec)
+    for _ in range(3):
+        ops.stack_bf16(x, K0, layers, slope=0.0)
+    torch.cuda.synchronize()
+    if last_f32:
+        assert torch.equal(layers[-1]["out_f32"][:rows], yf[:rows])
+    else:
+        assert torch.equal(layers[-1]["out_blocked"].to_f32(), yb.to_f32())
