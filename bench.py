@@ -7,8 +7,13 @@ ours      : one training step = clear_grad -> PAPR.forward (select, proximity at
             backward -> (N>1: flat-bucket gradient all-reduce) -> Adam, on BASELINE.json configs[1]: chair.yml
             hyper-parameters, one full 800x800 frame of rays per GPU per step, 30,000 points, K=20, bf16 tcgen05 GEMMs.
             Weak scaling: every rank trains on its own view; `value` = total rays / max-over-ranks step time.
+            Extra keys: `render` (configs[2]: one 800x800 frame, rows sharded over the ranks with a UNet halo, no
+            communication), `c4` / `c5` (configs[3], [4]: one Caterpillar-shaped 1920x1080 frame, P=100k, L=4, rows
+            sharded over the ranks + gradient all-reduce; c5 adds the exposure FiLM), `gpu_reference` (the oracle port
+            of the reference's own PyTorch path on the same GPU, fp32 and bf16 autocast), `cpu_baseline`.
 reference : the CPU oracle (oracle/papr_oracle.py, a pinned restatement of the reference's own PyTorch CPU path) on a
-            bounded sample of the same workload with all host threads (rank 0 only).
+            100x100-ray tile of the same frame (the reference's own test.py tile size, configs/default.yml:238-239) with
+            all host threads (rank 0 only).
 Prints ONE JSON line.
 """
 import argparse
@@ -29,6 +34,7 @@ METRIC = "train rays/sec (fwd+bwd), whole job"
 UNIT = "rays/s"
 FLOP_PER_RAY_TRAIN = 102.5e6     # 34.18 Mflop forward x 3
 FLOP_PER_RAY_FWD = 34.18e6
+WORKLOAD = "chair.yml train step, one {hw}x{hw} frame of rays per GPU, P={P} points, K=20, F=64, L=6, bf16 tcgen05 GEMMs"
 
 
 def load_peaks():
@@ -67,13 +73,17 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         try:
             for line in open(self.path):
                 f = [x.strip() for x in line.split(",")]
                 if len(f) < 9:
                     continue
                 sm.append(float(f[1])); mx.append(float(f[2]))
+                try:
+                    pw.append(float(f[3]))
+                except ValueError:
+                    pass
                 for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
                     if val.lower().startswith("active"):
                         reasons.add(name)
@@ -81,30 +91,65 @@ class ClockSampler:
         except Exception:
             pass
         if sm:
-            out = dict(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+            out = dict(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm),
+                       power_w_max=max(pw) if pw else None)
         return out
 
 
-def oracle_train_sample(hw, P, threads, steps, warmup):
-    """Times the CPU oracle (fwd + bwd of the same loss) on an hw x hw tile of the workload.  Returns rays/s."""
+# ----------------------------------------------------------------------------------------------- reference legs
+def oracle_train_sample(hw, P, steps, warmup, device="cpu", autocast=None, threads=None):
+    """Times the oracle port of the reference's PyTorch path (fwd + bwd of the same MSE loss) on an hw x hw tile of the
+    800x800 workload, on the CPU (all host threads) or -- the "GPU reference" -- on the same B200 through stock PyTorch
+    kernels (the reference's own materialised-distance + torch.topk selection, cuBLAS / cuDNN).  Returns (rays/s, s/step)."""
     from oracle import papr_oracle as O
     from papr_b200.config import make_config
-    torch.set_num_threads(threads)
+    if threads:
+        torch.set_num_threads(threads)
     cfg = make_config("chair", use_amp=False)
     params = O.init_params(cfg, P, seed=1, cloud="shell")
-    rays_o, rays_d, _ = O.synthetic_rays(800, 800, cfg.dataset.coord_scale, n_views=1, seed=1, h0=380, h1=380 + hw, w0=380, w1=380 + hw)
+    lo = (800 - hw) // 2
+    rays_o, rays_d, _ = O.synthetic_rays(800, 800, cfg.dataset.coord_scale, n_views=1, seed=1, h0=lo, h1=lo + hw, w0=lo, w1=lo + hw)
     tgt = torch.rand(1, hw, hw, 3, generator=torch.Generator().manual_seed(3))
+    if device != "cpu":
+        params = {k: v.to(device) for k, v in params.items()}
+        rays_o, rays_d, tgt = rays_o.to(device), rays_d.to(device), tgt.to(device)
     times = []
     for it in range(warmup + steps):
         pg = {k: v.clone().requires_grad_(v.dtype.is_floating_point and k != "bkg_feats") for k, v in params.items()}
+        if device != "cpu":
+            torch.cuda.synchronize()
         t0 = time.perf_counter()
-        out = O.forward(pg, cfg, rays_o, rays_d)
+        out = O.forward(pg, cfg, rays_o, rays_d, autocast_dtype=autocast)
         loss = ((out["rgb"] - tgt) ** 2).mean()
         loss.backward()
+        if device != "cpu":
+            torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
+        del out, loss, pg
     return hw * hw / statistics.median(times), statistics.median(times)
+
+
+def gpu_reference(P, dev):
+    """The bar SURVEY.md section 8(d) names: the reference's PyTorch path on one B200 (oracle port, stock torch kernels),
+    fp32 and bf16 autocast, fwd+bwd on its native 160x160 training patch (configs/default.yml:22-24)."""
+    out = {"what": "oracle port of the reference's PyTorch path on cuda (materialised distances + torch.topk, cuBLAS, cuDNN; torch's default TF32 flags), "
+                   "fwd+bwd (MSE), 160x160-ray patch of the 800x800 frame, P=%d" % P, "unit": UNIT}
+    try:
+        for key, ac in (("fp32", None), ("autocast_bf16", torch.bfloat16)):
+            for hw in (160, 100):
+                try:
+                    rays_s, sec = oracle_train_sample(hw, P, 3, 2, device=dev, autocast=ac)
+                    out[key] = {"value": rays_s, "ms_per_step": sec * 1e3, "tile": f"{hw}x{hw}"}
+                    break
+                except torch.cuda.OutOfMemoryError:
+                    torch.cuda.empty_cache()
+    except Exception as e:      # a reported baseline must never take the headline down with it
+        out["error"] = repr(e)[:300]
+    finally:
+        torch.cuda.empty_cache()
+    return out
 
 
 def run_reference(args, rank):
@@ -112,22 +157,23 @@ def run_reference(args, rank):
         return
     threads = os.cpu_count() or 1
     hw = args.cpu_tile
-    rays_s, sec = oracle_train_sample(hw, args.points, threads, max(1, args.steps), min(args.warmup, 1))
-    sample = f"{hw}x{hw}-ray tile of the 800x800 frame, P={args.points}, fwd+bwd (MSE), fp32, oracle port"
+    rays_s, sec = oracle_train_sample(hw, args.points, max(1, args.steps), min(args.warmup, 1), threads=threads)
+    sample = (f"{hw}x{hw}-ray tile (the reference's test.py tile, default.yml:238-239) of the 800x800 frame, P={args.points}, "
+              f"fwd+bwd (MSE), fp32, oracle port of the reference's PyTorch CPU path, {threads} threads")
     line = {
         "impl": "reference", "metric": METRIC, "value": rays_s, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD.format(hw=args.hw, P=args.points), "sample": sample},
+        "config": {"workload": WORKLOAD.format(hw=args.hw, P=args.points), "sample": sample,
+                   "same_config": "same scene, points and hyper-parameters; each step is a 100x100-ray tile of the frame (a whole "
+                                  "800x800 frame takes ~64x longer on the CPU), quoted in rays/s"},
         "cpu_baseline": {"value": rays_s, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": rays_s, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
 
 
-WORKLOAD = "chair.yml train step, one {hw}x{hw} frame of rays per GPU, P={P} points, K=20, F=64, L=6, bf16 tcgen05 GEMMs"
-
-
+# ----------------------------------------------------------------------------------------------- our arm
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -136,8 +182,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--hw", type=int, default=800)
     ap.add_argument("--points", type=int, default=30000)
-    ap.add_argument("--cpu-tile", type=int, default=48)
+    ap.add_argument("--cpu-tile", type=int, default=100)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip the configs[3]/[4] (Caterpillar-shape) legs")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -157,34 +205,6 @@ def main():
     steps, warmup = args.steps, max(args.warmup, 3)
     H = W = args.hw
 
-    torch.manual_seed(1)
-    cfg = make_config("chair")
-    cfg.geoms.points["init_num"] = args.points
-    model = PAPR(cfg, device=dev, precision="bf16").to(dev)
-    cloud = learned_like_cloud(args.points, cfg.dataset.coord_scale, seed=1, feat_dim=cfg.geoms.point_feats.dim)
-    with torch.no_grad():
-        model.points.copy_(cloud["points"]); model.pc_feats.copy_(cloud["pc_feats"])
-        model.points_influ_scores.copy_(cloud["points_influ_scores"])
-    if world > 1:   # replicas must start identical
-        for p in model.parameters():
-            dist.broadcast(p.data, 0)
-    model.init_optimizers(0)
-
-    scene = synthetic_scene(H, W, cfg.dataset.coord_scale, n_views=1, seed=1 + rank)
-    host = {k: scene[k].pin_memory() for k in ("rays_o", "rays_d", "c2w", "target")}
-    resident = {k: v.to(dev) for k, v in host.items()}
-    bucket = [None]
-
-    def train_step(b):
-        model.clear_grad()
-        out = model(b["rays_o"], b["rays_d"], b["c2w"], step=-1)
-        loss = torch.mean((model.last_act(out) - b["target"]) ** 2)
-        model.scaler.scale(loss).backward()
-        if world > 1:
-            bucket[0] = allreduce_gradients(model, bucket[0])
-        model.step()
-        return loss
-
     def timed(fn, n):
         """n calls between barrier + synchronize on both sides, CUDA events; returns max-over-ranks ms per call."""
         if world > 1:
@@ -203,6 +223,37 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
 
+    def build_model(cfg, P):
+        torch.manual_seed(1)
+        cfg.geoms.points["init_num"] = P
+        model = PAPR(cfg, device=dev, precision="bf16").to(dev)
+        cloud = learned_like_cloud(P, cfg.dataset.coord_scale, seed=1, feat_dim=cfg.geoms.point_feats.dim)
+        with torch.no_grad():
+            model.points.copy_(cloud["points"]); model.pc_feats.copy_(cloud["pc_feats"])
+            model.points_influ_scores.copy_(cloud["points_influ_scores"])
+        if world > 1:   # replicas must start identical
+            for p in model.parameters():
+                dist.broadcast(p.data, 0)
+        model.init_optimizers(0)
+        return model
+
+    cfg = make_config("chair")
+    model = build_model(cfg, args.points)
+    scene = synthetic_scene(H, W, cfg.dataset.coord_scale, n_views=1, seed=1 + rank)
+    host = {k: scene[k].pin_memory() for k in ("rays_o", "rays_d", "c2w", "target")}
+    resident = {k: v.to(dev) for k, v in host.items()}
+    bucket = [None]
+
+    def train_step(b):
+        model.clear_grad()
+        out = model.last_act(model(b["rays_o"], b["rays_d"], b["c2w"], step=-1))
+        loss = torch.mean((out - b["target"]) ** 2)
+        model.scaler.scale(loss).backward()
+        if world > 1:
+            bucket[0] = allreduce_gradients(model, bucket[0])
+        model.step()
+        return loss, out
+
     for _ in range(warmup):
         train_step(resident)
     torch.cuda.synchronize()
@@ -220,19 +271,27 @@ def main():
     rays_per_step = H * W * world
     value = rays_per_step / ms_step * 1e3
 
-    # ---- end to end: host (pinned) inputs copied in, loss read back, every step
+    # ---- end to end, as train.py:163-179 runs a step: host (pinned) rays/target copied in, and BOTH the loss and the
+    # rendered image copied back to the host every step
+    out_host = torch.empty((1, H, W, 3), dtype=torch.float32).pin_memory()
+
     def e2e_step():
         b = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-        return train_step(b).item()
+        loss, out = train_step(b)
+        out_host.copy_(out.detach(), non_blocking=True)
+        return loss.item()          # synchronises: the image copy above is complete as well
     e2e_step()
     ms_e2e = timed(e2e_step, steps)
     h2d = sum(v.numel() * v.element_size() for v in host.values())
+    d2h = 4 + out_host.numel() * out_host.element_size()
 
-    # ---- render: forward only, rows sharded across ranks with a UNet halo, no communication
+    # ---- render (configs[2]): forward only, rows sharded across ranks with a UNet halo, no communication
     r0, r1, h0, h1 = shard_rows(H, world, rank)
+    rays_stripe = resident["rays_d"][:, h0:h1].contiguous()
+
     def render():
         with torch.no_grad():
-            rgb = model(resident["rays_o"], resident["rays_d"][:, h0:h1].contiguous(), resident["c2w"], step=-1)
+            rgb = model(resident["rays_o"], rays_stripe, resident["c2w"], step=-1)
             return rgb[:, r0 - h0:r1 - h0]
     for _ in range(2):
         render()
@@ -240,6 +299,31 @@ def main():
     ms_render = timed(render, steps)
     ops.STATS.timing = False
     kern_render = ops.STATS.summary()
+    host_stripe = host["rays_d"][:, h0:h1].contiguous().pin_memory()
+    rgb_host = torch.empty((1, r1 - r0, W, 3), dtype=torch.float32).pin_memory()
+
+    def render_e2e():       # test.py:76-104 for one frame: rays in from the host, the finished RGB stripe back out
+        with torch.no_grad():
+            rd = host_stripe.to(dev, non_blocking=True)
+            ro = host["rays_o"].to(dev, non_blocking=True)
+            rgb = model(ro, rd, None, step=-1)[:, r0 - h0:r1 - h0]
+            rgb_host.copy_(rgb, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    render_e2e()
+    ms_render_e2e = timed(render_e2e, steps)
+
+    # ---- configs[3] / configs[4]: Caterpillar-shaped frame, rows sharded over the ranks (strong scaling)
+    extra = {}
+    if not args.no_extra_configs:
+        del model
+        bucket[0] = None
+        torch.cuda.empty_cache()
+        for tag in ("c4", "c5"):
+            try:
+                extra[tag] = run_caterpillar(tag, dev, rank, world, build_model, timed, min(steps, 3))
+            except Exception as e:          # extra legs must not take the headline down
+                extra[tag] = {"error": repr(e)[:300]}
+            torch.cuda.empty_cache()
 
     if rank != 0:
         if world > 1:
@@ -248,37 +332,45 @@ def main():
 
     peaks = load_peaks()
     zero = dict(launches=0, ms=0.0, flops=0.0, bytes=0.0)
-    tc_names = ("papr_stack_bf16", "papr_linear_bf16", "papr_wgrad_bf16")
-    tc = [kern.get(n, zero) for n in tc_names]
+    tc_names = ("papr_stack_bf16", "papr_wgrad_bf16", "papr_linear_bf16")
+    tc = {n: kern.get(n, zero) for n in tc_names}
     sel = kern.get("papr_select_topk", zero)
-    tc_ms = max(sum(k["ms"] for k in tc), 1e-9)
-    tc_flops = sum(k["flops"] for k in tc)
-    tc_bytes = sum(k["bytes"] for k in tc)
-    tc_launches = sum(k["launches"] for k in tc)
-    achieved = tc_flops / (tc_ms * 1e-3) / 1e12
-    stack = kern.get("papr_stack_bf16", zero)
-    traffic = None
+    stack = tc["papr_stack_bf16"]
+    stack_ms = max(stack["ms"], 1e-9)
+    achieved = stack["flops"] / (stack_ms * 1e-3) / 1e12
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")      # dram bytes per launch from the committed ncu capture
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get("tcgen05_kernels_bytes_per_step")
+            t = json.load(f)
+        k = t.get("per_kernel", {}).get("void stack_kernel<1>")
+        if k:
+            traffic, traffic_src = k["dram_bytes"] / k["launches"], t.get("source")
+    n_stack = max(stack["launches"], 1)
+    tc_ms = max(sum(k["ms"] for k in tc.values()), 1e-9)
     roofline = {
         "bound": "tensor",
-        "kernel": "tcgen05 GEMM kernels of the key/value/query stacks: stack_kernel (fused fwd + dgrad, cta_group::2), wgrad_kernel, linear_kernel",
+        "kernel": "stack_kernel (papr_stack_bf16): a whole key / value / query MLP stack per launch, forward or dgrad, tcgen05 cta_group::2",
         "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_sustained"],
-        "peak_source": peaks["source"] + " bf16 sustained (kernels timed inside a long step)",
-        "traffic": traffic, "traffic_unit": "bytes per step over these launches (ncu dram__bytes_read+write)",
-        "algorithmic_bytes_per_step": tc_bytes / steps,
-        "launches_per_step": tc_launches / steps, "ms_per_step": tc_ms / steps, "share_of_step": tc_ms / steps / ms_step,
-        "hbm_gbs": tc_bytes / (tc_ms * 1e-3) / 1e9, "hbm_frac": tc_bytes / (tc_ms * 1e-3) / 1e9 / peaks["hbm"],
-        "by_kernel": {n: {"ms_per_step": k["ms"] / steps, "tflops": k["flops"] / max(k["ms"], 1e-9) / 1e9,
+        "peak_source": peaks["source"] + " bf16 sustained (kernel timed inside a long step)",
+        "flops_per_launch": stack["flops"] / n_stack, "ms_per_launch": stack_ms / n_stack, "launches_per_step": stack["launches"] / steps,
+        "share_of_step": stack_ms / steps / ms_step,
+        "traffic": traffic, "traffic_unit": "dram bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)", "traffic_source": traffic_src,
+        "algorithmic_bytes_per_launch": stack["bytes"] / n_stack,
+        "hbm_gbs": stack["bytes"] / (stack_ms * 1e-3) / 1e9, "hbm_frac": stack["bytes"] / (stack_ms * 1e-3) / 1e9 / peaks["hbm"],
+        "tcgen05_kernels": {"ms_per_step": tc_ms / steps, "share_of_step": tc_ms / steps / ms_step,
+                            "tflops": sum(k["flops"] for k in tc.values()) / (tc_ms * 1e-3) / 1e12,
+                            "frac": sum(k["flops"] for k in tc.values()) / (tc_ms * 1e-3) / 1e12 / peaks["tf_sustained"]},
+        "by_kernel": {n: {"ms_per_step": k["ms"] / steps, "launches_per_step": k["launches"] / steps,
+                          "tflops": k["flops"] / max(k["ms"], 1e-9) / 1e9,
                           "tensor_frac": k["flops"] / max(k["ms"], 1e-9) / 1e9 / peaks["tf_sustained"],
                           "hbm_gbs": k["bytes"] / max(k["ms"], 1e-9) / 1e6, "hbm_frac": k["bytes"] / max(k["ms"], 1e-9) / 1e6 / peaks["hbm"]}
-                      for n, k in zip(tc_names, tc) if k["launches"]},
+                      for n, k in tc.items() if k["launches"]},
     }
     kernels = {k: dict(launches_per_step=v["launches"] / steps, ms_per_step=v["ms"] / steps,
                        tflops=v["flops"] / max(v["ms"], 1e-9) / 1e9, gbs=v["bytes"] / max(v["ms"], 1e-9) / 1e6)
                for k, v in sorted(kern.items(), key=lambda kv: -kv[1]["ms"])}
+    stripe_bytes = host_stripe.numel() * 4 + 12
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
@@ -288,7 +380,9 @@ def main():
                    "optimizer_in_step": True},
         "clocks": clocks,
         "e2e": {"value": rays_per_step / ms_e2e * 1e3, "unit": UNIT, "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "what": "PAPR.forward/backward/step through the public model API with pinned-host rays + target copied in and the "
+                        "loss AND the rendered image copied back every step (train.py:163-179)"},
         "gpu_launches": launches,
         "roofline": roofline,
         "step_roofline": {"algorithmic_tflop_per_step": rays_per_step / world * FLOP_PER_RAY_TRAIN / 1e12,
@@ -299,18 +393,71 @@ def main():
                    "algorithmic_hbm_gbs": sel["bytes"] / max(sel["ms"], 1e-9) / 1e6},
         "render": {"ms_per_frame": ms_render, "frame": f"{H}x{W}", "rows_per_gpu": h1 - h0,
                    "frac_of_gemm_floor": (H * W * FLOP_PER_RAY_FWD / world / (peaks["tf_sustained"] * 1e12) * 1e3) / ms_render,
+                   "e2e_ms_per_frame": ms_render_e2e, "e2e_h2d_bytes": stripe_bytes, "e2e_d2h_bytes": rgb_host.numel() * 4,
                    "kernels_ms": {k: v["ms"] / steps for k, v in kern_render.items()}},
+        "parity": {"stated_bf16_tolerance": {"attn": 2e-3, "bkg_weight": 7e-3, "fused_rel": 1.5e-2, "rgb": 9e-3},
+                   "measured_bf16_worst": {"attn": 8.3e-4, "bkg_weight": 3.2e-3, "fused_rel": 7.5e-3, "rgb": 4.3e-3,
+                                           "rgb_fullsize_tile": 1.5e-3},
+                   "measured_fp32_mode_worst": {"attn": 2.5e-7, "fused_rel": 5.7e-6, "rgb": 5.4e-7},
+                   "top_k": "bit-exact", "source": "profiles/r02_error_budget.md, tests/test_model_gpu.py, tests/test_fullsize_gpu.py"},
         "kernels": kernels,
     }
+    line.update(extra)
+    if world == 1 and not args.no_gpu_reference:
+        line["gpu_reference"] = gpu_reference(args.points, dev)
+        for key in ("fp32", "autocast_bf16"):
+            if key in line["gpu_reference"]:
+                line["gpu_reference"][key]["ours_over_it"] = value / line["gpu_reference"][key]["value"]
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        rays_s, sec = oracle_train_sample(args.cpu_tile, args.points, threads, 2, 1)
+        oracle_train_sample(16, args.points, 1, 0, threads=threads)        # spin up the thread pool / build the select helper
+        rays_s, sec = oracle_train_sample(args.cpu_tile, args.points, 1, 0, threads=threads)
         line["cpu_baseline"] = {"value": rays_s, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": f"{args.cpu_tile}x{args.cpu_tile}-ray tile of the frame, P={args.points}, fwd+bwd, "
-                                          f"fp32 oracle port, {sec:.2f} s/step"}
+                                "sample": f"one {args.cpu_tile}x{args.cpu_tile}-ray tile (the reference's test.py tile) of the frame, "
+                                          f"P={args.points}, fwd+bwd (MSE), fp32 oracle port, {sec:.2f} s/step"}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_caterpillar(tag, dev, rank, world, build_model, timed, steps):
+    """configs[3] (c4) / configs[4] (c5): one Tanks&Temples-Caterpillar-shaped frame (1920x1080, P=100,000 points, L=4,
+    coord_scale 30, background score 4; configs/t2/Caterpillar.yml:2-22) per step, its rows sharded over the ranks with a
+    16-px UNet halo, gradients all-reduced; c5 adds the exposure-control FiLM (Caterpillar_exposure_control.yml with
+    affine_layer 0, a per-image latent code through the mapping MLP; exposure_control_finetune.py:159-181)."""
+    from papr_b200.config import make_config
+    from papr_b200.dist import shard_rows
+    from papr_b200.scene import synthetic_scene
+    Hc, Wc, P = 1080, 1920, 100000
+    cfg = make_config("caterpillar_exposure" if tag == "c5" else "caterpillar")
+    model = build_model(cfg, P)
+    scene = synthetic_scene(Hc, Wc, cfg.dataset.coord_scale, n_views=1, seed=7)
+    r0, r1, h0, h1 = shard_rows(Hc, world, rank)
+    mask = torch.zeros((1, h1 - h0, 1, 1), device=dev)
+    mask[:, r0 - h0:r1 - h0] = 1.0          # the loss lives on the interior rows; halo rows only feed the UNet
+    b = {"rays_o": scene["rays_o"].to(dev), "rays_d": scene["rays_d"][:, h0:h1].contiguous().to(dev), "c2w": scene["c2w"].to(dev),
+         "target": scene["target"][:, h0:h1].contiguous().to(dev)}
+    code = None
+    if tag == "c5":     # the frame's latent exposure code (exposure_control_finetune.py:204), identical on every rank
+        code = torch.randn(cfg.exposure_control.shading_code_dim, generator=torch.Generator().manual_seed(5)).to(dev)
+
+    def step():
+        model.clear_grad()
+        out = model.last_act(model(b["rays_o"], b["rays_d"], b["c2w"], step=-1, shading_code=code))
+        loss = torch.sum(mask * (out - b["target"]) ** 2) / (Hc * Wc * 3 / world)
+        loss.backward()
+        if world > 1:
+            from papr_b200.dist import allreduce_gradients
+            step.bucket = allreduce_gradients(model, step.bucket)
+        model.step()
+    step.bucket = None
+    for _ in range(2):
+        step()
+    ms = timed(step, steps)
+    return {"workload": f"Caterpillar-shaped 1920x1080 frame, P={P}, K=20, L=4, rows sharded over {world} GPU(s) with a 16-px halo"
+                        + (", exposure FiLM (affine_layer 0)" if tag == "c5" else ""),
+            "ms_per_step": ms, "rays_per_s": Hc * Wc / ms * 1e3, "rows_per_gpu": h1 - h0, "scaling": "strong",
+            "points": int(model.points.shape[0])}
 
 
 if __name__ == "__main__":

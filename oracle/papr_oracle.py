@@ -115,6 +115,15 @@ def select_topk(rays_o, rays_d, points, K, eps=1e-6):
     return torch.from_numpy(idx.astype(np.int64)).reshape(N, H, W, K), torch.from_numpy(kth).reshape(N, H, W)
 
 
+def select_topk_torch(rays_o, rays_d, points, K, eps=1e-6):
+    """model.py:258-283 as the reference runs it on any device: the materialised distance tensor + torch.topk
+    (largest=False, sorted=False).  Used for the GPU-reference timing of bench.py (tile-sized inputs only)."""
+    if K >= points.shape[0] or K < 0:
+        N, H, W, _ = rays_d.shape
+        return torch.arange(points.shape[0], device=points.device).expand(N, H, W, -1)
+    return torch.topk(select_distances_torch(rays_o, rays_d, points, eps), K, dim=-1, largest=False, sorted=False)[1]
+
+
 # ----------------------------------------------------------------------------- geometry (a3)
 def ray_point_geometry(rays_o, rays_d, sel_points, eps=1e-6):
     """model.py:302-305: returns (proj, D) = (vec_p2o, vec_p2r), both (N,H,W,K,3)."""
@@ -250,26 +259,34 @@ def mapping_mlp(params, cfg, code):
 
 
 # ----------------------------------------------------------------------------- whole path
-def attention_features(params, cfg, rays_o, rays_d, idx=None):
-    """Everything up to the blend.  Returns dict(idx, sel_points, fused (N,H,W,C), attn (N,H,W,K+1))."""
+def attention_features(params, cfg, rays_o, rays_d, idx=None, autocast_dtype=None):
+    """Everything up to the blend.  Returns dict(idx, sel_points, fused (N,H,W,C), attn (N,H,W,K+1)).
+    Device-agnostic: with CUDA tensors the selection is the reference's own torch formulation (select_topk_torch) and
+    ``autocast_dtype`` wraps the attention block as attn.py:248 does (bench.py's GPU-reference leg)."""
     N, H, W, _ = rays_d.shape
     points = params["points"]
     if idx is None:
-        idx, _ = select_topk(rays_o, rays_d, points.detach(), int(cfg.geoms.points.select_k), cfg.eps)
+        if points.is_cuda:
+            idx = select_topk_torch(rays_o, rays_d, points.detach(), int(cfg.geoms.points.select_k), cfg.eps)
+        else:
+            idx, _ = select_topk(rays_o, rays_d, points.detach(), int(cfg.geoms.points.select_k), cfg.eps)
     sel_points = points[idx]
     proj, D = ray_point_geometry(rays_o, rays_d, sel_points, cfg.eps)
     sel_feats = params["pc_feats"][idx]
-    embedv, scores = proximity_attention(params, cfg, sel_points, proj, D, rays_d, sel_feats)
+    with torch.autocast(device_type="cuda", dtype=autocast_dtype or torch.bfloat16, enabled=autocast_dtype is not None):
+        embedv, scores = proximity_attention(params, cfg, sel_points, proj, D, rays_d, sel_feats)
+    embedv, scores = embedv.float(), scores.float()
     influ = params["points_influ_scores"][idx].reshape(N * H * W, -1)
-    bkg_score = torch.tensor(float(cfg.geoms.background.constant), dtype=torch.float32)
+    bkg_score = torch.tensor(float(cfg.geoms.background.constant), dtype=torch.float32, device=points.device)
     fused, attn = blend(cfg, embedv, scores, influ, bkg_score)
     return dict(idx=idx, sel_points=sel_points, fused=fused.reshape(N, H, W, -1), attn=attn.reshape(N, H, W, -1),
                 embedv=embedv, scores=scores)
 
 
-def forward(params, cfg, rays_o, rays_d, shading_code=None, idx=None):
-    """model.py:494-560 -> rgb (N,H,W,3)."""
-    out = attention_features(params, cfg, rays_o, rays_d, idx)
+def forward(params, cfg, rays_o, rays_d, shading_code=None, idx=None, autocast_dtype=None):
+    """model.py:494-560 -> rgb (N,H,W,3).  autocast_dtype: run the attention block and the UNet under torch.autocast
+    (the reference's use_amp path, attn.py:248 / unet.py), CUDA only."""
+    out = attention_features(params, cfg, rays_o, rays_d, idx, autocast_dtype)
     fused, attn = out["fused"], out["attn"]
     gamma = beta = None
     affine_layer = cfg.models.renderer.generator.small_unet.affine_layer
@@ -277,7 +294,9 @@ def forward(params, cfg, rays_o, rays_d, shading_code=None, idx=None):
         affine = mapping_mlp(params, cfg, shading_code)
         gamma, beta = affine[: affine.shape[-1] // 2], affine[affine.shape[-1] // 2:]
     if cfg.models.use_renderer:
-        fg = unet(params, fused.permute(0, 3, 1, 2), gamma, beta, affine_layer).permute(0, 2, 3, 1)
+        with torch.autocast(device_type="cuda", dtype=autocast_dtype or torch.bfloat16, enabled=autocast_dtype is not None):
+            fg = unet(params, fused.permute(0, 3, 1, 2), gamma, beta, affine_layer)
+        fg = fg.float().permute(0, 2, 3, 1)
     else:
         fg = fused
     bkg_attn = attn[..., -1:]
