@@ -201,6 +201,70 @@ int papr_query_tail_fwd(const float *q5, const float *w_c, float c_const, float 
 int papr_query_tail_bwd(const float *q5, const float *stats, const float *w_c, const float *dz, int64_t ld_dz,
                         const float *dc, float eps, int64_t R, float *dq5, float *g_wc, float *g_cconst, void *stream);
 
+
+/*
+ * SURVEY section 8(f1) -- replaces the optimiser half of PAPR.step (reference models/model.py:439-446: one
+ * torch.optim.Adam.step per parameter group) with ONE multi-tensor launch.  Gradients and both Adam moments live in
+ * flat fp32 buffers of `total` elements; tensor t occupies [offsets[t], offsets[t+1]) of them, its parameter storage is
+ * param_ptrs[t] (contiguous fp32) and it belongs to group group_of[t].  offsets / param_ptrs / group_of are DEVICE
+ * arrays, `groups` is a HOST array (n_groups <= 8).  Update rule = torch.optim.Adam (L2 weight decay, bias correction
+ * from `step`, which counts from 1); grad_scale multiplies every gradient first (1/world after a summed all-reduce).
+ * A group with enabled == 0 or step < 1 is skipped.
+ */
+typedef struct papr_adam_group {
+    float lr, beta1, beta2, eps, weight_decay;
+    int32_t step;
+    int32_t enabled;
+} papr_adam_group;
+
+int papr_adam_step(const int64_t *offsets, float *const *param_ptrs, const int32_t *group_of, int n_tensors, int64_t total,
+                   const float *grad, float *exp_avg, float *exp_avg_sq, const papr_adam_group *groups, int n_groups,
+                   float grad_scale, void *stream);
+
+/*
+ * Batched papr_pack_weight: one launch rebuilds every weight image listed in the DEVICE array `descs` (after an
+ * optimiser step: all forward and transposed images of the key / value / query stacks).  Each image may be written
+ * `replicas` times, rep_stride bytes apart (papr_stack_layer.w_replicas).
+ */
+typedef struct papr_pack_desc {
+    const float *w;        /* fp32 source matrix, leading dimension ld */
+    int64_t ld;
+    int32_t rows, cols;    /* source shape */
+    int32_t transpose;     /* element (n,k) = W[k][n] instead of W[n][k] */
+    int32_t N, K;          /* padded image shape (multiples of 16, <= 256) */
+    int32_t replicas;
+    float scale;
+    int32_t _pad;
+    int64_t rep_stride;
+    void *image;
+} papr_pack_desc;
+
+int papr_pack_weight_batch(const papr_pack_desc *descs, int n_descs, void *stream);
+
+/*
+ * Stage a14 -- point growing / pruning bookkeeping on the device (reference models/utils.py:9-109 add_points_knn uses a
+ * host scipy KDTree; models/model.py:335-358 prune_points uses boolean-mask indexing).
+ * papr_knn: for each of Q queries (Q,3) the k <= 32 nearest of P points (P,3), exact float64 Euclidean distances as the
+ * KDTree computes them, ascending, ties by smaller point index: dist_out (Q,k) f64, idx_out (Q,k) i32.
+ * papr_prune_compact: keeps, in order, the rows whose influence score is > thresh (keep_less = 0, the reference's
+ * prune_type "<") or < thresh (keep_less = 1); writes compacted points / influ / feats (feats may be NULL) and the
+ * number of kept rows to the DEVICE scalar n_kept.  scratch: ceil(P/256) int32.
+ */
+int papr_knn(const float *points, int64_t P, const float *queries, int64_t Q, int k, double *dist_out, int32_t *idx_out,
+             void *stream);
+int papr_prune_compact(const float *points, const float *influ, const float *feats, int64_t P, int F, float thresh,
+                       int keep_less, float *out_points, float *out_influ, float *out_feats, int32_t *scratch,
+                       int64_t *n_kept, void *stream);
+
+/*
+ * SURVEY section 8(f3) -- the step before the path: pinhole rays of the pixels [h0,h0+h) x [w0,w0+w) of an H x W view
+ * (reference dataset/utils.py:81-96 get_rays, dataset/dataset.py:19-25 origin scaling) generated on the device, so that
+ * a training step uploads a 4x4 pose instead of 12 bytes per ray.  c2w (n_views,4,4) f32 -> rays_o (n_views,3) =
+ * coord_scale * c2w[:3,3], rays_d (n_views,h,w,3) unit norm.
+ */
+int papr_generate_rays(const float *c2w, int64_t n_views, int H, int W, float focal_x, float focal_y, int h0, int w0, int h,
+                       int w, float coord_scale, float *rays_o, float *rays_d, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

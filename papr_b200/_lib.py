@@ -31,6 +31,11 @@ SIGNATURES = {
     "papr_query_tail_fwd": [_ptr, _ptr, _f32, _f32, _i64, _ptr, _ptr, _ptr, _ptr],
     "papr_query_tail_bwd": [_ptr, _ptr, _ptr, _ptr, _i64, _ptr, _f32, _i64, _ptr, _ptr, _ptr, _ptr],
     "papr_wgrad_bf16": [_ptr, _i32, _ptr, _i32, _ptr, _i64, _i32, _i32, _i32, _i64, _ptr],
+    "papr_adam_step": [_ptr, _ptr, _ptr, _i32, _i64, _ptr, _ptr, _ptr, _ptr, _i32, _f32, _ptr],
+    "papr_pack_weight_batch": [_ptr, _i32, _ptr],
+    "papr_knn": [_ptr, _i64, _ptr, _i64, _i32, _ptr, _ptr, _ptr],
+    "papr_prune_compact": [_ptr, _ptr, _ptr, _i64, _i32, _f32, _i32, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
+    "papr_generate_rays": [_ptr, _i64, _i32, _i32, _f32, _f32, _i32, _i32, _i32, _i32, _f32, _ptr, _ptr, _ptr],
 }
 _RESTYPE = {"papr_status_string": _c.c_char_p, "papr_last_cuda_error": _c.c_char_p}
 
@@ -40,6 +45,19 @@ class StackLayer(ctypes.Structure):
     _fields_ = [("w_image", _ptr), ("bias", _ptr), ("out_blocked", _ptr), ("out_f32", _ptr), ("ld_f32", _i64),
                 ("sign_bits_out", _ptr), ("sign_bits_in", _ptr), ("colsum", _ptr), ("N", ctypes.c_int32),
                 ("act", ctypes.c_int32), ("w_replicas", ctypes.c_int32), ("_pad", ctypes.c_int32), ("w_replica_stride", _i64)]
+
+
+class AdamGroup(ctypes.Structure):
+    """papr_adam_group of include/papr_b200.h"""
+    _fields_ = [("lr", _f32), ("beta1", _f32), ("beta2", _f32), ("eps", _f32), ("weight_decay", _f32),
+                ("step", ctypes.c_int32), ("enabled", ctypes.c_int32)]
+
+
+class PackDesc(ctypes.Structure):
+    """papr_pack_desc of include/papr_b200.h"""
+    _fields_ = [("w", _ptr), ("ld", _i64), ("rows", ctypes.c_int32), ("cols", ctypes.c_int32), ("transpose", ctypes.c_int32),
+                ("N", ctypes.c_int32), ("K", ctypes.c_int32), ("replicas", ctypes.c_int32), ("scale", _f32),
+                ("_pad", ctypes.c_int32), ("rep_stride", _i64), ("image", _ptr)]
 
 
 class PaprError(RuntimeError):

@@ -116,6 +116,8 @@ class _Shape:
         # grad mode of the CALLER: inside autograd.Function.forward it always reads False, and ctx.needs_input_grad
         # mirrors requires_grad regardless of torch.no_grad(), so this is what decides whether a backward stash is kept
         self.grad = torch.is_grad_enabled()
+        self.k_images = attn.weight_images.stack("k", len(attn.embed.embed_k.mlp.linears()))
+        self.v_images = attn.weight_images.stack("v", len(attn.embed.embed_v.mlp.linears()))
 
 
 def _prologue_fwd(sh, rays_o, rays_d, points, feats, idx, ln_a, ln_b, taps=False):
@@ -218,6 +220,64 @@ def _stash_unpack(tensors, spec):
     return out
 
 
+class WeightImages:
+    """bf16 weight images of the key / query / value stacks -- every layer, forward and transposed (dgrad), with the
+    replicas the fused stack kernel wants -- kept in persistent buffers and rebuilt by ONE papr_pack_weight_batch launch
+    per forward call instead of one papr_pack_weight launch per layer and direction (38 per training step)."""
+
+    def __init__(self, attn):
+        self.attn = attn
+        self.images = {}          # (stack, layer, "f"|"t") -> uint8 (replicas, bytes)
+        self._ptrs = None
+        self._table = None
+        self._n = 0
+
+    def _specs(self):
+        out = []
+        for name in ("k", "q", "v"):
+            mlp = getattr(self.attn.embed, f"embed_{name}").mlp
+            lins = mlp.linears()
+            if mlp.skip_layers or len(lins) > 8 or any(l.weight.shape[0] != 256 for l in lins[:-1]):
+                continue          # those stacks run layer by layer and pack on the fly
+            in_pad = ops.pad_cols(lins[0].weight.shape[1])
+            for i, lin in enumerate(lins):
+                n_out, n_in = lin.weight.shape
+                out.append(((name, i, "f"), lin.weight, 0, (n_out + 31) // 32 * 32, (n_in + 15) // 16 * 16))
+                out.append(((name, i, "t"), lin.weight, 1, n_in if i > 0 else in_pad, (n_out + 15) // 16 * 16))
+        return out
+
+    def refresh(self):
+        import ctypes
+        from ._lib import PackDesc
+        specs = self._specs()
+        if not specs:
+            self.images = {}
+            return
+        ptrs = [w.data_ptr() for _, w, _, _, _ in specs]
+        if ptrs != self._ptrs:
+            dev = specs[0][1].device
+            arr = (PackDesc * len(specs))()
+            self.images = {}
+            for j, (key, w, tr, N, K) in enumerate(specs):
+                nbytes = (K + 63) // 64 * N * 128
+                img = torch.empty((ops.WEIGHT_REPLICAS, nbytes), dtype=torch.uint8, device=dev)
+                self.images[key] = img
+                arr[j].w, arr[j].ld, arr[j].rows, arr[j].cols = w.data_ptr(), w.stride(0), w.shape[0], w.shape[1]
+                arr[j].transpose, arr[j].N, arr[j].K, arr[j].replicas = tr, N, K, ops.WEIGHT_REPLICAS
+                arr[j].scale, arr[j].rep_stride, arr[j].image = 1.0, img.stride(0), img.data_ptr()
+            raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+            self._table = raw.to(dev)
+            self._ptrs, self._n = ptrs, len(specs)
+        ops.call("papr_pack_weight_batch", self._table.data_ptr(), self._n,
+                 nbytes=sum(6.0 * w.numel() for _, w, _, _, _ in specs))
+
+    def stack(self, name, n_layers):
+        """(forward images, transposed images) of a stack, or (None, None) if it is not cached."""
+        if (name, 0, "f") not in self.images:
+            return None, None
+        return ([self.images[(name, i, "f")] for i in range(n_layers)], [self.images[(name, i, "t")] for i in range(n_layers)])
+
+
 def _pad_bias(b, N):
     b = b.detach().float().contiguous()
     return b if b.numel() == N else F.pad(b, (0, N - b.numel()))
@@ -226,7 +286,7 @@ def _pad_bias(b, N):
 FUSE_STACKS = True      # one cta_group::2 launch per MLP stack (papr_stack_bf16) instead of one launch per layer
 
 
-def _stack_forward_fused(x, weights, biases, slope, n_in0, save, last_f32):
+def _stack_forward_fused(x, weights, biases, slope, n_in0, save, last_f32, images=None):
     n_layers = len(weights)
     dev = weights[0].device
     K0 = (n_in0 + 15) // 16 * 16
@@ -238,7 +298,8 @@ def _stack_forward_fused(x, weights, biases, slope, n_in0, save, last_f32):
         N = (n_out + 31) // 32 * 32
         last = i == n_layers - 1
         act = (not last) and slope is not None
-        spec = dict(w_image=ops.pack_weight(w, N, K, replicas=ops.WEIGHT_REPLICAS), N=N, bias=_pad_bias(b, N), act=act)
+        img = images[i] if images is not None else ops.pack_weight(w, N, K, replicas=ops.WEIGHT_REPLICAS)
+        spec = dict(w_image=img, N=N, bias=_pad_bias(b, N), act=act)
         bits = None
         if save and act:
             bits = torch.empty((x.rows_pad, ops.pad_cols(N) // 64), dtype=torch.int64, device=dev)
@@ -259,12 +320,12 @@ def _stack_forward_fused(x, weights, biases, slope, n_in0, save, last_f32):
     return inputs, bits_list, out
 
 
-def _stack_forward(x, weights, biases, slope, n_in0, save, last_f32=False, skip_layers=()):
+def _stack_forward(x, weights, biases, slope, n_in0, save, last_f32=False, skip_layers=(), images=None):
     """Run one MLP stack on the tensor cores.  Returns (layer inputs, sign bits, last output: Blocked or fp32).
     A skip layer (mlp.py:54-55: input = cat[h, stack input]) is two GEMMs into one accumulator: the stack-input half
     is computed first in fp32 and handed to the main launch as its `addend`."""
     if FUSE_STACKS and not skip_layers and len(weights) <= 8 and all(w.shape[0] == 256 for w in weights[:-1]):
-        return _stack_forward_fused(x, weights, biases, slope, n_in0, save, last_f32)
+        return _stack_forward_fused(x, weights, biases, slope, n_in0, save, last_f32, images)
     inputs, bits_list = [], []
     h = x
     n_layers = len(weights)
@@ -291,7 +352,7 @@ def _stack_forward(x, weights, biases, slope, n_in0, save, last_f32=False, skip_
     return inputs, bits_list, out
 
 
-def _stack_backward(dz, inputs, bits_list, weights, slope, g_bias_last, in_valid, in_pad, skip_layers=()):
+def _stack_backward(dz, inputs, bits_list, weights, slope, g_bias_last, in_valid, in_pad, skip_layers=(), images_t=None):
     """Backward of _stack_forward.  dz: Blocked gradient of the last layer's output.  Returns (d_input Blocked,
     [gW], [gb])."""
     n_layers = len(weights)
@@ -307,7 +368,8 @@ def _stack_backward(dz, inputs, bits_list, weights, slope, g_bias_last, in_valid
             Kd = (n_out + 15) // 16 * 16
             Nd = n_in if i > 0 else in_pad
             ob = ops.Blocked(dz.rows, Nd, dev)
-            spec = dict(w_image=ops.pack_weight(w, Nd, Kd, transpose=True, replicas=ops.WEIGHT_REPLICAS), N=Nd, out_blocked=ob)
+            img = images_t[i] if images_t is not None else ops.pack_weight(w, Nd, Kd, transpose=True, replicas=ops.WEIGHT_REPLICAS)
+            spec = dict(w_image=img, N=Nd, out_blocked=ob)
             if i > 0:
                 gbs[i - 1] = torch.zeros((weights[i - 1].shape[0],), device=dev)
                 spec["colsum"] = gbs[i - 1]
@@ -363,11 +425,12 @@ class _StackBf16Fn(torch.autograd.Function):
     layers, sign bits drive the dgrad masks and the dgrad epilogues produce the bias gradients."""
 
     @staticmethod
-    def forward(ctx, x, slope, n, grad, *wb):
+    def forward(ctx, x, slope, n, grad, images, *wb):
         ws, bs = wb[:n], wb[n:]
         xb = ops.Blocked.from_f32(x)
         save = grad and any(ctx.needs_input_grad)
-        inputs, bits, y = _stack_forward(xb, [w.detach() for w in ws], bs, slope, x.shape[1], save, last_f32=True)
+        img_f, ctx.img_t = images if images is not None else (None, None)
+        inputs, bits, y = _stack_forward(xb, [w.detach() for w in ws], bs, slope, x.shape[1], save, last_f32=True, images=img_f)
         n_out = ws[-1].shape[0]
         if save:
             tensors, ctx.spec = _stash_pack(list(inputs) + list(bits))
@@ -386,8 +449,8 @@ class _StackBf16Fn(torch.autograd.Function):
         dz = ops.Blocked.from_f32(g, cols_pad=max(ops.pad_cols(n_out), 128))
         gb_last = g.sum(0)
         in_pad = ops.pad_cols(ctx.n_in)
-        dx, gWs, gbs = _stack_backward(dz, inputs, bits, ws, ctx.slope, gb_last, ctx.n_in, in_pad)
-        return (dx.to_f32(ctx.rows, ctx.n_in), None, None, None, *gWs, *gbs)
+        dx, gWs, gbs = _stack_backward(dz, inputs, bits, ws, ctx.slope, gb_last, ctx.n_in, in_pad, images_t=ctx.img_t)
+        return (dx.to_f32(ctx.rows, ctx.n_in), None, None, None, None, *gWs, *gbs)
 
 
 class _QueryTailFn(torch.autograd.Function):
@@ -443,9 +506,10 @@ class RowAttentionFn(torch.autograd.Function):
         pts = points.detach().contiguous()
         fts = feats.detach().contiguous() if feats is not None else None
         kin, vin, _, _ = _prologue_fwd(sh, rays_o, rays_d, pts, fts, idx, ln_a.detach(), ln_b.detach())
-        k_in, k_bits, h5 = _stack_forward(kin, [w.detach() for w in kw], kb, sh.k_slope, sh.dk, save, skip_layers=sh.k_skip)
+        k_in, k_bits, h5 = _stack_forward(kin, [w.detach() for w in kw], kb, sh.k_slope, sh.dk, save, skip_layers=sh.k_skip,
+                                          images=sh.k_images[0])
         v_in, v_bits, v = _stack_forward(vin, [w.detach() for w in vw], vb, sh.v_slope, sh.dv, save, last_f32=True,
-                                         skip_layers=sh.v_skip)
+                                         skip_layers=sh.v_skip, images=sh.v_images[0])
         infl = influ.detach().reshape(-1).contiguous()
         fused, attn, sc, stats = _score_blend_fwd(sh, h5, None, ua.detach().contiguous(), cprime.detach().contiguous(),
                                                   infl, idx, v)
@@ -470,9 +534,9 @@ class RowAttentionFn(torch.autograd.Function):
         P = pts.shape[0]
         d_attn_c = d_attn.contiguous() if d_attn is not None else None
         dv, d_score, g_influ, g_bv = _blend_bwd(sh, d_fused.contiguous(), d_attn_c, attn, sc, infl, idx, v, P)
-        d_vin, gvW, gvb = _stack_backward(dv, v_in, v_bits, vw, sh.v_slope, g_bv, sh.dv, sh.dv_pad, sh.v_skip)
+        d_vin, gvW, gvb = _stack_backward(dv, v_in, v_bits, vw, sh.v_slope, g_bv, sh.dv, sh.dv_pad, sh.v_skip, images_t=sh.v_images[1])
         dh5, _, zsum, dssum, g_b5 = _key_score_bwd(sh, d_score, h5, None, stats, ua)
-        d_kin, gkW, gkb = _stack_backward(dh5, k_in, k_bits, kw, sh.k_slope, g_b5, sh.dk, sh.dk_pad, sh.k_skip)
+        d_kin, gkW, gkb = _stack_backward(dh5, k_in, k_bits, kw, sh.k_slope, g_b5, sh.dk, sh.dk_pad, sh.k_skip, images_t=sh.k_images[1])
         g_points, g_feats, g_a, g_b = _prologue_bwd(sh, rays_o, rays_d, pts, idx, ln_a, d_kin, d_vin, None, None, P)
         return (None, None, None, None, g_points, g_feats, g_influ.reshape(-1, 1), zsum, dssum, g_a, g_b, None,
                 *gkW, *gkb, *gvW, *gvb)
@@ -559,6 +623,7 @@ class ProximityAttention(nn.Module):
         self.precision = precision
         self.embed = Embeddings(self.dk, self.dq, self.dv, E, eps)
         self.attention_layer = AttentionLayer(E, A.d_model, A.score_act)
+        self.weight_images = WeightImages(self)
 
     # ------------------------------------------------------------------ per-ray query side (5% of the work)
     def query_terms(self, rays_d_flat, precision):
@@ -572,8 +637,9 @@ class ProximityAttention(nn.Module):
         elif fq.mlp.skip_layers:
             raise NotImplementedError("skip_layers in the query stack are not used by any shipped config")
         else:
-            q = _StackBf16Fn.apply(q, self.q_slope, len(lins), torch.is_grad_enabled(), *[l.weight for l in lins],
-                                   *[l.bias for l in lins])
+            imgs = self.weight_images.stack("q", len(lins))
+            q = _StackBf16Fn.apply(q, self.q_slope, len(lins), torch.is_grad_enabled(), imgs if imgs[0] is not None else None,
+                                   *[l.weight for l in lins], *[l.bias for l in lins])
         al = self.attention_layer
         scale = 1.0 / math.sqrt(self.d_model)
         on = self.embed.embed_k.outnorm
@@ -648,6 +714,8 @@ class ProximityAttention(nn.Module):
             if need > 0.8 * free:
                 ray_chunk = max(4096, int(0.4 * free / (K * per_row)) // 128 * 128)
         with torch.cuda.device(rd.device):      # the C ABI launches on the current device
+            if precision != "fp32":
+                self.weight_images.refresh()    # one launch: every weight image of the three stacks, both directions
             if not ray_chunk or (N == 1 and H * W <= ray_chunk) or (N * H * W <= ray_chunk):
                 return self._rows(rays_o, rd.reshape(-1, 3), idx.reshape(-1, K), points, feats, influ, precision, N, H * W)
             from torch.utils.checkpoint import checkpoint

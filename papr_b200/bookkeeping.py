@@ -1,16 +1,22 @@
 """Point growing (stage a14): reference models/utils.py:9-109 ``add_points_knn`` on the GPU.
 
-The reference copies the cloud to the host and queries a scipy KDTree; here the k-nearest-neighbour search is an exact
-brute-force pass on the device (float64 distances, chunked so the P x P matrix never exists), which returns the same
-neighbours as the KDTree up to exact distance ties.  The random convex weights come from numpy's global RNG with the
-reference's call (np.random.uniform(0, 1, (Nq, k))) so that a seeded run draws the same numbers.
+The reference copies the cloud to the host and queries a scipy KDTree; here the k-nearest-neighbour search is the
+library's exact brute-force kernel (``papr_knn``: float64 distances, one warp per query, nothing of size P x P ever
+exists), which returns the same neighbours as the KDTree up to exact distance ties.  The random convex weights come
+from numpy's global RNG with the reference's call (np.random.uniform(0, 1, (Nq, k))) so that a seeded run draws the same
+numbers.
 """
 import numpy as np
 import torch
 
+from . import ops
+
 
 def knn(points, queries, k, chunk=4096):
-    """(dist float64 (Q,k), idx int64 (Q,k)) of the k nearest `points` for every query, ascending (self included)."""
+    """(dist float64 (Q,k), idx int64 (Q,k)) of the k nearest `points` for every query, ascending (self included).
+    CUDA tensors go through papr_knn; host tensors (the CPU-constructed container of tests/test_host_logic.py) use torch."""
+    if points.is_cuda and k <= 32:
+        return ops.knn(points, queries, k)
     p64 = points.double()
     dists, inds = [], []
     for s in range(0, queries.shape[0], chunk):

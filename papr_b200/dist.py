@@ -63,7 +63,19 @@ class GradBucket:
 
 
 def allreduce_gradients(model, bucket=None):
-    """Average gradients across ranks with one flat-bucket all-reduce; returns the (re)usable bucket."""
+    """Average gradients across ranks with one flat-bucket all-reduce; returns the (re)usable bucket.
+
+    With the fused optimiser (papr_b200/optim.py) the gradients already ARE views of one flat fp32 bucket: the
+    all-reduce (sum) runs on it in place -- no pack / unpack copies -- and the 1/world averaging is folded into the Adam
+    launch of the following model.step()."""
+    flat = getattr(model, "_flat", None)
+    if flat is not None and flat.flat_g is not None:
+        flat.bind_grads()
+        world = dist.get_world_size() if dist.is_initialized() else 1
+        if world > 1:
+            dist.all_reduce(flat.flat_g, op=dist.ReduceOp.SUM)
+            model._grad_scale = 1.0 / world
+        return flat
     params = trainable_parameters(model)
     if bucket is None or not bucket.matches(params):
         bucket = GradBucket(params)      # rebuilt after prune/add (parameter tensors are replaced)

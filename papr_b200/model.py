@@ -23,6 +23,7 @@ from . import ops
 from .attention import ProximityAttention
 from .bookkeeping import add_points_knn
 from .nn import MappingMLP, make_activation
+from .optim import FlatAdam, FlatAdamBucket
 from .renderer import get_generator
 from .schedule import create_learning_rate_fn, reposition
 
@@ -55,9 +56,10 @@ def _cube_lattice(center, num_pts, scale):
 
 
 class PAPR(nn.Module):
-    def __init__(self, args, device="cuda", precision="bf16", verbose=False, ray_chunk=None):
+    def __init__(self, args, device="cuda", precision="bf16", verbose=False, ray_chunk=None, fused_optimizer=True):
         super().__init__()
         self.args = args
+        self.fused_optimizer = fused_optimizer      # False: one torch.optim.Adam per group as the reference (A/B in tests)
         self.eps = args.eps
         self.device = device
         self.verbose = verbose
@@ -143,31 +145,65 @@ class PAPR(nn.Module):
         if self.bkg_feats is not None and self.args.geoms.background.learnable:
             groups.append(("bkg_feats", [self.bkg_feats], lr_opt.bkg_feats))
         self.optimizers, self.schedulers = {}, {}
+        # On the GPU all groups share one flat gradient / moment bucket and step in ONE launch (papr_b200/optim.py,
+        # SURVEY 8(f1)); a model still on the host keeps torch.optim.Adam (container behaviour only, as the reference).
+        self._flat = FlatAdamBucket(self.points.device) if (self.points.is_cuda and self.fused_optimizer) else None
+        self._grad_scale = 1.0
+        self._opt_total_steps, self._opt_stepped = total_steps, False
         for name, params, opt in groups:
             if name in self.args.training.fix_keys:
                 continue
             wd = 0 if name == "points" else opt.weight_decay
-            optim = torch.optim.Adam(params, lr=opt.base_lr * f, weight_decay=wd)
+            if self._flat is not None:
+                optim = FlatAdam(params, self._flat, lr=opt.base_lr * f, weight_decay=wd)
+            else:
+                optim = torch.optim.Adam(params, lr=opt.base_lr * f, weight_decay=wd)
             self.optimizers[name] = optim
             self.schedulers[name] = create_learning_rate_fn(optim, steps, opt, start_step=total_steps)
+        if self._flat is not None:
+            self._flat.finalize()
+
+    def _apply(self, fn, *args, **kwargs):
+        """model.to(device) / .cuda(): the optimisers built in __init__ (before the move) are rebuilt for the new device,
+        as long as they have not been stepped -- this is what switches the usual `PAPR(args, device).to(device)` flow of
+        train.py:304-307 to the fused optimiser."""
+        out = super()._apply(fn, *args, **kwargs)
+        if getattr(self, "optimizers", None) is not None and not getattr(self, "_opt_stepped", True):
+            was_cuda = self._flat is not None
+            if self.points.is_cuda != was_cuda:
+                self.init_optimizers(self._opt_total_steps)
+        return out
 
     def clear_optimizer(self):
         self.optimizers.clear()
         del self.optimizers
+        self._flat = None
 
     def clear_scheduler(self):
         self.schedulers.clear()
         del self.schedulers
 
     def clear_grad(self):
+        if self._flat is not None:
+            self._flat.zero_grad()          # one memset; .grad tensors stay views of the flat bucket
+            return
         for optimizer in self.optimizers.values():
             if optimizer is not None:
                 optimizer.zero_grad()
 
     def step(self, step=-1):
-        for optimizer in self.optimizers.values():
-            if optimizer is not None:
-                self.scaler.step(optimizer)
+        self._opt_stepped = True
+        if self._flat is not None and not self.scaler.is_enabled():
+            # every group in one papr_adam_step launch; _grad_scale = 1/world after a summed all-reduce (papr_b200/dist.py)
+            self._flat.step_all([o for o in self.optimizers.values() if o is not None], self._grad_scale)
+            self._grad_scale = 1.0
+            for optimizer in self.optimizers.values():       # keep LambdaLR's "optimizer.step() before lr_scheduler.step()" bookkeeping
+                if optimizer is not None:
+                    optimizer._opt_called = True
+        else:
+            for optimizer in self.optimizers.values():
+                if optimizer is not None:
+                    self.scaler.step(optimizer)
         for scheduler in self.schedulers.values():
             if scheduler is not None:
                 scheduler.step()
@@ -204,12 +240,21 @@ class PAPR(nn.Module):
     def prune_points(self, thresh):
         if self.points_influ_scores is None:
             return 0
-        if self.args.training.prune_type == "<":
-            mask = self.points_influ_scores[:, 0] > thresh
-        elif self.args.training.prune_type == ">":
-            mask = self.points_influ_scores[:, 0] < thresh
-        else:
+        if self.args.training.prune_type not in ("<", ">"):
             raise ValueError("Invalid prune type")
+        keep_less = self.args.training.prune_type == ">"
+        if self.points.is_cuda:       # order-preserving stream compaction on the device (papr_prune_compact)
+            P = self.points.shape[0]
+            feats = self.pc_feats.detach() if self.use_pc_feats else None
+            pts, influ, feats, kept = ops.prune_compact(self.points.detach(), self.points_influ_scores.detach(), feats,
+                                                        float(thresh), keep_less)
+            self.points = nn.Parameter(pts.clone(), requires_grad=self.points.requires_grad)
+            self.points_influ_scores = nn.Parameter(influ.clone(), requires_grad=self.points_influ_scores.requires_grad)
+            if self.use_pc_feats:
+                self.pc_feats = nn.Parameter(feats.clone(), requires_grad=self.pc_feats.requires_grad)
+            self._idx32 = None
+            return torch.tensor(P - kept, device=pts.device)
+        mask = self.points_influ_scores[:, 0] < thresh if keep_less else self.points_influ_scores[:, 0] > thresh
         n_pruned = torch.sum(mask == 0)
         self.points = nn.Parameter(self.points[mask, :], requires_grad=self.points.requires_grad)
         self.points_influ_scores = nn.Parameter(self.points_influ_scores[mask, :],

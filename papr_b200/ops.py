@@ -257,3 +257,53 @@ def stack_bf16(x, K0, layers, slope=0.0):
         K = l["N"]
     call("papr_stack_bf16", x.data_ptr(), K0, ctypes.cast(arr, ctypes.c_void_p), len(layers), x.rows_pad, float(slope),
          flops=flops, nbytes=nbytes)
+
+
+# --------------------------------------------------------------------------- bookkeeping / ray generation
+def knn(points, queries, k):
+    """Stage a14 (reference models/utils.py:21,73: KDTree.query): (dist float64 (Q,k), idx int64 (Q,k)) of the k nearest
+    `points` for every query, ascending, ties by smaller index.  CUDA fp32 inputs, exact float64 distances."""
+    pts, qs = _f32c(points), _f32c(queries)
+    P, Q = pts.shape[0], qs.shape[0]
+    if not (1 <= k <= 32) or k > P:
+        raise ValueError(f"knn needs 1 <= k <= min(32, P) (k={k}, P={P})")
+    dist = torch.empty((Q, k), dtype=torch.float64, device=pts.device)
+    idx = torch.empty((Q, k), dtype=torch.int32, device=pts.device)
+    with torch.cuda.device(pts.device):
+        call("papr_knn", pts.data_ptr(), P, qs.data_ptr(), Q, k, dist.data_ptr(), idx.data_ptr(), flops=8.0 * P * Q,
+             nbytes=12.0 * (P + Q) + 12.0 * Q * k)
+    return dist, idx.long()
+
+
+def prune_compact(points, influ, feats, thresh, keep_less=False):
+    """Stage a14 (reference models/model.py:335-358): rows with influence > thresh (or < thresh) kept in order.
+    Returns (points, influ (n,1), feats or None, n_kept int) -- one device->host read of the count."""
+    pts, inf = _f32c(points), _f32c(influ).reshape(-1)
+    fts = _f32c(feats) if feats is not None else None
+    P = pts.shape[0]
+    F = fts.shape[1] if fts is not None else 0
+    dev = pts.device
+    out_p, out_i = torch.empty_like(pts), torch.empty_like(inf)
+    out_f = torch.empty_like(fts) if fts is not None else None
+    scratch = torch.empty(((P + 255) // 256 + 1,), dtype=torch.int32, device=dev)
+    n = torch.zeros((1,), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        call("papr_prune_compact", pts.data_ptr(), inf.data_ptr(), fts.data_ptr() if fts is not None else None, P, F,
+             float(thresh), int(keep_less), out_p.data_ptr(), out_i.data_ptr(), out_f.data_ptr() if out_f is not None else None,
+             scratch.data_ptr(), n.data_ptr(), nbytes=8.0 * P * (4 + F), kernels=3)
+    kept = int(n.item())
+    return out_p[:kept], out_i[:kept].reshape(-1, 1), (out_f[:kept] if out_f is not None else None), kept
+
+
+def generate_rays(c2w, H, W, focal_x, focal_y=None, window=None, coord_scale=1.0):
+    """SURVEY 8(f3) (reference dataset/utils.py:81-96 get_rays): rays of the pixel window (h0, h1, w0, w1) of H x W views
+    on the device.  c2w (N,4,4) CUDA fp32 -> rays_o (N,3) = coord_scale * c2w[:, :3, 3], rays_d (N,h,w,3) unit norm."""
+    c = _f32c(c2w).reshape(-1, 4, 4)
+    h0, h1, w0, w1 = window if window is not None else (0, H, 0, W)
+    N = c.shape[0]
+    rays_o = torch.empty((N, 3), dtype=torch.float32, device=c.device)
+    rays_d = torch.empty((N, h1 - h0, w1 - w0, 3), dtype=torch.float32, device=c.device)
+    with torch.cuda.device(c.device):
+        call("papr_generate_rays", c.data_ptr(), N, H, W, float(focal_x), float(focal_y if focal_y is not None else focal_x),
+             h0, w0, h1 - h0, w1 - w0, float(coord_scale), rays_o.data_ptr(), rays_d.data_ptr(), nbytes=12.0 * rays_d.numel() / 3)
+    return rays_o, rays_d
