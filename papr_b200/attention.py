@@ -698,8 +698,8 @@ class ProximityAttention(nn.Module):
         precision = precision or self.precision
         N, H, W, _ = rays_d.shape
         K = idx.shape[-1]
-        if K > 31:
-            raise NotImplementedError("the blend kernel holds the K candidates + background in one warp: K <= 31")
+        if K > 32:
+            raise NotImplementedError("the blend kernels hold a ray's K candidates in the lanes of one warp: K <= 32")
         rays_o = rays_o.detach().float().contiguous()
         rd = rays_d.detach().float().contiguous().reshape(N, H * W, 3)
         idx = idx.reshape(N, H * W, K).contiguous()

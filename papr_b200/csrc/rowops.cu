@@ -894,8 +894,9 @@ __global__ void __launch_bounds__(128, 2) attn_prologue_bwd_rows_kernel(const Pr
             atomicAdd(p.g_points + (size_t)pidx * 3 + 0, dx[3] + u[0] * sd);
             atomicAdd(p.g_points + (size_t)pidx * 3 + 1, dx[4] + u[1] * sd);
             atomicAdd(p.g_points + (size_t)pidx * 3 + 2, dx[5] + u[2] * sd);
-            // d feats = the tail of d vin (columns DPE .. DV-1)
-            float fv[F];
+            // d feats = the tail of d vin (columns DPE .. DV-1), sent out four at a time as they complete
+            float *gf = p.g_feats + (size_t)pidx * F;
+            float grp[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int c = DPE >> 3; c <= (DV - 1) >> 3; ++c) {
                 float f8[8];
@@ -903,12 +904,12 @@ __global__ void __launch_bounds__(128, 2) attn_prologue_bwd_rows_kernel(const Pr
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     const int f = c * 8 + e - DPE;
-                    if (f >= 0 && f < F) fv[f] = f8[e];
+                    if (f >= 0 && f < F) {
+                        grp[f & 3] = f8[e];
+                        if ((f & 3) == 3) red_add_v4(gf + (f - 3), grp[0], grp[1], grp[2], grp[3]);
+                    }
                 }
             }
-            float *gf = p.g_feats + (size_t)pidx * F;
-#pragma unroll
-            for (int f = 0; f < F; f += 4) red_add_v4(gf + f, fv[f], fv[f + 1], fv[f + 2], fv[f + 3]);
         }
         __syncwarp();
         column_sums(acc_a2, row0);                   // g_a2 += sum over rows of d kin * z (bf16 products staged in place)
@@ -1078,17 +1079,20 @@ __global__ void __launch_bounds__(kRowThreads) score_blend_fwd_kernel(const Scor
         }
         }
         // model.py:524-533: influence scores, background token, softmax, top-K renormalisation
+        // (the background token is a warp-uniform scalar, not a lane, so K may use all 32 lanes)
         float s = -INFINITY;
         if (lane < p.K) {
             if (!p.sc_ready) p.sc[ray * p.K + lane] = my_sc;
             s = my_sc * __ldg(p.influ + p.idx[ray * p.K + lane]);
-        } else if (lane == p.K) s = p.bkg_score;
-        const float mx = warp_max(s);
-        const float e = (lane <= p.K) ? expf(s - mx) : 0.f;
-        const float tot = warp_sum(e);
+        }
+        const float mx = fmaxf(warp_max(s), p.bkg_score);
+        const float e = (lane < p.K) ? expf(s - mx) : 0.f;
+        const float eb = expf(p.bkg_score - mx);
+        const float tot = warp_sum(e) + eb;
         const float attn = e / tot;
-        if (lane <= p.K) p.attn[ray * (p.K + 1) + lane] = attn;
-        const float topk = warp_sum(lane < p.K ? attn : 0.f);
+        if (lane < p.K) p.attn[ray * (p.K + 1) + lane] = attn;
+        if (lane == 0) p.attn[ray * (p.K + 1) + p.K] = eb / tot;
+        const float topk = warp_sum(attn);
         const float w = p.normalize ? attn / topk : attn;
         for (int c0 = 0; c0 < p.C; c0 += 32) {
             const int c = c0 + lane;
@@ -1110,8 +1114,9 @@ __global__ void __launch_bounds__(kRowThreads) blend_bwd_kernel(const ScoreParam
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc_bv[e] = 0.f;
     for (int64_t ray = (int64_t)blockIdx.x * kRowWarps + warp; ray < p.R; ray += (int64_t)gridDim.x * kRowWarps) {
-        const float attn = (lane <= p.K) ? p.attn[ray * (p.K + 1) + lane] : 0.f;
-        const float topk = warp_sum(lane < p.K ? attn : 0.f);
+        const float attn = (lane < p.K) ? p.attn[ray * (p.K + 1) + lane] : 0.f;
+        const float attn_b = p.attn[ray * (p.K + 1) + p.K];          // background weight: warp-uniform, K may be 32
+        const float topk = warp_sum(attn);
         const float w = p.normalize ? attn / topk : attn;
         // d w_k = d_fused . v_k   (lane k)
         float dw = 0.f;
@@ -1133,9 +1138,10 @@ __global__ void __launch_bounds__(kRowThreads) blend_bwd_kernel(const ScoreParam
             const float mix = warp_sum(lane < p.K ? dw * w : 0.f);
             da = (lane < p.K) ? (dw - mix) / topk : 0.f;
         } else da = (lane < p.K) ? dw : 0.f;
-        if (p.d_attn && lane <= p.K) da += p.d_attn[ray * (p.K + 1) + lane];
-        const float inner = warp_sum(lane <= p.K ? attn * da : 0.f);
-        const float ds = (lane <= p.K) ? attn * (da - inner) : 0.f;       // softmax backward
+        if (p.d_attn && lane < p.K) da += p.d_attn[ray * (p.K + 1) + lane];
+        const float da_b = p.d_attn ? p.d_attn[ray * (p.K + 1) + p.K] : 0.f;
+        const float inner = warp_sum(attn * da) + attn_b * da_b;
+        const float ds = (lane < p.K) ? attn * (da - inner) : 0.f;        // softmax backward
         if (lane < p.K) {
             const float sc = p.sc[ray * p.K + lane];
             const int pi = p.idx[ray * p.K + lane];
@@ -1342,6 +1348,37 @@ static int row_grid(int64_t R)
 
 using namespace papr;
 
+// row-per-lane prologues exist for the shipped shapes: PE order 6 (nerfsyn) / 4 (Tanks&Temples), feature width 64 / 128 (materials.yml)
+template <int L, int F>
+static int launch_prologue_fwd_rows(const PrologueParams &p, cudaStream_t stream)
+{
+    constexpr int S = 1 + 2 * L, NBK = (9 * S + 63) / 64, NBV = (6 * S + F + 63) / 64, NBS = NBK > NBV ? NBK : NBV;
+    constexpr int smem = kRowWarps * NBS * 4096;
+    static SmemAttrOnce once;
+    PAPR_CUDA_TRY(ensure_dyn_smem(once, attn_prologue_fwd_rows_kernel<L, F>, smem));
+    const int64_t groups = ((p.R * p.K + 127) / 128 * 128 + kRowThreads - 1) / kRowThreads;
+    attn_prologue_fwd_rows_kernel<L, F><<<(int)(groups < 2 * kNumSMs ? groups : 2 * kNumSMs), kRowThreads, smem, stream>>>(p);
+    return check_launch();
+}
+
+template <int L, int F>
+static int launch_prologue_bwd_rows(const PrologueParams &p, cudaStream_t stream)
+{
+    constexpr int S = 1 + 2 * L, NBK = (9 * S + 63) / 64, NBV = (6 * S + F + 63) / 64;
+    constexpr int smem = 4 * (NBK + NBV) * 4096;
+    static SmemAttrOnce once;
+    PAPR_CUDA_TRY(ensure_dyn_smem(once, attn_prologue_bwd_rows_kernel<L, F>, smem));
+    const int64_t groups = ((p.R * p.K + 127) / 128 * 128 + 127) / 128;
+    attn_prologue_bwd_rows_kernel<L, F><<<(int)(groups < 2 * kNumSMs ? groups : 2 * kNumSMs), 128, smem, stream>>>(p);
+    return check_launch();
+}
+
+static bool rows_shape(const PrologueParams &p, int L, int F)
+{
+    const int S = 1 + 2 * L;
+    return p.L == L && p.F == F && p.nblk_k == (9 * S + 63) / 64 && p.nblk_v == (6 * S + F + 63) / 64;
+}
+
 static int prologue_check(int64_t R, int64_t rays_per_view, int K, int L, int F, int dk_pad, int dv_pad)
 {
     if (R <= 0 || rays_per_view <= 0 || K < 1 || K > 32 || L < 0 || L > 6 || F < 0) return PAPR_ERR_INVALID_ARGUMENT;
@@ -1364,13 +1401,11 @@ extern "C" int papr_attn_prologue_fwd(const float *rays_o, const float *rays_d, 
     p.nblk_k = dk_pad / 64; p.nblk_v = dv_pad / 64; p.eps = eps;
     p.kin = (uint8_t *)kin; p.vin = (uint8_t *)vin; p.kin_f32 = kin_f32; p.vin_f32 = vin_f32;
     if (kin_f32 || vin_f32) attn_prologue_fwd_kernel<<<row_grid(R), kRowThreads, 0, (cudaStream_t)stream>>>(p);
-    else if (L == 6 && F == 64 && p.nblk_k == 2 && p.nblk_v == 3 && !getenv("PAPR_PROLOGUE_HALFWARP")) {
-        constexpr int smem = kRowWarps * 3 * 4096;
-        static SmemAttrOnce once;
-        PAPR_CUDA_TRY(ensure_dyn_smem(once, attn_prologue_fwd_rows_kernel<6, 64>, smem));
-        const int64_t groups = ((R * K + 127) / 128 * 128 + kRowThreads - 1) / kRowThreads;
-        attn_prologue_fwd_rows_kernel<6, 64><<<(int)(groups < 2 * kNumSMs ? groups : 2 * kNumSMs), kRowThreads, smem, (cudaStream_t)stream>>>(p);
-    } else attn_prologue_fwd_fast_kernel<<<row_grid(R), kRowThreads, 0, (cudaStream_t)stream>>>(p);
+    else if (!getenv("PAPR_PROLOGUE_HALFWARP") && rows_shape(p, 6, 64)) return launch_prologue_fwd_rows<6, 64>(p, (cudaStream_t)stream);
+    else if (!getenv("PAPR_PROLOGUE_HALFWARP") && rows_shape(p, 4, 64)) return launch_prologue_fwd_rows<4, 64>(p, (cudaStream_t)stream);
+    else if (!getenv("PAPR_PROLOGUE_HALFWARP") && rows_shape(p, 6, 128)) return launch_prologue_fwd_rows<6, 128>(p, (cudaStream_t)stream);
+    else if (!getenv("PAPR_PROLOGUE_HALFWARP") && rows_shape(p, 4, 128)) return launch_prologue_fwd_rows<4, 128>(p, (cudaStream_t)stream);
+    else attn_prologue_fwd_fast_kernel<<<row_grid(R), kRowThreads, 0, (cudaStream_t)stream>>>(p);
     return check_launch();
 }
 
@@ -1391,13 +1426,11 @@ extern "C" int papr_attn_prologue_bwd(const float *rays_o, const float *rays_d, 
     p.dkin = (const uint8_t *)dkin; p.dvin = (const uint8_t *)dvin; p.dkin_f32 = dkin_f32; p.dvin_f32 = dvin_f32;
     p.g_points = g_points; p.g_feats = g_feats; p.g_a2 = g_ln_a; p.g_b2 = g_ln_b;
     if (dkin_f32 || dvin_f32) attn_prologue_bwd_kernel<<<row_grid(R), kRowThreads, 0, (cudaStream_t)stream>>>(p);
-    else if (L == 6 && F == 64 && p.nblk_k == 2 && p.nblk_v == 3 && !getenv("PAPR_PROLOGUE_HALFWARP")) {
-        constexpr int smem = 4 * 5 * 4096;
-        static SmemAttrOnce once;
-        PAPR_CUDA_TRY(ensure_dyn_smem(once, attn_prologue_bwd_rows_kernel<6, 64>, smem));
-        const int64_t groups = ((R * K + 127) / 128 * 128 + 127) / 128;
-        attn_prologue_bwd_rows_kernel<6, 64><<<(int)(groups < 2 * kNumSMs ? groups : 2 * kNumSMs), 128, smem, (cudaStream_t)stream>>>(p);
-    } else attn_prologue_bwd_fast_kernel<<<row_grid(R), kRowThreads, 0, (cudaStream_t)stream>>>(p);
+    else if (!getenv("PAPR_PROLOGUE_HALFWARP") && rows_shape(p, 6, 64)) return launch_prologue_bwd_rows<6, 64>(p, (cudaStream_t)stream);
+    else if (!getenv("PAPR_PROLOGUE_HALFWARP") && rows_shape(p, 4, 64)) return launch_prologue_bwd_rows<4, 64>(p, (cudaStream_t)stream);
+    else if (!getenv("PAPR_PROLOGUE_HALFWARP") && rows_shape(p, 6, 128)) return launch_prologue_bwd_rows<6, 128>(p, (cudaStream_t)stream);
+    else if (!getenv("PAPR_PROLOGUE_HALFWARP") && rows_shape(p, 4, 128)) return launch_prologue_bwd_rows<4, 128>(p, (cudaStream_t)stream);
+    else attn_prologue_bwd_fast_kernel<<<row_grid(R), kRowThreads, 0, (cudaStream_t)stream>>>(p);
     return check_launch();
 }
 
@@ -1407,7 +1440,7 @@ extern "C" int papr_score_blend_fwd(const void *h5, const float *h5_f32, const f
                                     float *attn, float *sc, float *stats, void *stream)
 {
     if ((!h5 && !h5_f32) || !ua || !cprime || !influ || !idx || !v || !fused || !attn || !sc || !stats) return PAPR_ERR_INVALID_ARGUMENT;
-    if (R <= 0 || K < 1 || K > 31 || C < 1 || ldv < C) return PAPR_ERR_INVALID_ARGUMENT;
+    if (R <= 0 || K < 1 || K > 32 || C < 1 || ldv < C) return PAPR_ERR_INVALID_ARGUMENT;
     ScoreParams p = {};
     p.h5 = (const uint8_t *)h5; p.h5_f32 = h5_f32; p.ua = ua; p.cprime = cprime; p.influ = influ; p.idx = idx; p.v = v;
     p.R = R; p.K = K; p.C = C; p.ldv = (int)ldv; p.score_relu = score_relu; p.normalize = normalize;
@@ -1431,7 +1464,7 @@ extern "C" int papr_blend_bwd(const float *d_fused, const float *d_attn, const f
                               float *g_bias_v, void *stream)
 {
     if (!d_fused || !attn || !sc || !influ || !idx || !v || !dv_blocked || !d_score || !g_influ || !g_bias_v) return PAPR_ERR_INVALID_ARGUMENT;
-    if (R <= 0 || K < 1 || K > 31 || C < 1 || C > 64 || ldv < C) return PAPR_ERR_INVALID_ARGUMENT;
+    if (R <= 0 || K < 1 || K > 32 || C < 1 || C > 64 || ldv < C) return PAPR_ERR_INVALID_ARGUMENT;
     ScoreParams p = {};
     p.d_fused = d_fused; p.d_attn = d_attn; p.attn = const_cast<float *>(attn); p.sc = const_cast<float *>(sc); p.influ = influ; p.idx = idx; p.v = v;
     p.R = R; p.K = K; p.C = C; p.ldv = (int)ldv; p.score_relu = score_relu; p.normalize = normalize;
@@ -1445,7 +1478,7 @@ extern "C" int papr_key_score_bwd(const float *d_score, const void *h5, const fl
                                   float *zsum, float *dssum, float *g_bias5, void *stream)
 {
     if (!d_score || (!h5 && !h5_f32) || !stats || !ua || !dh5_blocked || !zsum || !dssum || !g_bias5) return PAPR_ERR_INVALID_ARGUMENT;
-    if (R <= 0 || K < 1 || K > 31) return PAPR_ERR_INVALID_ARGUMENT;
+    if (R <= 0 || K < 1 || K > 32) return PAPR_ERR_INVALID_ARGUMENT;
     ScoreParams p = {};
     p.d_score_in = d_score; p.h5 = (const uint8_t *)h5; p.h5_f32 = h5_f32; p.stats = const_cast<float *>(stats); p.ua = ua; p.R = R; p.K = K;
     p.eps = eps; p.dh5 = (uint8_t *)dh5_blocked; p.dh5_f32 = dh5_f32; p.zsum = zsum; p.dssum = dssum; p.g_b5 = g_bias5;
