@@ -60,6 +60,20 @@ int papr_select_topk_sorted(const float *rays_o, const float *rays_d, const floa
                             int K, float eps, const float *pmax, int32_t *idx_out, void *stream);
 
 /*
+ * Stage a1 with screen-space culling (same result as papr_select_topk, bit for bit) -- the product path.  All rays of a
+ * view share one origin, so a point can only be near a ray if its DIRECTION from the origin is near the ray's: the caller
+ * bins every view's points on a G x G grid in gnomonic coordinates around the view's mean ray direction and sorts them by
+ * cell (papr_b200/ops.py view_grids); a warp then visits the cells in rings around its rays and stops when a conservative
+ * lower bound on the distance to everything unvisited exceeds its current thresholds.
+ *   sorted_v (n_views*P, 4) f32 = (p - o, eps*|p - o|^2) in cell order, per view;  perm (n_views*P) i32 original indices;
+ *   cells (n_views*G*G, 4) i32 = first / one-past-last position within the view, bits of the smallest |depth| of the cell, 0;
+ *   view_params (n_views, 20) f32 = e1(3) e2(3) c(3) gmin(2) cell(2) 1/cell(2) min depth, max |v|^2, 0, 0, 0.
+ */
+int papr_select_topk_grid(const float *rays_o, const float *rays_d, const void *sorted_v, const int32_t *perm,
+                          const int32_t *cells, const float *view_params, int64_t n_views, int64_t rays_per_view, int64_t P,
+                          int G, int K, float eps, int32_t *idx_out, void *stream);
+
+/*
  * Tensor-core building blocks (stages a7/a8/a12).  Activations use the library's "tile-blocked" bf16 layout: a logical
  * [rows, cols] matrix (rows % 128 == 0, cols % 64 == 0) stored as [rows/128][cols/64] blocks of 16 KB, each block
  * 128 rows x 64 columns with the eight 16-byte chunks of a row XOR-swizzled by (row & 7) -- the shared-memory image

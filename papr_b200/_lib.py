@@ -18,6 +18,7 @@ SIGNATURES = {
     "papr_last_cuda_error": [],
     "papr_select_topk": [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i32, _f32, _ptr, _ptr],
     "papr_select_topk_sorted": [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _i32, _f32, _ptr, _ptr, _ptr],
+    "papr_select_topk_grid": [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i64, _i64, _i32, _i32, _f32, _ptr, _ptr],
     "papr_blocked_from_f32": [_ptr, _i64, _i32, _i64, _ptr, _i64, _i32, _ptr],
     "papr_blocked_to_f32": [_ptr, _i32, _ptr, _i64, _i32, _i64, _ptr],
     "papr_pack_weight": [_ptr, _i64, _i32, _i32, _i32, _i32, _i32, _f32, _ptr, _ptr],

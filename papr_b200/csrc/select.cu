@@ -404,6 +404,221 @@ select_topk3_kernel(const float *__restrict__ rays_o, const float *__restrict__ 
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Screen-space grid variant (the product path for all but tiny clouds): the same two-phase exact selection, but a warp
+// only looks at the points that can matter for its rays.
+//   All rays of a view leave one origin o, so the distance from a point p (v = p - o) to the line through o with
+//   direction d depends on the two DIRECTIONS only: in a camera frame (e1, e2, c) with c the view's mean ray direction,
+//   write v = w3 (g1, g2, 1) and d ~ (h1, h2, 1) (gnomonic coordinates g = (v.e1, v.e2)/(v.c), h likewise).  Then
+//       dist(p, line) = |v x d| / |d| = |w3| |(g,1) x (h,1)| / |(h,1)|  >=  |w3| |g - h| / sqrt(1 + |h|^2),
+//   because the first two components of (g,1) x (h,1) are (g2 - h2, h1 - g1).  The host bins the points of every view
+//   on a G x G grid over the gnomonic extent of the view's rays (border cells extend to infinity, points with v.c ~ 0
+//   make their cell unboundable), sorts them by cell and records each cell's smallest |w3|.  A warp walks the cells in
+//   square rings around the cell under its rays and skips a cell -- or stops altogether -- when
+//       |d|_min^2 * zmin^2 * dist2D(cell box, box of the warp's h)^2 / (1 + max|h|^2),   less rounding slack,
+//   exceeds the largest of its rays' current thresholds.  A skipped point could not have been inserted (insertion needs
+//   cheap key < threshold, thresholds only fall), so the candidate lists are those of the full scan up to ties at the
+//   32nd place, which the phase-2 safety test covers: the result is bit-identical to the plain kernel's.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kGridViewFloats = 20;   // per view: e1(3) e2(3) c(3) gmin(2) cell(2) inv_cell(2) zmin_all wmax pad(3)
+
+template <int RPW>
+__global__ void __launch_bounds__(kSelThreads)
+select_grid_kernel(const float *__restrict__ rays_o, const float *__restrict__ rays_d,
+                   const float4 *__restrict__ sv /* (n_views*P): v = p - o and eps*|v|^2, sorted by cell, per view */,
+                   const int32_t *__restrict__ perm /* (n_views*P) original point index */,
+                   const int4 *__restrict__ cells /* (n_views*G*G): start, end, zmin bits, 0 */,
+                   const float *__restrict__ views /* (n_views, kGridViewFloats) */,
+                   int64_t rays_per_view, int P, int G, int K, float eps, int32_t *__restrict__ idx_out, int blocks_per_view)
+{
+    const int view = blockIdx.x / blocks_per_view;
+    const int blk = blockIdx.x - view * blocks_per_view;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const unsigned full = 0xffffffffu;
+    const float INF = __int_as_float(0x7f800000);
+
+    const float *vp = views + (int64_t)view * kGridViewFloats;
+    const float e1x = vp[0], e1y = vp[1], e1z = vp[2], e2x = vp[3], e2y = vp[4], e2z = vp[5], ccx = vp[6], ccy = vp[7], ccz = vp[8];
+    const float gminx = vp[9], gminy = vp[10], cellx = vp[11], celly = vp[12], icx = vp[13], icy = vp[14];
+    const float zmin_all = vp[15], wmax = vp[16];
+    const int4 *vcells = cells + (int64_t)view * G * G;
+
+    const int64_t ray0 = (int64_t)blk * (kSelWarps * RPW) + warp * RPW;
+    if (ray0 >= rays_per_view) return;                          // warp-uniform; no block-wide barrier below
+    float dx[RPW], dy[RPW], dz[RPW], thr[RPW], lk[RPW];
+    int li[RPW];
+    float bx0 = INF, bx1 = -INF, by0 = INF, by1 = -INF, h2max = 0.f, dmin2 = INF, dmax2 = 0.f;
+    bool can_cull = true;
+#pragma unroll
+    for (int j = 0; j < RPW; ++j) {
+        int64_t r = ray0 + j;
+        if (r >= rays_per_view) r = rays_per_view - 1;
+        const float *d = rays_d + ((int64_t)view * rays_per_view + r) * 3;
+        dx[j] = d[0]; dy[j] = d[1]; dz[j] = d[2];
+        thr[j] = INF; lk[j] = INF; li[j] = -1;
+        const float n2 = dx[j] * dx[j] + dy[j] * dy[j] + dz[j] * dz[j];
+        const float w3 = dx[j] * ccx + dy[j] * ccy + dz[j] * ccz;
+        can_cull = can_cull && (w3 * w3 > 0.04f * n2) && w3 > 0.f && n2 > 1e-30f && n2 < 1e30f;
+        const float iw = 1.f / w3;
+        const float hx = (dx[j] * e1x + dy[j] * e1y + dz[j] * e1z) * iw, hy = (dx[j] * e2x + dy[j] * e2y + dz[j] * e2z) * iw;
+        bx0 = fminf(bx0, hx); bx1 = fmaxf(bx1, hx); by0 = fminf(by0, hy); by1 = fmaxf(by1, hy);
+        h2max = fmaxf(h2max, hx * hx + hy * hy);
+        dmin2 = fminf(dmin2, n2); dmax2 = fmaxf(dmax2, n2);
+    }
+    can_cull = can_cull && zmin_all > 0.f && bx1 - bx0 < 1e6f && by1 - by0 < 1e6f;
+    // rounding slack of the gnomonic coordinates (points: host fp32, rays: above), absolute, per axis
+    const float ext = fmaxf(fmaxf(fabsf(gminx), fabsf(gminx + cellx * G)), fmaxf(fabsf(gminy), fabsf(gminy + celly * G)));
+    const float slack = 4e-6f * (1.f + fmaxf(ext, sqrtf(h2max)));
+    const float scale = can_cull ? dmin2 / (1.f + h2max) * 0.998f : 0.f;
+    const float u = 5.9604645e-8f;
+    const float V2c = wmax * dmax2;                              // (max|v| |d|)^2 for the cheap key's rounding-error bound
+    // lower bound of the COMPUTED cheap key of any point at gnomonic distance >= dist of a cell with smallest depth z
+    auto cell_bound = [&](float z, float dist2) -> float {
+        const float b = z * z * dist2 * scale;
+        return b - (32.f * u * sqrtf(V2c * b) + 128.f * u * u * V2c + 8.f * u * b);
+    };
+    int hcx = G >> 1, hcy = G >> 1;
+    if (can_cull) {
+        hcx = min(max((int)floorf((0.5f * (bx0 + bx1) - gminx) * icx), 0), G - 1);
+        hcy = min(max((int)floorf((0.5f * (by0 + by1) - gminy) * icy), 0), G - 1);
+    }
+    float tmax = INF;
+
+    for (int r = 0; r < 2 * G; ++r) {
+        if (r > 0) {
+            const int q = r - 1;                                 // rings 0..q have been visited: cells [hcx-q, hcx+q] x [hcy-q, hcy+q]
+            const bool openL = hcx - q > 0, openR = hcx + q < G - 1, openT = hcy - q > 0, openB = hcy + q < G - 1;
+            if (!(openL || openR || openT || openB)) break;      // the whole grid has been visited
+            if (can_cull) {
+                float lb = INF;
+                if (openL) lb = fminf(lb, bx0 - (gminx + cellx * (float)(hcx - q)));
+                if (openR) lb = fminf(lb, (gminx + cellx * (float)(hcx + q + 1)) - bx1);
+                if (openT) lb = fminf(lb, by0 - (gminy + celly * (float)(hcy - q)));
+                if (openB) lb = fminf(lb, (gminy + celly * (float)(hcy + q + 1)) - by1);
+                lb = fmaxf(lb - slack, 0.f);
+                if (cell_bound(zmin_all, lb * lb) > tmax) break; // nothing outside the visited square can be inserted any more
+            }
+        }
+        const int n = r ? 8 * r : 1;
+        const int x0 = hcx - r, x1 = hcx + r, y0 = hcy - r, y1 = hcy + r;
+        for (int t0 = 0; t0 < n; t0 += 32) {
+            const int t = t0 + lane;
+            int cx = hcx, cy = hcy;
+            if (r) {
+                const int side = t / (2 * r), k = t - side * 2 * r;
+                cx = side == 0 ? x0 + k : side == 1 ? x1 : side == 2 ? x1 - k : x0;
+                cy = side == 0 ? y0 : side == 1 ? y0 + k : side == 2 ? y1 : y1 - k;
+            }
+            int start = 0, end = 0;
+            float bnd = -INF;
+            if (t < n && cx >= 0 && cx < G && cy >= 0 && cy < G) {
+                const int4 m = __ldg(vcells + cy * G + cx);
+                start = m.x; end = m.y;
+                if (can_cull && end > start) {
+                    const float z = __int_as_float(m.z);
+                    const float cxa = (cx == 0) ? -INF : gminx + cellx * (float)cx, cxb = (cx == G - 1) ? INF : gminx + cellx * (float)(cx + 1);
+                    const float cya = (cy == 0) ? -INF : gminy + celly * (float)cy, cyb = (cy == G - 1) ? INF : gminy + celly * (float)(cy + 1);
+                    const float ddx = fmaxf(fmaxf(cxa - bx1, bx0 - cxb) - slack, 0.f);
+                    const float ddy = fmaxf(fmaxf(cya - by1, by0 - cyb) - slack, 0.f);
+                    bnd = cell_bound(z, ddx * ddx + ddy * ddy);
+                }
+            }
+            unsigned todo = __ballot_sync(full, end > start && !(bnd > tmax));
+            while (todo) {
+                const int src = __ffs(todo) - 1;
+                todo &= todo - 1;
+                if (__shfl_sync(full, bnd, src) > tmax) continue;            // the thresholds have fallen since the ballot
+                const int cs = __shfl_sync(full, start, src), ce = __shfl_sync(full, end, src);
+                for (int c = cs; c < ce; c += 32) {
+                    const int pi = c + lane;
+                    float4 v = make_float4(0.f, 0.f, 0.f, INF);
+                    if (pi < ce) v = __ldg(sv + (int64_t)view * P + pi);
+#pragma unroll
+                    for (int j = 0; j < RPW; ++j) {
+                        const float kx = fmaf(v.y, dz[j], -v.z * dy[j]);
+                        const float ky = fmaf(v.z, dx[j], -v.x * dz[j]);
+                        const float kz = fmaf(v.x, dy[j], -v.y * dx[j]);
+                        const float a = fmaf(kx, kx, fmaf(ky, ky, fmaf(kz, kz, v.w)));
+                        unsigned m = __ballot_sync(full, a < thr[j]);
+                        while (m) {
+                            const int s2 = __ffs(m) - 1;
+                            m &= m - 1;
+                            const float ck = __shfl_sync(full, a, s2);
+                            const int ci = c + s2;
+                            if (ck < thr[j]) thr[j] = list_insert(lk[j], li[j], ck, ci, lane, 31);
+                        }
+                    }
+                }
+                tmax = thr[0];
+#pragma unroll
+                for (int j = 1; j < RPW; ++j) tmax = fmaxf(tmax, thr[j]);
+            }
+        }
+    }
+
+    // ---- phase 2: exact keys of the candidates, rank by (key, original index), safety test, (rare) exact rescan
+    const float4 *vsv = sv + (int64_t)view * P;
+    const int32_t *vperm = perm + (int64_t)view * P;
+#pragma unroll
+    for (int j = 0; j < RPW; ++j) {
+        const int64_t r = ray0 + j;
+        if (r >= rays_per_view) continue;                       // warp-uniform
+        const float den = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx[j], dx[j]), __fmul_rn(dy[j], dy[j])),
+                                              __fmul_rn(dz[j], dz[j])), eps);
+        const float rinv = __frcp_rn(den);
+        const int si = li[j];                                   // position in the view's sorted array
+        int ci = -1;
+        float ek = INF;
+        if (si >= 0) {
+            ci = vperm[si];
+            const float4 v = vsv[si];
+            ek = exact_key(v.x, v.y, v.z, dx[j], dy[j], dz[j], den, rinv);
+        }
+        int rank = 0;
+        for (int t = 0; t < 32; ++t) {
+            const float ok = __shfl_sync(full, ek, t);
+            const int oi = __shfl_sync(full, ci, t);
+            rank += (ci >= 0 && oi >= 0 && (ok < ek || (ok == ek && oi < ci))) ? 1 : 0;
+        }
+        const unsigned who = __ballot_sync(full, rank == K - 1 && ci >= 0);
+        const float eK = __shfl_sync(full, ek, who ? __ffs(who) - 1 : 0);
+        const float a32 = thr[j];
+        const float V2 = wmax * den;
+        const float err = 32.f * u * sqrtf(V2 * a32) + 128.f * u * u * V2 + 8.f * u * a32;
+        const bool safe = who != 0 && ((a32 == INF) || (a32 > 1e-8f * fmaxf(V2, 1.f) && eK * den * (1.f + 4.f * u) < a32 - err));
+        if (safe) {
+            if (ci >= 0 && rank < K) idx_out[((int64_t)view * rays_per_view + r) * K + rank] = ci;
+        } else {
+            if (lane == 0) atomicAdd(&g_sel_fallbacks, 1ull);
+            float xk = INF, xt = INF;
+            int xi = -1;
+            for (int c = 0; c < P; c += 32) {
+                const int pi = c + lane;
+                int oi = -1;
+                float key = INF;
+                if (pi < P) {
+                    oi = vperm[pi];
+                    const float4 v = vsv[pi];
+                    key = exact_key(v.x, v.y, v.z, dx[j], dy[j], dz[j], den, rinv);
+                }
+                unsigned m = __ballot_sync(full, key <= xt && oi >= 0);
+                while (m) {
+                    const int src = __ffs(m) - 1;
+                    m &= m - 1;
+                    const float ck = __shfl_sync(full, key, src);
+                    const int cc = __shfl_sync(full, oi, src);
+                    const float lastk = __shfl_sync(full, xk, K - 1);
+                    const int lasti = __shfl_sync(full, xi, K - 1);
+                    if (ck < lastk || (ck == lastk && (lasti < 0 || cc < lasti))) xt = list_insert_lex(xk, xi, ck, cc, lane, K - 1);
+                }
+            }
+            if (lane < K) idx_out[((int64_t)view * rays_per_view + r) * K + lane] = xi;
+        }
+    }
+}
+
 }  // namespace papr
 
 extern "C" int papr_select_topk(const float *rays_o, const float *rays_d, const float *points,
@@ -444,6 +659,24 @@ extern "C" int papr_select_topk_sorted(const float *rays_o, const float *rays_d,
     if (blocks_per_view * n_views > INT32_MAX) return PAPR_ERR_INVALID_ARGUMENT;
     select_topk3_kernel<RPW><<<(unsigned)(blocks_per_view * n_views), kSelThreads, 0, (cudaStream_t)stream>>>(
         rays_o, rays_d, sorted_points, perm, (const float4 *)spheres, (const float4 *)spheres8, rays_per_view, (int)P_pad, K, eps, pmax, idx_out,
+        (int)blocks_per_view);
+    return check_launch();
+}
+
+extern "C" int papr_select_topk_grid(const float *rays_o, const float *rays_d, const void *sorted_v, const int32_t *perm,
+                                     const int32_t *cells, const float *view_params, int64_t n_views, int64_t rays_per_view, int64_t P,
+                                     int G, int K, float eps, int32_t *idx_out, void *stream)
+{
+    using namespace papr;
+    if (!rays_o || !rays_d || !sorted_v || !perm || !cells || !view_params || !idx_out) return PAPR_ERR_INVALID_ARGUMENT;
+    if (K < 1 || K > 32 || P <= K || P > INT32_MAX || G < 1 || G > 1024 || n_views < 0 || rays_per_view < 0) return PAPR_ERR_INVALID_ARGUMENT;
+    if (n_views == 0 || rays_per_view == 0) return PAPR_OK;
+    constexpr int RPW = 4;
+    const int64_t rays_per_block = kSelWarps * RPW;
+    const int64_t blocks_per_view = (rays_per_view + rays_per_block - 1) / rays_per_block;
+    if (blocks_per_view * n_views > INT32_MAX) return PAPR_ERR_INVALID_ARGUMENT;
+    select_grid_kernel<RPW><<<(unsigned)(blocks_per_view * n_views), kSelThreads, 0, (cudaStream_t)stream>>>(
+        rays_o, rays_d, (const float4 *)sorted_v, perm, (const int4 *)cells, view_params, rays_per_view, (int)P, G, K, eps, idx_out,
         (int)blocks_per_view);
     return check_launch();
 }

@@ -57,7 +57,6 @@ def _f32c(t):
     return t.detach().contiguous().float()
 
 
-CULL_MIN_POINTS = 65536    # measured on B200: the culled kernel wins from ~50k points (2x at 100k); below, the plain scan
 
 
 def _bounding_spheres(grp, valid):
@@ -108,10 +107,76 @@ def morton_groups(points):
     return spts, perm, spheres, spheres8, points.norm(dim=-1).max()
 
 
+GRID_MIN_POINTS = 1024     # below this the plain scan is as fast as building the grid
+
+
+def view_grids(rays_o, rays_d, points, eps, G=None):
+    """Host side of the screen-space grid selection (see select_grid_kernel in csrc/select.cu): per view, a camera frame
+    around the mean ray direction, the gnomonic extent of the view's rays, and the points binned on a G x G grid over that
+    extent, sorted by cell.  All torch ops on the device, batched over views, no host synchronisation.
+    rays_o (N,3), rays_d (N,R,3), points (P,3) -> (sorted_v (N*P,4), perm (N*P,) i32, cells (N*G*G,4) i32, views (N,20), G)."""
+    N, R, _ = rays_d.shape
+    P = points.shape[0]
+    dev = points.device
+    if G is None:
+        G = int(min(128, max(8, round((P / 8.0) ** 0.5))))
+    dn = rays_d / rays_d.norm(dim=-1, keepdim=True).clamp_min(1e-30)
+    c = dn.mean(1)
+    c = torch.where(c.norm(dim=-1, keepdim=True) > 1e-6, c, torch.tensor([0.0, 0.0, 1.0], device=dev).expand(N, 3))
+    c = c / c.norm(dim=-1, keepdim=True)
+    helper = torch.where(c[:, :1].abs() < 0.9, torch.tensor([1.0, 0.0, 0.0], device=dev).expand(N, 3),
+                         torch.tensor([0.0, 1.0, 0.0], device=dev).expand(N, 3))
+    e1 = torch.linalg.cross(helper, c)
+    e1 = e1 / e1.norm(dim=-1, keepdim=True)
+    e2 = torch.linalg.cross(c, e1)
+    B = torch.stack([e1, e2, c], dim=1)                                   # (N,3,3), rows = camera axes
+    # gnomonic extent of the rays that point forward (the others cannot be bounded and scan everything)
+    w = torch.einsum("nrj,nij->nri", dn, B)
+    ok = w[..., 2] > 0.25
+    h = w[..., :2] / torch.where(ok, w[..., 2], torch.ones_like(w[..., 2])).unsqueeze(-1)
+    inf = torch.full_like(h, float("inf"))
+    hmin = torch.where(ok.unsqueeze(-1), h, inf).amin(1)
+    hmax = torch.where(ok.unsqueeze(-1), h, -inf).amax(1)
+    none = ~ok.any(1, keepdim=True)
+    hmin = torch.where(none, torch.full_like(hmin, -1.0), hmin)
+    hmax = torch.where(none, torch.full_like(hmax, 1.0), hmax)
+    span = (hmax - hmin).clamp_min(1e-3)
+    gmin = hmin - 0.02 * span
+    cell = (span * 1.04) / G
+    icell = 1.0 / cell
+    # points in every view's frame
+    v = points.unsqueeze(0) - rays_o.unsqueeze(1)                         # (N,P,3): the kernel's v = p - o, rounded once
+    vn2 = torch.addcmul(torch.addcmul(v[..., 0] * v[..., 0], v[..., 1], v[..., 1]), v[..., 2], v[..., 2])
+    pw = torch.einsum("npj,nij->npi", v, B)
+    valid = pw[..., 2].abs() > 1e-3 * vn2.sqrt()
+    g = pw[..., :2] / torch.where(valid, pw[..., 2], torch.ones_like(pw[..., 2])).unsqueeze(-1)
+    cxy = ((g - gmin.unsqueeze(1)) * icell.unsqueeze(1)).floor().clamp(0, G - 1)
+    cxy = torch.where(valid.unsqueeze(-1), cxy, torch.zeros_like(cxy)).long()
+    cid = (torch.arange(N, device=dev).unsqueeze(1) * G + cxy[..., 1]) * G + cxy[..., 0]          # (N,P)
+    az = torch.where(valid, pw[..., 2].abs(), torch.zeros_like(vn2))      # 0: the cell can never be skipped
+    flat = cid.reshape(-1)
+    order = torch.argsort(flat, stable=True)
+    sorted_cid = flat[order]
+    sv = torch.cat([v, (eps * vn2).unsqueeze(-1)], dim=-1).reshape(-1, 4)[order].contiguous()
+    perm = (order % P).to(torch.int32).contiguous()
+    bounds = torch.searchsorted(sorted_cid, torch.arange(N * G * G + 1, device=dev))
+    view_start = (torch.arange(N, device=dev) * P).repeat_interleave(G * G)
+    zmin = torch.full((N * G * G,), float("inf"), device=dev).scatter_reduce(0, flat, az.reshape(-1), "amin")
+    cells = torch.stack([(bounds[:-1] - view_start).to(torch.int32), (bounds[1:] - view_start).to(torch.int32),
+                         zmin.view(torch.int32), torch.zeros(N * G * G, dtype=torch.int32, device=dev)], dim=-1).contiguous()
+    zmin_all = zmin.reshape(N, -1).amin(1) * (1.0 - 1e-6)
+    views = torch.zeros((N, 20), device=dev)
+    views[:, 0:3], views[:, 3:6], views[:, 6:9] = e1, e2, c
+    views[:, 9:11], views[:, 11:13], views[:, 13:15] = gmin, cell, icell
+    views[:, 15], views[:, 16] = zmin_all, vn2.amax(1)
+    return sv, perm, cells, views.contiguous(), G
+
+
 def select_topk(rays_o, rays_d, points, K, eps=1e-6, cull=None):
     """Stage a1 (reference models/model.py:258-283): int32 (N,H,W,K) nearest-point indices per ray,
     ordered by (distance, index).  rays_o (N,3), rays_d (N,H,W,3), points (P,3), all CUDA fp32.
-    cull=None picks the spatially culled kernel for P >= CULL_MIN_POINTS (identical result, see select.cu)."""
+    cull: None = automatic (the screen-space grid kernel for P >= GRID_MIN_POINTS, else the plain scan); "grid";
+    True / "morton" = the Morton-group kernel; False = plain scan.  All variants return the identical result."""
     N, H, W, _ = rays_d.shape
     P = points.shape[0]
     if not (1 <= K <= 32) or K >= P:
@@ -121,8 +186,12 @@ def select_topk(rays_o, rays_d, points, K, eps=1e-6, cull=None):
     R = N * H * W
     work = dict(flops=17.0 * R * P, nbytes=12.0 * R + 12.0 * P + 4.0 * K * R)
     if cull is None:
-        cull = P >= CULL_MIN_POINTS
-    if cull:
+        cull = "grid" if P >= GRID_MIN_POINTS else False
+    if cull == "grid":
+        sv, perm, cells, views, G = view_grids(ro, rd.reshape(N, H * W, 3), pts, float(eps))
+        call("papr_select_topk_grid", ro.data_ptr(), rd.data_ptr(), sv.data_ptr(), perm.data_ptr(), cells.data_ptr(), views.data_ptr(),
+             N, H * W, P, G, K, float(eps), idx.data_ptr(), **work)
+    elif cull:
         spts, perm, spheres, spheres8, pmax = morton_groups(pts)
         pmax = pmax.reshape(1).float().contiguous()
         call("papr_select_topk_sorted", ro.data_ptr(), rd.data_ptr(), spts.data_ptr(), perm.data_ptr(), spheres.data_ptr(), spheres8.data_ptr(),

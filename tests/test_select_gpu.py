@@ -10,15 +10,15 @@ from tests.parity import load_golden, topk_sets_match
 pytestmark = pytest.mark.gpu
 
 
-def _run(rays_o, rays_d, points, K, eps=1e-6):
+def _run(rays_o, rays_d, points, K, eps=1e-6, cull=None):
     from papr_b200 import ops
-    idx = ops.select_topk(rays_o.cuda(), rays_d.cuda(), points.cuda(), K, eps)
+    idx = ops.select_topk(rays_o.cuda(), rays_d.cuda(), points.cuda(), K, eps, cull=cull)
     torch.cuda.synchronize()
     return idx.cpu()
 
 
-def _compare(rays_o, rays_d, points, K, eps=1e-6):
-    got = _run(rays_o, rays_d, points, K, eps)
+def _compare(rays_o, rays_d, points, K, eps=1e-6, cull=None):
+    got = _run(rays_o, rays_d, points, K, eps, cull)
     want, kth = O.select_topk(rays_o, rays_d, points, K, eps)
     assert got.dtype == torch.int32 and got.shape == want.shape
     if torch.equal(got.long(), want):      # same order too: (distance, index) ascending
@@ -50,11 +50,12 @@ def test_select_golden_reference_sets(golden_dir):
     (16, 16, 3000, 20, 1, "cube"), (7, 5, 257, 20, 3, "shell"), (33, 31, 2049, 30, 2, "cube"),
     (4, 4, 33, 32, 1, "cube"), (1, 1, 21, 20, 1, "cube"), (40, 40, 30000, 20, 1, "shell"), (3, 3, 4100, 1, 2, "cube"),
 ])
-def test_select_matches_oracle(H, W, P, K, views, cloud):
+@pytest.mark.parametrize("cull", [False, "grid"])
+def test_select_matches_oracle(H, W, P, K, views, cloud, cull):
     cfg = make_config("chair")
     params = O.init_params(cfg, P, seed=H * 131 + P, cloud=cloud)
     rays_o, rays_d, _ = O.synthetic_rays(H * 4, W * 4, cfg.dataset.coord_scale, n_views=views, seed=P, h0=H, h1=2 * H, w0=W, w1=2 * W)
-    _compare(rays_o, rays_d, params["points"], K)
+    _compare(rays_o, rays_d, params["points"], K, cull=cull)
 
 
 def test_select_exact_ties_and_lattice():
@@ -66,7 +67,8 @@ def test_select_exact_ties_and_lattice():
     # axis-aligned rays through the lattice: plenty of exact ties
     rays_d[0, 0, 0] = torch.tensor([0.0, 0.0, -1.0])
     rays_d[0, 0, 1] = torch.tensor([1.0, 0.0, 0.0])
-    _compare(rays_o, rays_d, pts, 20)
+    for cull in (False, "grid", "morton"):
+        _compare(rays_o, rays_d, pts, 20, cull=cull)
 
 
 def test_select_unnormalised_directions_and_duplicates():
@@ -76,9 +78,10 @@ def test_select_unnormalised_directions_and_duplicates():
     pts = torch.cat([pts, pts[:100]])            # exact duplicates
     rays_o = torch.randn(2, 3, generator=g) * 20
     rays_d = torch.randn(2, 9, 9, 3, generator=g) * torch.rand(2, 9, 9, 1, generator=g) * 3
-    got = _run(rays_o, rays_d, pts, 20)
     want, _ = O.select_topk(rays_o, rays_d, pts, 20)
-    assert torch.equal(got.long(), want)          # identical order: (key, index)
+    for cull in (False, "grid"):
+        got = _run(rays_o, rays_d, pts, 20, cull=cull)
+        assert torch.equal(got.long(), want), cull          # identical order: (key, index)
 
 
 def test_select_rejects_bad_arguments():
@@ -98,7 +101,8 @@ def test_culled_and_plain_kernels_agree_exactly(P, cloud):
     rays_o, rays_d, _ = O.synthetic_rays(256, 256, cfg.dataset.coord_scale, n_views=2, seed=3, h0=100, h1=164, w0=90, w1=150)
     a = ops.select_topk(rays_o.cuda(), rays_d.cuda(), params["points"].cuda(), 20, cull=True)
     b = ops.select_topk(rays_o.cuda(), rays_d.cuda(), params["points"].cuda(), 20, cull=False)
-    assert torch.equal(a, b)
+    c = ops.select_topk(rays_o.cuda(), rays_d.cuda(), params["points"].cuda(), 20, cull="grid")
+    assert torch.equal(a, b) and torch.equal(c, b)
     want, _ = O.select_topk(rays_o[:1], rays_d[:1, :8, :8], params["points"], 20)
     assert torch.equal(a[:1, :8, :8].cpu().long(), want)
 
@@ -114,6 +118,37 @@ def test_culled_kernel_with_ties_duplicates_and_wide_rays():
     rays_o = torch.randn(2, 3, generator=g) * 25
     rays_d = torch.randn(2, 6, 7, 3, generator=g)
     rays_d[0, 0, :4] = torch.tensor([[0.0, 0.0, -1.0], [1.0, 0.0, 0.0], [0.0, 0.0, 1.0], [0.0, -2.0, 0.0]])
-    got = ops.select_topk(rays_o.cuda(), rays_d.cuda(), pts.cuda(), 20, cull=True).cpu().long()
     want, _ = O.select_topk(rays_o, rays_d, pts, 20)
-    assert torch.equal(got, want)
+    for cull in (True, "grid"):
+        got = ops.select_topk(rays_o.cuda(), rays_d.cuda(), pts.cuda(), 20, cull=cull).cpu().long()
+        assert torch.equal(got, want), cull
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_grid_kernel_with_points_all_around_the_camera(seed):
+    """Screen-space culling must stay exact when the cloud surrounds the camera: points behind it (the distance is to the
+    LINE, so they count), points perpendicular to the viewing direction (unbounded gnomonic coordinates), a point at the
+    ray origin itself, several views with different frames, and a view whose rays point everywhere (no culling possible)."""
+    g = torch.Generator().manual_seed(seed)
+    P = 5000
+    pts = torch.randn(P, 3, generator=g) * 30
+    rays_o, rays_d, _ = O.synthetic_rays(96, 96, 10.0, n_views=3, seed=seed, h0=40, h1=56, w0=30, w1=50)
+    pts[7] = rays_o[0]
+    pts[8] = rays_o[1] + 1e-3
+    rays_d[2] = torch.randn(16, 20, 3, generator=g)           # the third view: directions all over the sphere
+    want, _ = O.select_topk(rays_o, rays_d, pts, 20)
+    got = _run(rays_o, rays_d, pts, 20, cull="grid")
+    assert torch.equal(got.long(), want)
+
+
+def test_grid_kernel_matches_plain_scan_on_a_dense_frame():
+    """200x200 rays of the 800x800 frame against 30,000 and 100,000 points: the grid kernel and the plain scan agree on every
+    ray (the oracle cannot run this many), also with a tiny eps and K = 32."""
+    from papr_b200 import ops
+    cfg = make_config("chair")
+    for P, K, eps in ((30000, 20, 1e-6), (100000, 32, 1e-12)):
+        params = O.init_params(cfg, P, seed=P, cloud="shell")
+        rays_o, rays_d, _ = O.synthetic_rays(800, 800, cfg.dataset.coord_scale, n_views=1, seed=7, h0=250, h1=450, w0=300, w1=500)
+        a = ops.select_topk(rays_o.cuda(), rays_d.cuda(), params["points"].cuda(), K, eps, cull="grid")
+        b = ops.select_topk(rays_o.cuda(), rays_d.cuda(), params["points"].cuda(), K, eps, cull=False)
+        assert torch.equal(a, b), (P, K)

@@ -7,13 +7,14 @@ g = torch.Generator().manual_seed(0)
 pts = ((torch.rand(P, 3, generator=g) * 2 - 1) * 12).cuda()
 if os.environ.get('CLOUD') == 'shell':
     pts = torch.randn(P, 3, generator=g); pts = (pts / pts.norm(dim=-1, keepdim=True) * 8 + 0.2 * torch.randn(P, 3, generator=g)).cuda()
-CULL = {'0': False, '1': True}.get(os.environ.get('CULL', ''), None)
+CULL = {'0': False, '1': True, 'grid': 'grid'}.get(os.environ.get('CULL', ''), None)
 if os.environ.get('RAYS') == 'random':
     d = torch.randn(1, H, W, 3, generator=g); d = (d / d.norm(dim=-1, keepdim=True)).cuda()
     o = torch.tensor([[30.0, 20.0, 15.0]]).cuda()
 else:
     from papr_b200.scene import synthetic_scene
-    sc = synthetic_scene(H, W, 10.0)
+    sc = synthetic_scene(H, int(os.environ.get("WID", W)), 10.0)
+    W = int(os.environ.get("WID", W))
     d, o = sc['rays_d'].cuda(), sc['rays_o'].cuda()
 for _ in range(3):
     idx = ops.select_topk(o, d, pts, 20, cull=CULL)
