@@ -120,12 +120,17 @@ def view_grids(rays_o, rays_d, points, eps, G=None):
     dev = points.device
     if G is None:
         G = int(min(128, max(8, round((P / 8.0) ** 0.5))))
+    # (no torch.tensor(python data, device=...) in here: a pageable host-to-device copy synchronises the stream and would
+    # stop the host from running ahead of the GPU)
     dn = rays_d / rays_d.norm(dim=-1, keepdim=True).clamp_min(1e-30)
     c = dn.mean(1)
-    c = torch.where(c.norm(dim=-1, keepdim=True) > 1e-6, c, torch.tensor([0.0, 0.0, 1.0], device=dev).expand(N, 3))
+    ax = torch.zeros((3, N, 3), device=dev)
+    ax[0, :, 0] = 1.0
+    ax[1, :, 1] = 1.0
+    ax[2, :, 2] = 1.0
+    c = torch.where(c.norm(dim=-1, keepdim=True) > 1e-6, c, ax[2])
     c = c / c.norm(dim=-1, keepdim=True)
-    helper = torch.where(c[:, :1].abs() < 0.9, torch.tensor([1.0, 0.0, 0.0], device=dev).expand(N, 3),
-                         torch.tensor([0.0, 1.0, 0.0], device=dev).expand(N, 3))
+    helper = torch.where(c[:, :1].abs() < 0.9, ax[0], ax[1])
     e1 = torch.linalg.cross(helper, c)
     e1 = e1 / e1.norm(dim=-1, keepdim=True)
     e2 = torch.linalg.cross(c, e1)
