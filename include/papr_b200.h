@@ -29,6 +29,9 @@ typedef enum papr_status {
 
 /* ABI version (bumped when a signature changes) and human-readable error text. */
 int papr_abi_version(void);
+/* PAPR_OK if `device` (-1: the current one) is an sm_100 part, PAPR_ERR_UNSUPPORTED_DEVICE otherwise; every launch on
+ * another architecture reports the same status. */
+int papr_check_device(int device);
 const char *papr_status_string(int status);
 const char *papr_last_cuda_error(void);
 

@@ -14,6 +14,7 @@ _ptr, _i64, _i32, _f32 = _c.c_void_p, _c.c_int64, _c.c_int, _c.c_float
 # name -> argtypes; must list every symbol declared in include/papr_b200.h (tests/test_abi.py checks that)
 SIGNATURES = {
     "papr_abi_version": [],
+    "papr_check_device": [_i32],
     "papr_status_string": [_i32],
     "papr_last_cuda_error": [],
     "papr_select_topk": [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i32, _f32, _ptr, _ptr],
@@ -82,6 +83,19 @@ def lib():
             fn.restype = _RESTYPE.get(name, _i32)
         _lib = handle
     return _lib
+
+
+_checked_devices = set()
+
+
+def check_device(index):
+    """Raise PaprError unless CUDA device `index` is an sm_100 part (checked once per device)."""
+    if index in _checked_devices:
+        return
+    status = lib().papr_check_device(int(index))
+    if status != 0:
+        raise PaprError(f"cuda:{index}: " + lib().papr_status_string(status).decode())
+    _checked_devices.add(index)
 
 
 def check(status, what):

@@ -11,7 +11,18 @@ void set_last_cuda_error(cudaError_t e)
 }
 }  // namespace papr
 
-extern "C" int papr_abi_version(void) { return 1; }
+extern "C" int papr_abi_version(void) { return 2; }
+
+// The library holds sm_100a code only (tcgen05 / TMEM / bulk TMA): anything else cannot run it.
+extern "C" int papr_check_device(int device)
+{
+    int dev = device;
+    if (dev < 0) PAPR_CUDA_TRY(cudaGetDevice(&dev));
+    int major = 0, minor = 0;
+    PAPR_CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    PAPR_CUDA_TRY(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+    return (major == 10 && minor == 0) ? PAPR_OK : PAPR_ERR_UNSUPPORTED_DEVICE;
+}
 
 extern "C" const char *papr_last_cuda_error(void) { return papr::g_last_error; }
 

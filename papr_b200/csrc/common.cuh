@@ -12,6 +12,7 @@ void set_last_cuda_error(cudaError_t e);
 inline int check_launch()
 {
     cudaError_t e = cudaGetLastError();
+    if (e == cudaErrorNoKernelImageForDevice || e == cudaErrorInvalidDeviceFunction) { set_last_cuda_error(e); return PAPR_ERR_UNSUPPORTED_DEVICE; }
     if (e != cudaSuccess) { set_last_cuda_error(e); return PAPR_ERR_CUDA; }
     return PAPR_OK;
 }

@@ -19,7 +19,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from . import ops
+from . import _lib, ops
 from .attention import ProximityAttention
 from .bookkeeping import add_points_knn
 from .nn import MappingMLP, make_activation
@@ -292,6 +292,7 @@ class PAPR(nn.Module):
     def _attend(self, rays_o, rays_d, c2w, step):
         if not rays_d.is_cuda:
             raise RuntimeError("papr_b200 needs CUDA tensors: there is no CPU path (and no fallback)")
+        _lib.check_device(rays_d.device.index if rays_d.device.index is not None else torch.cuda.current_device())
         with torch.cuda.device(rays_d.device):      # the C ABI launches on the current device
             idx = self._get_points(rays_o, rays_d, c2w, step)
         feats = self.pc_feats if self.use_pc_feats else None

@@ -71,9 +71,10 @@ class SmallUNet(nn.Module):
 
     @staticmethod
     def _film(x, gamma, beta):
+        """x * gamma + beta per channel (unet.py:213-247); gamma / beta (C,) or one pair per image (B, C)."""
         C = x.shape[1]
-        assert gamma.shape == (C,) and beta.shape == (C,)
-        return x * gamma.reshape(1, C, 1, 1).to(x.dtype) + beta.reshape(1, C, 1, 1).to(x.dtype)
+        assert gamma.shape[-1] == C and beta.shape[-1] == C and gamma.dim() in (1, 2)
+        return x * gamma.reshape(-1, C, 1, 1).to(x.dtype) + beta.reshape(-1, C, 1, 1).to(x.dtype)
 
     def forward(self, x, log=False, gamma=None, beta=None):
         if self.affine_layer >= 0:

@@ -167,3 +167,46 @@ def test_fullsize_rgb_and_gradients_fp32_tile(frame, tile_truth):
         e = rel_err(got, want)
         print(f"   {attr}: max-abs/max vs reference fp32 {e:.3e}")
         assert e <= 5e-3, (attr, e)
+
+
+# ----------------------------------------------------------------------------- configs[3]: Caterpillar shape
+def test_caterpillar_shape_select_exact_and_chunked_training_equals_unchunked():
+    """BASELINE configs[3] shape (1920x1080 frame, P=100,000 points, L=4, coord_scale 30; configs/t2/Caterpillar.yml:2-22):
+    the grid selection over the whole frame is bit-exact against the C oracle on sampled rays, and training a crop of the
+    frame in checkpointed ray chunks gives the unchunked result (outputs equal, gradients up to atomics reordering)."""
+    from papr_b200.model import PAPR
+    from papr_b200 import ops
+    cfg = make_config("caterpillar", use_amp=False)
+    P = 100000
+    cfg.geoms.points["init_num"] = P
+    params = O.init_params(cfg, P, seed=8, cloud="shell")
+    rays_o, rays_d, c2w = O.synthetic_rays(1080, 1920, cfg.dataset.coord_scale, n_views=1, seed=3)
+    idx = ops.select_topk(rays_o.cuda(), rays_d.cuda(), params["points"].cuda(), 20)
+    pick = torch.randint(0, 1080 * 1920, (1500,), generator=torch.Generator().manual_seed(4))
+    want, _ = O.select_topk(rays_o, rays_d.reshape(-1, 3)[pick].reshape(1, 1, -1, 3), params["points"], 20)
+    assert torch.equal(idx.reshape(-1, 20)[pick.cuda()].cpu().long(), want.reshape(-1, 20))
+    model = PAPR(cfg, device="cuda", precision="bf16").cuda()
+    model.load_my_state_dict({k: v.clone() for k, v in params.items()})
+    assert model.proximity_attn.L == 4 and model.proximity_attn.dk == 81 and model.proximity_attn.dv == 118
+    crop = rays_d[:, 400:580, 800:1120].contiguous().cuda()          # 180 x 320 rays
+    tgt = torch.rand(1, 180, 320, 3, generator=torch.Generator().manual_seed(6)).cuda()
+
+    def run(chunk):
+        model.ray_chunk = chunk
+        model.clear_grad()
+        out = model(rays_o.cuda(), crop, None)
+        torch.mean((out - tgt) ** 2).backward()
+        return out.detach().clone(), {k: getattr(model, k).grad.detach().clone() for k in ("points", "pc_feats", "points_influ_scores")}
+
+    out_a, g_a = run(10 ** 9)
+    out_b, g_b = run(12800)            # 5 chunks, ragged last one
+    assert float((out_a - out_b).abs().max()) < 1e-5
+    for k in g_a:
+        assert float((g_a[k] - g_b[k]).abs().max()) <= 2e-2 * float(g_a[k].abs().max()), k
+    # against the oracle on a small tile of the crop (features are what the L=4 row kernels produce)
+    tile = rays_d[:, 480:496, 900:924].contiguous()
+    with torch.no_grad():
+        f, a = model.evaluate(rays_o.cuda(), tile.cuda(), None)
+        w = O.attention_features(params, cfg, rays_o, tile, idx=model.select_k_ind.cpu())
+    assert float((a.squeeze(-1).cpu() - w["attn"]).abs().max()) <= 7e-3
+    assert float((f.squeeze(-2).cpu() - w["fused"]).abs().max()) <= 1.5e-2 * float(w["fused"].abs().max())

@@ -23,7 +23,7 @@ def test_abi_library_exports_every_declared_symbol(built_library):
         assert hasattr(handle, name), f"{name} declared in include/papr_b200.h but not exported"
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     lib = _lib.lib()
-    assert lib.papr_abi_version() == 1
+    assert lib.papr_abi_version() == 2
     assert lib.papr_status_string(-1) == b"invalid argument"
 
 

@@ -169,9 +169,9 @@ def test_against_oracle_medium(precision):
         assert e_attn <= 7e-3 and e_fused <= 1.5e-2 and e_rgb <= 9e-3
 
 
-@pytest.mark.parametrize("K,P", [(1, 50), (31, 200), (20, 21)])
+@pytest.mark.parametrize("K,P", [(1, 50), (31, 200), (32, 300), (20, 21)])
 def test_edge_candidate_counts(K, P):
-    """select_k extremes the kernels accept (1 <= K <= 31 in the blend; P barely above K) against the oracle."""
+    """select_k extremes the kernels accept (1 <= K <= 32; P barely above K) against the oracle."""
     from tests.parity import golden_config
     cfg = golden_config("chair")
     cfg.geoms.points["select_k"] = K
@@ -201,3 +201,25 @@ def test_all_points_bypass_when_k_exceeds_cloud():
     assert attn.shape[-2] == 13 and model.select_k_ind.shape[-1] == 12
     assert float((attn.squeeze(-1).cpu() - want["attn"]).abs().max()) <= 1e-5
     assert rel_err(fused.squeeze(-2).cpu(), want["fused"]) <= 1e-5
+
+
+def test_k32_gradients_match_oracle_autograd():
+    """K = 32 uses every lane of the blend kernels' warp (the background token is a warp-uniform scalar): forward and the
+    influence / feature / point gradients against the CPU oracle's autograd, parity mode."""
+    from tests.parity import golden_config
+    cfg = golden_config("chair")
+    cfg.geoms.points["select_k"] = 32
+    params = O.init_params(cfg, 400, seed=11, cloud="shell")
+    rays_o, rays_d, c2w = O.synthetic_rays(64, 64, cfg.dataset.coord_scale, n_views=1, seed=3, h0=24, h1=36, w0=20, w1=36)
+    tgt = torch.rand(1, 12, 16, 3, generator=torch.Generator().manual_seed(2))
+    model = _build(cfg, params, "fp32")
+    model.clear_grad()
+    rgb = model(rays_o.cuda(), rays_d.cuda(), c2w.cuda())
+    torch.mean((rgb - tgt.cuda()) ** 2).backward()
+    pg = {k: v.clone().requires_grad_(v.dtype.is_floating_point and k != "bkg_feats") for k, v in params.items()}
+    want = O.forward(pg, cfg, rays_o, rays_d, idx=model.select_k_ind.cpu())
+    torch.mean((want["rgb"] - tgt) ** 2).backward()
+    assert float((rgb.detach().cpu() - want["rgb"].detach()).abs().max()) <= 1e-4
+    for key in ("points", "points_influ_scores", "pc_feats"):
+        e = rel_err(getattr(model, key).grad.cpu(), pg[key].grad)
+        assert e <= 5e-3, (key, e)

@@ -12,18 +12,23 @@ from papr_b200 import attention as A
 pytestmark = pytest.mark.gpu
 
 
-def _case(R=301, K=20, P=700, views=1, seed=0):
+SHAPES = [(6, 64), (4, 64), (6, 128), (4, 128)]      # (PE order, feature width): nerfsyn / Tanks&Temples x default / materials.yml
+
+
+def _case(R=301, K=20, P=700, views=1, seed=0, L=6, F=64):
     g = torch.Generator(device="cuda").manual_seed(seed)
     dev = "cuda"
-    sh = types.SimpleNamespace(R=R, rays_per_view=R // views, K=K, M=R * K, L=6, F=64, dk=117, dv=142,
-                               dk_pad=128, dv_pad=192, eps=1e-6)
+    S = 1 + 2 * L
+    dk, dv = 9 * S, 6 * S + F
+    sh = types.SimpleNamespace(R=R, rays_per_view=R // views, K=K, M=R * K, L=L, F=F, dk=dk, dv=dv,
+                               dk_pad=ops.pad_cols(dk), dv_pad=ops.pad_cols(dv), eps=1e-6)
     rays_o = torch.randn(views, 3, device=dev, generator=g) * 3
     rays_d = torch.nn.functional.normalize(torch.randn(R, 3, device=dev, generator=g), dim=-1)
     points = torch.randn(P, 3, device=dev, generator=g)
-    feats = torch.randn(P, 64, device=dev, generator=g)
+    feats = torch.randn(P, F, device=dev, generator=g)
     idx = torch.randint(0, P, (R, K), device=dev, generator=g, dtype=torch.int32)
-    ln_a = 1 + 0.1 * torch.randn(117, device=dev, generator=g)
-    ln_b = 0.1 * torch.randn(117, device=dev, generator=g)
+    ln_a = 1 + 0.1 * torch.randn(dk, device=dev, generator=g)
+    ln_b = 0.1 * torch.randn(dk, device=dev, generator=g)
     return sh, rays_o, rays_d, points, feats, idx, ln_a, ln_b
 
 
@@ -36,9 +41,10 @@ def _with_env(flag, fn):
         os.environ.pop("PAPR_PROLOGUE_HALFWARP", None)
 
 
+@pytest.mark.parametrize("L,F", SHAPES)
 @pytest.mark.parametrize("R,views", [(301, 1), (96, 2), (5, 1)])
-def test_prologue_forward_families_agree(R, views):
-    sh, rays_o, rays_d, points, feats, idx, ln_a, ln_b = _case(R=R, views=views)
+def test_prologue_forward_families_agree(R, views, L, F):
+    sh, rays_o, rays_d, points, feats, idx, ln_a, ln_b = _case(R=R, views=views, L=L, F=F)
     _, _, k32, v32 = A._prologue_fwd(sh, rays_o, rays_d, points, feats, idx, ln_a, ln_b, taps=True)
     outs = {}
     for name, flag in (("halfwarp", True), ("rows", False)):
@@ -55,12 +61,14 @@ def test_prologue_forward_families_agree(R, views):
     # the two bf16 kernels differ only where a value sits on a rounding boundary
     dk = (outs["rows"][0] - outs["halfwarp"][0]).abs()
     assert float((dk > 0).float().mean()) < 0.02 and float((dk - 8e-3 * outs["rows"][0].abs()).max()) <= 1e-6
-    assert torch.equal(outs["rows"][1][:, 78:], outs["halfwarp"][1][:, 78:])       # gathered point features: copies
+    dpe = 6 * (1 + 2 * L)
+    assert torch.equal(outs["rows"][1][:, dpe:], outs["halfwarp"][1][:, dpe:])       # gathered point features: copies
 
 
+@pytest.mark.parametrize("L,F", SHAPES)
 @pytest.mark.parametrize("R,views", [(301, 1), (96, 2)])
-def test_prologue_backward_families_agree(R, views):
-    sh, rays_o, rays_d, points, feats, idx, ln_a, ln_b = _case(R=R, views=views, seed=1)
+def test_prologue_backward_families_agree(R, views, L, F):
+    sh, rays_o, rays_d, points, feats, idx, ln_a, ln_b = _case(R=R, views=views, seed=1, L=L, F=F)
     g = torch.Generator(device="cuda").manual_seed(5)
     dk32 = torch.randn(sh.M, sh.dk, device="cuda", generator=g)
     dv32 = torch.randn(sh.M, sh.dv, device="cuda", generator=g)
@@ -77,7 +85,7 @@ def test_prologue_backward_families_agree(R, views):
             assert float((a - b).abs().max()) <= tol * scale, (name, what, float((a - b).abs().max()), scale)
 
 
-@pytest.mark.parametrize("R,K,relu", [(301, 20, True), (77, 16, False), (40, 31, True)])
+@pytest.mark.parametrize("R,K,relu", [(301, 20, True), (77, 16, False), (40, 31, True), (33, 32, True)])
 def test_score_rows_kernel_matches_warp_per_ray(R, K, relu):
     """Raw scores / LayerNorm statistics by the row-per-lane kernel against the warp-per-ray kernel (same bf16 h5) and
     against a float64 evaluation of ua . LN(h5) + c' (attn.py:39-42, 212-226 after the key-head fold)."""

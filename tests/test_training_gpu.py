@@ -174,3 +174,44 @@ def test_inference_keeps_no_backward_stash():
     p_inf, p_trn = peak(infer), peak(train_fwd)
     print(f"bytes/row: inference {p_inf / rows:.0f}, training {p_trn / rows:.0f}")
     assert p_inf / rows < 2600 and p_inf < 0.5 * p_trn
+
+
+def test_exposure_resampling_and_render_outputs_match_reference_procedure():
+    """one whole-frame evaluate + one batched decode picks the same shading code as the reference's loop
+    (tiled evaluate, one UNet pass per code: utils.py:406-494); depth / foreground / mask follow test.py:86-126."""
+    from papr_b200 import exposure
+    from papr_b200.model import PAPR
+    from papr_b200.scene import learned_like_cloud, synthetic_scene
+    torch.manual_seed(3)
+    cfg = make_config("caterpillar_exposure", geoms=dict(points=dict(init_num=1500)), exposure_control=dict(shading_code_num_samples=6))
+    model = PAPR(cfg, device="cuda").cuda()
+    cloud = learned_like_cloud(1500, cfg.dataset.coord_scale, seed=1)
+    with torch.no_grad():
+        model.points.copy_(cloud["points"]); model.pc_feats.copy_(cloud["pc_feats"]); model.points_influ_scores.copy_(cloud["points_influ_scores"])
+    b = {k: v.cuda() for k, v in synthetic_scene(36, 48, cfg.dataset.coord_scale, n_views=1, seed=2).items()}
+    codes_table = torch.zeros(3, 128, device="cuda")
+    torch.manual_seed(11)
+    best, losses, psnrs, codes = exposure.resample_shading_codes(codes_table, model, 1, b["rays_o"], b["rays_d"], b["target"])
+    assert torch.equal(codes_table[1], codes[best]) and losses.shape == (6,)
+    # the reference procedure: tiled evaluate, then one decode per code
+    with torch.no_grad():
+        fmap = torch.zeros(1, 36, 48, 1, 32, device="cuda"); attn = torch.zeros(1, 36, 48, 21, 1, device="cuda")
+        for h0 in range(0, 36, 20):
+            for w0 in range(0, 48, 20):
+                fmap[:, h0:h0 + 20, w0:w0 + 20], attn[:, h0:h0 + 20, w0:w0 + 20] = model.evaluate(b["rays_o"], b["rays_d"][:, h0:h0 + 20, w0:w0 + 20], b["c2w"])
+        ref_psnr = []
+        for i in range(6):
+            aff = model.mapping_mlp(codes[i])
+            fg = model.renderer(fmap.squeeze(-2).permute(0, 3, 1, 2), gamma=aff[:32], beta=aff[32:]).permute(0, 2, 3, 1)
+            rgb = fg * (1 - attn[..., 20, :]) + model.bkg_feats.reshape(1, 1, 1, -1) * attn[..., 20, :]
+            ref_psnr.append(-10.0 * np.log(((rgb - b["target"]) ** 2).mean().item()) / np.log(10.0))
+    assert int(np.argmax(ref_psnr)) == best
+    assert np.allclose(np.array(ref_psnr), psnrs.cpu().numpy(), atol=2e-2)
+    out = exposure.render_outputs(model, b["rays_o"], b["rays_d"], b["c2w"], shading_code=codes[best])
+    assert out["rgb"].shape == (1, 36, 48, 3) and out["depth"].shape == (1, 36, 48) and out["bkg_mask"].shape == (1, 36, 48)
+    sel = model.selected_points
+    od = -b["rays_o"][0]
+    dist = ((sel * od).sum(-1) - (od * b["rays_o"][0]).sum()).abs() / od.norm()
+    want_depth = (out["attn"].squeeze(-1)[..., :20] * dist).sum(-1)
+    assert torch.allclose(out["depth"], want_depth, rtol=1e-5, atol=1e-5) and float(out["depth"].min()) >= 0
+    assert float((out["bkg_mask"] - out["attn"][..., 20, 0]).abs().max()) == 0
