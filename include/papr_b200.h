@@ -282,6 +282,77 @@ int papr_prune_compact(const float *points, const float *influ, const float *fea
 int papr_generate_rays(const float *c2w, int64_t n_views, int H, int W, float focal_x, float focal_y, int h0, int w0, int h,
                        int w, float coord_scale, float *rays_o, float *rays_d, void *stream);
 
+/*
+ * Stage a10 -- the SmallUNet decode (reference models/unet.py:196-258, built by models/renderer.py:21-34) on the library's
+ * own tensor-core kernels instead of cuDNN.
+ *
+ * "Pixel planes": a feature map of one image is a zero-padded raster (padded width Wp, a multiple of 8; pixel (y,x) ->
+ * raster index (y+1)*Wp + (x+1); row0 guard rows of zeros before and after); every block of 64 channels is a plane of
+ * 128-byte rows (64 bf16), chunks XOR-swizzled by (row & 7), so any 128 rows that start at a multiple of 8 are a
+ * tcgen05.mma operand tile fetched by one 1-D TMA bulk copy.  Maps that feed a 3x3 convolution are stored three times,
+ * shifted by dx = -1, 0, +1 (copy_dx[p] = X[p + dx], copy_bytes apart), so that all nine taps are row offsets that keep
+ * the swizzle phase.  papr_raster describes one map; planes of a copy are plane_bytes apart.
+ */
+typedef struct papr_raster {
+    int32_t H, W, Wp, _pad;
+    int64_t row0;          /* guard rows before pixel 0 (>= Wp + 1) */
+    int64_t plane_bytes;   /* bytes of one 64-channel plane (rows * 128) */
+    int64_t copy_bytes;    /* distance between the dx copies (0 for single-copy maps) */
+} papr_raster;
+
+/*
+ * Convolution as implicit GEMM (unet.py:14-26 Conv2d 3x3 padding 1, :171-179 1x1; their data gradients with sign = -1 and
+ * the weight image packed as W'[ci][tap*Cout + co]): for each tile of 128 raster rows
+ *     Y[p, n] = act( sum_{tap, cb} in(copy dx(tap), plane cb, row p + sign*dy(tap)*Wp) . w_image[tap*cbs + cb][n] + bias[n] )
+ * in_planes points at plane 0 of copy dx = -1 (ntaps = 9) or of the only copy (ntaps = 1); w_image holds ntaps*cbs blocks of
+ * N x 128 B (papr_pack_weight_batch layout over K = ntaps*cbs*64).  Output: unshifted planes (out_planes, ceil(N/64) of
+ * them, written as whole 128-row tiles INCLUDING padding rows -- papr_unet_spread re-establishes the zero border) and / or
+ * fp32 rows out_f32[tile*128 + r][ld_f32].  32 <= N <= 256, N % 32 == 0.
+ */
+int papr_conv_bf16(const void *in_planes, int64_t in_copy_bytes, int64_t in_plane_bytes, int64_t in_row0, int cbs, int ntaps,
+                   int Wp, int sign, const void *w_image, const float *bias, int N, int act, float slope, void *out_planes,
+                   int64_t out_plane_bytes, int64_t out_row0, float *out_f32, int64_t ld_f32, int64_t n_tiles, void *stream);
+/*
+ * Weight gradient of one convolution tap (autograd of the same lines): C[a][b] += sum_rows A[row][a] * B[row][b] over `rows`
+ * raster rows (multiple of 64), A = d output (unshifted planes, a_valid <= 256 channels, ceil(a_valid/128)*2 planes present),
+ * B = the layer input: the caller passes the dx copy of the tap with its pointer advanced by dy*Wp rows.
+ */
+int papr_conv_wgrad_bf16(const void *a_planes, int64_t a_plane_bytes, int a_valid, const void *b_planes, int64_t b_plane_bytes,
+                         int b_valid, float *c, int64_t ldc, int64_t rows, void *stream);
+
+/* fp32 (H,W,C) rows of ld_pix floats [FiLM x*gamma+beta, unet.py:213-217] -> planes (1 or 3 copies, cbs planes each). */
+int papr_unet_pack_input(const float *src, int64_t ld_pix, int C, const float *gamma, const float *beta, void *dst_planes,
+                         const papr_raster *geom, int ncopies, int cbs, void *stream);
+/* planes (unshifted copy) -> fp32 (H,W,C). */
+int papr_unet_unpack(const void *src_planes, const papr_raster *geom, int cbs, float *dst, int64_t ld_pix, int C, void *stream);
+/*
+ * Between two convolutions: dst(interior) = film( relu_mask( src + add + maxpool_backward(pool_grad) ) ), 1 or 3 shifted
+ * copies, optional per-channel sums of what was stored (bias gradients).  All sources are unshifted planes on `geom`;
+ * pool_grad lives on pool_geom (half resolution) and pool_ref is the map that was pooled (unet.py:45-53 MaxPool2d(2):
+ * the gradient goes to the first maximum of each 2x2 window).
+ */
+typedef struct papr_spread_args {
+    const void *src, *add, *mask, *pool_grad, *pool_ref;
+    const float *gamma, *beta;
+    void *dst;
+    float *colsum;
+    papr_raster geom, pool_geom, dst_geom;
+    int32_t src_cb0, add_cb0, mask_cb0, pool_ref_cb0, dst_cb0, ncopies, cbs, _pad;
+} papr_spread_args;
+int papr_unet_spread(const papr_spread_args *args, void *stream);
+/* MaxPool2d(2) (unet.py:45-53): unshifted planes at H x W -> planes at floor(H/2) x floor(W/2). */
+int papr_unet_pool(const void *src_planes, const papr_raster *geom, int src_cb0, void *dst_planes, const papr_raster *dst_geom,
+                   int ncopies, int cbs, void *stream);
+/*
+ * ConvTranspose2d(kernel 2, stride 2) (unet.py:60-76) = a 1x1 GEMM to 4*cout channels ordered (a, b, co) followed by this
+ * pixel shuffle (+ bias, + the F.pad offset of unet.py:70-74); the gather is its inverse for the backward pass (colsum: the
+ * bias gradient).
+ */
+int papr_unet_convt_scatter(const void *src_planes, const papr_raster *low, int cout, const float *bias, void *dst_planes,
+                            const papr_raster *high, int dst_cb0, int ncopies, int pad_y, int pad_x, void *stream);
+int papr_unet_convt_gather(const void *src_planes, const papr_raster *high, int src_cb0, int cout, void *dst_planes,
+                           const papr_raster *low, int pad_y, int pad_x, float *colsum, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -37,6 +37,14 @@ SIGNATURES = {
     "papr_pack_weight_batch": [_ptr, _i32, _ptr],
     "papr_knn": [_ptr, _i64, _ptr, _i64, _i32, _ptr, _ptr, _ptr],
     "papr_prune_compact": [_ptr, _ptr, _ptr, _i64, _i32, _f32, _i32, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
+    "papr_conv_bf16": [_ptr, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _ptr, _ptr, _i32, _i32, _f32, _ptr, _i64, _i64, _ptr, _i64, _i64, _ptr],
+    "papr_conv_wgrad_bf16": [_ptr, _i64, _i32, _ptr, _i64, _i32, _ptr, _i64, _i64, _ptr],
+    "papr_unet_pack_input": [_ptr, _i64, _i32, _ptr, _ptr, _ptr, _ptr, _i32, _i32, _ptr],
+    "papr_unet_unpack": [_ptr, _ptr, _i32, _ptr, _i64, _i32, _ptr],
+    "papr_unet_spread": [_ptr, _ptr],
+    "papr_unet_pool": [_ptr, _ptr, _i32, _ptr, _ptr, _i32, _i32, _ptr],
+    "papr_unet_convt_scatter": [_ptr, _ptr, _i32, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _ptr],
+    "papr_unet_convt_gather": [_ptr, _ptr, _i32, _i32, _ptr, _ptr, _i32, _i32, _ptr, _ptr],
     "papr_generate_rays": [_ptr, _i64, _i32, _i32, _f32, _f32, _i32, _i32, _i32, _i32, _f32, _ptr, _ptr, _ptr],
 }
 _RESTYPE = {"papr_status_string": _c.c_char_p, "papr_last_cuda_error": _c.c_char_p}
@@ -60,6 +68,21 @@ class PackDesc(ctypes.Structure):
     _fields_ = [("w", _ptr), ("ld", _i64), ("rows", ctypes.c_int32), ("cols", ctypes.c_int32), ("transpose", ctypes.c_int32),
                 ("N", ctypes.c_int32), ("K", ctypes.c_int32), ("replicas", ctypes.c_int32), ("scale", _f32),
                 ("_pad", ctypes.c_int32), ("rep_stride", _i64), ("image", _ptr)]
+
+
+class Raster(ctypes.Structure):
+    """papr_raster of include/papr_b200.h"""
+    _fields_ = [("H", ctypes.c_int32), ("W", ctypes.c_int32), ("Wp", ctypes.c_int32), ("_pad", ctypes.c_int32),
+                ("row0", _i64), ("plane_bytes", _i64), ("copy_bytes", _i64)]
+
+
+class SpreadArgs(ctypes.Structure):
+    """papr_spread_args of include/papr_b200.h"""
+    _fields_ = [("src", _ptr), ("add", _ptr), ("mask", _ptr), ("pool_grad", _ptr), ("pool_ref", _ptr), ("gamma", _ptr),
+                ("beta", _ptr), ("dst", _ptr), ("colsum", _ptr), ("geom", Raster), ("pool_geom", Raster), ("dst_geom", Raster),
+                ("src_cb0", ctypes.c_int32), ("add_cb0", ctypes.c_int32), ("mask_cb0", ctypes.c_int32),
+                ("pool_ref_cb0", ctypes.c_int32), ("dst_cb0", ctypes.c_int32), ("ncopies", ctypes.c_int32),
+                ("cbs", ctypes.c_int32), ("_pad", ctypes.c_int32)]
 
 
 class PaprError(RuntimeError):

@@ -186,6 +186,10 @@ class PAPR(nn.Module):
     def clear_grad(self):
         if self._flat is not None:
             self._flat.zero_grad()          # one memset; .grad tensors stay views of the flat bucket
+            covered = {id(q) for q in self._flat.params}
+            for q in self.parameters():     # parameters replaced behind the optimisers' back (load / prune / add without re-init)
+                if id(q) not in covered and q.grad is not None:
+                    q.grad = None
             return
         for optimizer in self.optimizers.values():
             if optimizer is not None:
@@ -383,6 +387,10 @@ class PAPR(nn.Module):
             self.pc_feats = nn.Parameter(state_dict["pc_feats"].data.to(dev), requires_grad=self.pc_feats.requires_grad)
         self._select_k = int(self.select_k)      # the buffer may just have been overwritten (e.g. a K=30 checkpoint)
         self._idx32 = None
+        # the point tables are NEW Parameter objects now: optimisers that have not been stepped yet are rebuilt around them
+        # (the reference leaves its optimisers pointing at the old tensors until train.py re-creates them)
+        if getattr(self, "optimizers", None) is not None and not getattr(self, "_opt_stepped", True):
+            self.init_optimizers(self._opt_total_steps)
 
 
 def get_model(args, device="cuda", **kw):

@@ -1,9 +1,11 @@
 """Decode stage a10: the reference's SmallUNet (models/unet.py:182-258, built by models/renderer.py:21-34).
 
 Same module tree as the reference so checkpoints interchange (renderer.inc.double_conv.0.*, renderer.down{1,2}.
-maxpool_conv.1.double_conv.0.*, renderer.up{1,2}.{up,conv.double_conv.0}.*, renderer.outc.conv.*).  The convolutions run
-through cuDNN in bf16/channels_last (5% of the path's FLOPs); only the shipped variant
-(single conv blocks, transposed-conv upsampling, no normalisation) is implemented.
+maxpool_conv.1.double_conv.0.*, renderer.up{1,2}.{up,conv.double_conv.0}.*, renderer.outc.conv.*); the modules below only
+OWN the parameters.  On the product path (CUDA, bf16) the forward and backward run on the library's implicit-GEMM tcgen05
+convolution kernels (papr_b200/unet.py, csrc/conv.cu, csrc/unet_raster.cu) -- no cuDNN.  The torch modules are executed
+only in the fp32 parity mode and for FiLM at an inner stage (affine_layer 1..5, which no shipped config uses).  Only the
+shipped variant (single conv blocks, transposed-conv upsampling, no normalisation) exists.
 """
 import torch
 import torch.nn as nn
@@ -61,6 +63,7 @@ class SmallUNet(nn.Module):
             raise NotImplementedError("only the shipped SmallUNet variant (single=True, bilinear=False, norm='none')")
         self.affine_layer = affine_layer
         self.compute_dtype = compute_dtype
+        self.own_kernels = True         # False: cuDNN through torch (kept for A/B measurements in tools/, never the default)
         self.inc = ConvBlock(n_channels, 128)
         self.down1 = Down(128, 256)
         self.down2 = Down(256, 512)
@@ -79,6 +82,14 @@ class SmallUNet(nn.Module):
     def forward(self, x, log=False, gamma=None, beta=None):
         if self.affine_layer >= 0:
             assert gamma is not None and beta is not None
+        if x.is_cuda and self.compute_dtype != torch.float32 and self.affine_layer in (-1, 0) and self.own_kernels:
+            from . import unet as U
+            g = b = None
+            if self.affine_layer == 0:
+                C = x.shape[1]
+                g, b = gamma.reshape(-1, C).float(), beta.reshape(-1, C).float()
+            out = U.UNetFn.apply(x, g, b, torch.is_grad_enabled(), *U.parameter_list(self))
+            return self.last_act(out)
         amp = x.is_cuda and self.compute_dtype != torch.float32
         with torch.autocast(device_type="cuda", dtype=self.compute_dtype, enabled=amp):
             if amp:

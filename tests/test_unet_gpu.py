@@ -1,0 +1,102 @@
+"""GPU: the SmallUNet decode on the library's own kernels (stage a10, reference models/unet.py:196-258) against the CPU
+oracle's restatement (oracle.papr_oracle.unet, fp32 torch ops): forward, input gradient and every parameter gradient,
+even / odd / tiny image sizes, with and without the exposure FiLM, batches of images."""
+import pytest
+import torch
+
+from oracle import papr_oracle as O
+from papr_b200.config import make_config
+
+pytestmark = pytest.mark.gpu
+
+
+def _unet(affine_layer=-1, seed=0):
+    from papr_b200.renderer import SmallUNet
+    torch.manual_seed(seed)
+    m = SmallUNet(32, 3, affine_layer=affine_layer).cuda()
+    with torch.no_grad():
+        for p in m.parameters():                 # torch's default init is tiny for the deep layers: scale up so every layer matters
+            if p.dim() == 1:
+                p.uniform_(-0.1, 0.1)
+    return m
+
+
+def _oracle_params(m):
+    return {"renderer." + k: v.detach().cpu().float().clone() for k, v in m.state_dict().items()}
+
+
+def _rel(a, b):
+    return float((a - b).double().norm() / b.double().norm().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("H,W", [(32, 48), (37, 29), (6, 7), (160, 160), (4, 4)])
+def test_unet_forward_matches_oracle(H, W):
+    m = _unet()
+    x = torch.randn(1, 32, H, W, device="cuda")
+    with torch.no_grad():
+        got = m(x)
+        want = O.unet(_oracle_params(m), x.cpu())
+    assert got.shape == (1, 3, H, W)
+    e = float((got.cpu() - want).abs().max()) / float(want.abs().max())
+    print(f"unet fwd {H}x{W}: max-abs err / scale {e:.3e}, rel L2 {_rel(got.cpu(), want):.3e}")
+    assert e <= 3e-2 and _rel(got.cpu(), want) <= 1.5e-2
+
+
+@pytest.mark.parametrize("H,W,film,batch", [(32, 48, False, 1), (37, 29, True, 1), (24, 24, True, 3), (10, 6, False, 2)])
+def test_unet_gradients_match_oracle_autograd(H, W, film, batch):
+    m = _unet(affine_layer=0 if film else -1, seed=1)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(batch, 32, H, W, device="cuda", generator=g, requires_grad=True)
+    gamma = (1 + 0.2 * torch.randn(batch, 32, device="cuda", generator=g)).requires_grad_(True) if film else None
+    beta = (0.2 * torch.randn(batch, 32, device="cuda", generator=g)).requires_grad_(True) if film else None
+    tgt = torch.randn(batch, 3, H, W, device="cuda", generator=g)
+    out = m(x, gamma=gamma, beta=beta)
+    loss = ((out - tgt) ** 2).mean()
+    loss.backward()
+    # oracle, fp32 CPU autograd, image by image (its FiLM takes one (C,) pair)
+    P = {k: v.requires_grad_(True) for k, v in _oracle_params(m).items()}
+    xc = x.detach().cpu().requires_grad_(True)
+    gc = gamma.detach().cpu().requires_grad_(True) if film else None
+    bc = beta.detach().cpu().requires_grad_(True) if film else None
+    outs = [O.unet(P, xc[i:i + 1], gc[i] if film else None, bc[i] if film else None, 0 if film else -1) for i in range(batch)]
+    want = torch.cat(outs)
+    ((want - tgt.cpu()) ** 2).mean().backward()
+    assert _rel(out.detach().cpu(), want.detach()) <= 1.5e-2
+    checks = [("x", x.grad.cpu(), xc.grad)]
+    if film:
+        checks += [("gamma", gamma.grad.cpu(), gc.grad), ("beta", beta.grad.cpu(), bc.grad)]
+    for name, p in m.named_parameters():
+        checks.append((name, p.grad.cpu(), P["renderer." + name].grad))
+    for name, a, b in checks:
+        assert a.shape == b.shape, name
+        r = _rel(a, b)
+        cos = float(torch.nn.functional.cosine_similarity(a.flatten().double(), b.flatten().double(), dim=0))
+        print(f"   {name}: rel L2 {r:.3e} cosine {cos:.5f}")
+        assert r <= 6e-2 and cos >= 0.998, (name, r, cos)
+
+
+def test_unet_through_the_model_no_library_convolution(monkeypatch):
+    """The product path must not touch torch's convolution: PAPR.forward + backward with conv2d / conv_transpose2d poisoned."""
+    from papr_b200.model import PAPR
+    from papr_b200.scene import learned_like_cloud, synthetic_scene
+    import torch.nn.functional as F
+    cfg = make_config("chair", geoms=dict(points=dict(init_num=1500)))
+    model = PAPR(cfg, device="cuda").cuda()
+    cloud = learned_like_cloud(1500, cfg.dataset.coord_scale, seed=1)
+    with torch.no_grad():
+        model.points.copy_(cloud["points"]); model.pc_feats.copy_(cloud["pc_feats"]); model.points_influ_scores.copy_(cloud["points_influ_scores"])
+    b = {k: v.cuda() for k, v in synthetic_scene(40, 56, cfg.dataset.coord_scale, n_views=2, seed=1).items()}
+
+    def boom(*a, **k):
+        raise AssertionError("a library convolution ran on the product path")
+    monkeypatch.setattr(F, "conv2d", boom)
+    monkeypatch.setattr(F, "conv_transpose2d", boom)
+    monkeypatch.setattr(torch, "conv2d", boom)
+    monkeypatch.setattr(torch.nn.Conv2d, "forward", boom)
+    monkeypatch.setattr(torch.nn.ConvTranspose2d, "forward", boom)
+    model.clear_grad()
+    out = model(b["rays_o"], b["rays_d"], b["c2w"])
+    ((out - b["target"]) ** 2).mean().backward()
+    assert out.shape == (2, 40, 56, 3) and torch.isfinite(out).all()
+    for n, p in model.renderer.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all() and float(p.grad.abs().max()) > 0, n
