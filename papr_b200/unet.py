@@ -230,7 +230,6 @@ def unet_forward_image(x_hwc, p, W, gamma, beta, keep):
     _conv(U2, U2.ptr(), 4, 9, 1, W.fwd["up2c"], p["up2c.b"], True, Y2)
     out = torch.empty((Y2.L, 32), dtype=torch.float32, device=dev)
     _conv(Y2, Y2.ptr(), 2, 1, 1, W.fwd["outc"], p["outc.b"], False, None, out_f32=out)
-    rgb = out.view(H + 2 + (Y2.L - (H + 2) * Y2.Wp) // Y2.Wp if False else -1, 32) if False else out
     rgb = out[: (H + 2) * Y2.Wp].view(H + 2, Y2.Wp, 32)[1:H + 1, 1:Wd + 1, :3]
     saved = (P0, U2, P1, U1, P2, X3, Y1, Y2) if keep else None
     return rgb, saved
