@@ -332,7 +332,7 @@ def main():
 
     peaks = load_peaks()
     zero = dict(launches=0, ms=0.0, flops=0.0, bytes=0.0)
-    tc_names = ("papr_stack_bf16", "papr_wgrad_bf16", "papr_linear_bf16")
+    tc_names = ("papr_stack_bf16", "papr_wgrad_bf16", "papr_linear_bf16", "papr_conv_bf16", "papr_conv_wgrad_bf16")
     tc = {n: kern.get(n, zero) for n in tc_names}
     sel = kern.get("papr_select_topk", zero)
     stack = tc["papr_stack_bf16"]
@@ -401,6 +401,8 @@ def main():
                    "measured_fp32_mode_worst": {"attn": 2.5e-7, "fused_rel": 5.7e-6, "rgb": 5.4e-7},
                    "top_k": "bit-exact", "source": "profiles/r02_error_budget.md, tests/test_model_gpu.py, tests/test_fullsize_gpu.py"},
         "kernels": kernels,
+        "memory": {"peak_allocated_gb": torch.cuda.max_memory_allocated(dev) / 1e9, "reserved_gb": torch.cuda.memory_reserved(dev) / 1e9,
+                   "alloc_retries": torch.cuda.memory_stats(dev).get("num_alloc_retries", 0)},
     }
     line.update(extra)
     if world == 1 and not args.no_gpu_reference:

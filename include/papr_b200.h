@@ -313,12 +313,15 @@ int papr_conv_bf16(const void *in_planes, int64_t in_copy_bytes, int64_t in_plan
                    int Wp, int sign, const void *w_image, const float *bias, int N, int act, float slope, void *out_planes,
                    int64_t out_plane_bytes, int64_t out_row0, float *out_f32, int64_t ld_f32, int64_t n_tiles, void *stream);
 /*
- * Weight gradient of one convolution tap (autograd of the same lines): C[a][b] += sum_rows A[row][a] * B[row][b] over `rows`
- * raster rows (multiple of 64), A = d output (unshifted planes, a_valid <= 256 channels, ceil(a_valid/128)*2 planes present),
- * B = the layer input: the caller passes the dx copy of the tap with its pointer advanced by dy*Wp rows.
+ * Weight gradient of a convolution (autograd of the same lines), all taps in one launch:
+ *     C[tap][a][b] += sum_rows A[row][a] * B(copy dx(tap))[row + dy(tap)*Wp][b]        over `rows` raster rows (multiple of 64)
+ * A = d output (unshifted planes, a_valid <= 256 channels, ceil(a_valid/128)*2 planes present), B = the layer input
+ * (b_planes: plane 0 of copy dx = -1 at raster row 0 when ntaps = 9; of the only copy when ntaps = 1), b_valid <= 256.
+ * C: fp32, leading dimension ldc, taps c_tap_stride floats apart, accumulated atomically.
  */
 int papr_conv_wgrad_bf16(const void *a_planes, int64_t a_plane_bytes, int a_valid, const void *b_planes, int64_t b_plane_bytes,
-                         int b_valid, float *c, int64_t ldc, int64_t rows, void *stream);
+                         int64_t b_copy_bytes, int b_valid, int ntaps, int Wp, float *c, int64_t ldc, int64_t c_tap_stride,
+                         int64_t rows, void *stream);
 
 /* fp32 (H,W,C) rows of ld_pix floats [FiLM x*gamma+beta, unet.py:213-217] -> planes (1 or 3 copies, cbs planes each). */
 int papr_unet_pack_input(const float *src, int64_t ld_pix, int C, const float *gamma, const float *beta, void *dst_planes,

@@ -284,6 +284,7 @@ def _pad_bias(b, N):
 
 
 FUSE_STACKS = True      # one cta_group::2 launch per MLP stack (papr_stack_bf16) instead of one launch per layer
+BWD_SLICE_ROWS = 8 << 20    # rows per backward slice of a stack (bounds the dZ stash, see _stack_backward)
 
 
 def _stack_forward_fused(x, weights, biases, slope, n_in0, save, last_f32, images=None):
@@ -359,37 +360,46 @@ def _stack_backward(dz, inputs, bits_list, weights, slope, g_bias_last, in_valid
     gWs, gbs = [None] * n_layers, [None] * n_layers
     gbs[-1] = g_bias_last
     if FUSE_STACKS and not skip_layers and n_layers <= 8 and all(w.shape[0] == 256 for w in weights[:-1]):
-        # dgrad of the whole stack in one launch; the per-layer dZ tiles it stashes feed the weight-gradient launches
+        # dgrad of the whole stack in one launch per slice of rows; the per-layer dZ tiles it stashes feed the weight-gradient
+        # launches and are dropped before the next slice starts, so at most BWD_SLICE_ROWS rows of dZ stash (512 B per row
+        # and layer) are alive next to the forward stash -- at 800x800 (two slices) that is ~130 GB of peak instead of ~155 GB.
         dev = weights[0].device
-        layers, dzs = [], [dz]
-        for i in range(n_layers - 1, -1, -1):
-            w = weights[i]
-            n_out, n_in = w.shape
-            Kd = (n_out + 15) // 16 * 16
-            Nd = n_in if i > 0 else in_pad
-            ob = ops.Blocked(dz.rows, Nd, dev)
-            img = images_t[i] if images_t is not None else ops.pack_weight(w, Nd, Kd, transpose=True, replicas=ops.WEIGHT_REPLICAS)
-            spec = dict(w_image=img, N=Nd, out_blocked=ob)
-            if i > 0:
-                gbs[i - 1] = torch.zeros((weights[i - 1].shape[0],), device=dev)
-                spec["colsum"] = gbs[i - 1]
-                if slope is not None:
-                    spec["sign_bits_in"] = bits_list[i - 1]
-            layers.append(spec)
-            dzs.append(ob)
+        rows_pad = dz.rows_pad
+        n_slices = max(1, -(-rows_pad // BWD_SLICE_ROWS))
+        per = -(-(rows_pad // 128) // n_slices) * 128
+        Nd0 = in_pad
+        d_in = ops.Blocked(dz.rows, Nd0, dev)
+        for i in range(1, n_layers):
+            gbs[i - 1] = torch.zeros((weights[i - 1].shape[0],), device=dev)
+        for i in range(n_layers):
+            gWs[i] = torch.zeros(weights[i].shape, dtype=torch.float32, device=dev)
+        imgs = [images_t[i] if images_t is not None else
+                ops.pack_weight(weights[i], weights[i].shape[1] if i > 0 else in_pad, (weights[i].shape[0] + 15) // 16 * 16,
+                                transpose=True, replicas=ops.WEIGHT_REPLICAS) for i in range(n_layers)]
         K0 = (weights[-1].shape[0] + 15) // 16 * 16
-        ops.stack_bf16(dz, K0, layers, slope=slope or 0.0)
-        for i in range(n_layers - 1, -1, -1):
-            w = weights[i]
-            n_out, n_in = w.shape
-            gW = torch.zeros(w.shape, dtype=torch.float32, device=dev)
-            dzi = dzs[n_layers - 1 - i]
-            if n_out < 128:
-                ops.wgrad_bf16(inputs[i], dzi, gW, n_in, n_out, transpose_out=True)
-            else:
-                ops.wgrad_bf16(dzi, inputs[i], gW, n_out, n_in)
-            gWs[i] = gW
-        return dzs[-1], gWs, gbs
+        for r0 in range(0, rows_pad, per):
+            r1 = min(r0 + per, rows_pad)
+            layers, dzs = [], [dz.rows_view(r0, r1)]
+            for i in range(n_layers - 1, -1, -1):
+                Nd = weights[i].shape[1] if i > 0 else in_pad
+                ob = ops.Blocked(r1 - r0, Nd, dev) if i > 0 else d_in.rows_view(r0, r1)
+                spec = dict(w_image=imgs[i], N=Nd, out_blocked=ob)
+                if i > 0:
+                    spec["colsum"] = gbs[i - 1]
+                    if slope is not None:
+                        spec["sign_bits_in"] = bits_list[i - 1][r0:r1]
+                layers.append(spec)
+                dzs.append(ob)
+            ops.stack_bf16(dzs[0], K0, layers, slope=slope or 0.0)
+            for i in range(n_layers - 1, -1, -1):
+                n_out, n_in = weights[i].shape
+                dzi, xi = dzs[n_layers - 1 - i], inputs[i].rows_view(r0, r1)
+                if n_out < 128:
+                    ops.wgrad_bf16(xi, dzi, gWs[i], n_in, n_out, transpose_out=True)
+                else:
+                    ops.wgrad_bf16(dzi, xi, gWs[i], n_out, n_in)
+            del layers, dzs
+        return d_in, gWs, gbs
     d_in_extra = None          # fp32 gradient reaching the stack input through skip connections
     for i in range(n_layers - 1, -1, -1):
         w = weights[i]

@@ -40,4 +40,10 @@ inline cudaError_t ensure_dyn_smem(SmemAttrOnce &once, Kernel kernel, int bytes)
 
 constexpr int kNumSMs = 148;   // B200
 
+// 16-byte vector reduction into global memory (sm_90+): one instruction instead of four scalar atomics
+__device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d)
+{
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 }  // namespace papr

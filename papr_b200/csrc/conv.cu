@@ -202,20 +202,21 @@ static int launch_conv(const ConvParams &p, int smem, cudaStream_t stream)
 }
 
 // --------------------------------------------------------------------------------------------------------------------
-// Weight gradient of a convolution tap: C[a, b] += sum_p A[p, a] * B[p + shift, b] with A (d output, copy 0) and B (input,
-// the dx copy of the tap, rows shifted by dy*Wp) both consumed as MN-major SWIZZLE_128B operands straight from the planes.
-// Same structure as papr_wgrad_bf16 (split over the rows of the grid, whole product in TMEM, one atomic drain); only the
-// addressing differs (planes instead of tile-blocked blocks).
+// Weight gradient of a convolution: C[tap][a, b] += sum_p A[p, a] * B[p + off(tap), b] with A (d output, unshifted copy) and
+// B (the layer input: the dx copy of the tap, rows shifted by dy*Wp) both consumed as MN-major SWIZZLE_128B operands
+// straight from the planes.  Same pipeline as papr_wgrad_bf16 (row slices streamed through a TMA ring, the whole product
+// in TMEM, one atomic drain), but a CTA owns (tap, row slice): one launch covers all nine taps.
 // --------------------------------------------------------------------------------------------------------------------
 constexpr int kCwThreads = 256;
 constexpr int kCwHalf = kBlockBytes / 2;
 
 struct ConvWgradParams {
-    const uint8_t *a, *b;      // first used plane of each operand, at row 0 of the pixel raster (+ shift for b)
-    int64_t a_plane_bytes, b_plane_bytes;
-    float *c;                  // fp32 [a_valid, ldc] (+=, atomically)
+    const uint8_t *a, *b;      // first used plane of each operand at row 0 of the pixel raster; b: copy dx = -1 when ntaps == 9
+    int64_t a_plane_bytes, b_plane_bytes, b_copy_bytes;
+    float *c;                  // fp32 [ntaps][a_valid rows, ldc] (+=, atomically), taps c_tap_stride floats apart
+    int64_t c_tap_stride;
     int64_t n_units;           // 64-row units
-    int a_halves, a_used_blk, nb_used, Nb, ldc, stages, a_valid, b_valid;
+    int a_halves, a_used_blk, nb_used, Nb, ldc, stages, a_valid, b_valid, ntaps, splits, Wp;
 };
 
 __global__ void __launch_bounds__(kCwThreads, 1) conv_wgrad_kernel(const ConvWgradParams p)
@@ -239,19 +240,26 @@ __global__ void __launch_bounds__(kCwThreads, 1) conv_wgrad_kernel(const ConvWgr
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const bool has_work = (int64_t)blockIdx.x < p.n_units;
+    // one CTA = one tap x one slice of the rows: all nine taps of a 3x3 layer run in ONE launch, and only `splits` CTAs (not
+    // the whole grid) add their partial products into a tap's gradient at the end
+    const int tap = blockIdx.x / p.splits, split = blockIdx.x - tap * p.splits;
+    const bool has_work = (int64_t)split < p.n_units;
+    int dy = 0, dx = 0;
+    if (p.ntaps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
+    const uint8_t *bsrc = p.b + (int64_t)(p.ntaps == 9 ? dx + 1 : 0) * p.b_copy_bytes + (int64_t)dy * p.Wp * 128;
+    float *cdst = p.c + (int64_t)tap * p.c_tap_stride;
 
     if (warp == 0) {
         if (lane == 0) {
             int s = 0; uint32_t ph = 0;
-            for (int64_t u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+            for (int64_t u = split; u < p.n_units; u += p.splits) {
                 const size_t off = (size_t)u * kCwHalf;
                 mbar_wait(&empty[s], ph ^ 1);
                 mbar_arrive_expect_tx(&full[s], (uint32_t)stage_bytes);
                 uint8_t *dst = ring + s * stage_bytes;
                 for (int i = 0; i < p.a_used_blk; ++i) bulk_g2s(dst + i * kCwHalf, p.a + (size_t)i * p.a_plane_bytes + off, kCwHalf, &full[s]);
                 for (int i = 0; i < p.nb_used; ++i)
-                    bulk_g2s(dst + (p.a_used_blk + i) * kCwHalf, p.b + (size_t)i * p.b_plane_bytes + off, kCwHalf, &full[s]);
+                    bulk_g2s(dst + (p.a_used_blk + i) * kCwHalf, bsrc + (size_t)i * p.b_plane_bytes + off, kCwHalf, &full[s]);
                 if (++s == p.stages) { s = 0; ph ^= 1; }
             }
         }
@@ -259,7 +267,7 @@ __global__ void __launch_bounds__(kCwThreads, 1) conv_wgrad_kernel(const ConvWgr
         if (lane == 0 && has_work) {
             const uint32_t idesc = umma_idesc(128, p.Nb, true, true);
             int s = 0; uint32_t ph = 0; uint32_t first = 1;
-            for (int64_t u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+            for (int64_t u = split; u < p.n_units; u += p.splits) {
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
                 const uint32_t a0 = smem_u32(ring + s * stage_bytes);
@@ -289,10 +297,17 @@ __global__ void __launch_bounds__(kCwThreads, 1) conv_wgrad_kernel(const ConvWgr
                 tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + h * 256 + col0, v);
                 tmem_ld_wait();
                 if (ai < p.a_valid) {
+                    float *rowp = cdst + (size_t)ai * p.ldc + col0;
+                    if (col0 + 32 <= p.b_valid && (((uintptr_t)rowp) & 15) == 0) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int bi = col0 + j;
-                        if (bi < p.b_valid) atomicAdd(p.c + (size_t)ai * p.ldc + bi, __uint_as_float(v[j]));
+                        for (int j = 0; j < 32; j += 4)
+                            red_add_v4(rowp + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int bi = col0 + j;
+                            if (bi < p.b_valid) atomicAdd(cdst + (size_t)ai * p.ldc + bi, __uint_as_float(v[j]));
+                        }
                     }
                 }
             }
@@ -333,13 +348,16 @@ extern "C" int papr_conv_bf16(const void *in_planes, int64_t in_copy_bytes, int6
 }
 
 extern "C" int papr_conv_wgrad_bf16(const void *a_planes, int64_t a_plane_bytes, int a_valid, const void *b_planes, int64_t b_plane_bytes,
-                                    int b_valid, float *c, int64_t ldc, int64_t rows, void *stream)
+                                    int64_t b_copy_bytes, int b_valid, int ntaps, int Wp, float *c, int64_t ldc, int64_t c_tap_stride,
+                                    int64_t rows, void *stream)
 {
     using namespace papr;
     if (!a_planes || !b_planes || !c) return PAPR_ERR_INVALID_ARGUMENT;
-    if (rows <= 0 || rows % 64 || a_valid < 1 || a_valid > 256 || b_valid < 1 || b_valid > 256) return PAPR_ERR_INVALID_ARGUMENT;
+    if (rows <= 0 || rows % 64 || a_valid < 1 || a_valid > 256 || b_valid < 1 || b_valid > 256 || (ntaps != 1 && ntaps != 9)) return PAPR_ERR_INVALID_ARGUMENT;
+    if (ntaps == 9 && (Wp < 8 || Wp % 8)) return PAPR_ERR_INVALID_ARGUMENT;
     ConvWgradParams p;
     p.a = (const uint8_t *)a_planes; p.b = (const uint8_t *)b_planes; p.a_plane_bytes = a_plane_bytes; p.b_plane_bytes = b_plane_bytes;
+    p.b_copy_bytes = b_copy_bytes; p.ntaps = ntaps; p.Wp = Wp; p.c_tap_stride = c_tap_stride;
     p.c = c; p.n_units = rows / 64;
     p.a_halves = (a_valid + 127) / 128;                 // M = 128 per MMA: 1 or 2 row-halves of the product
     p.a_used_blk = p.a_halves * 2;                      // the caller provides ceil(a_valid/128)*2 planes (zero padded)
@@ -352,7 +370,8 @@ extern "C" int papr_conv_wgrad_bf16(const void *a_planes, int64_t a_plane_bytes,
     const int smem = 1024 + p.stages * stage_bytes + 1024;
     static SmemAttrOnce once;
     PAPR_CUDA_TRY(ensure_dyn_smem(once, conv_wgrad_kernel, 232448));
-    const int grid = (int)(p.n_units < kNumSMs ? p.n_units : kNumSMs);
-    conv_wgrad_kernel<<<grid, kCwThreads, smem, (cudaStream_t)stream>>>(p);
+    const int64_t per_tap = kNumSMs / ntaps;                        // 16 row slices per tap for 3x3, the whole grid for 1x1
+    p.splits = (int)(p.n_units < per_tap ? p.n_units : per_tap);
+    conv_wgrad_kernel<<<p.splits * ntaps, kCwThreads, smem, (cudaStream_t)stream>>>(p);
     return check_launch();
 }

@@ -317,11 +317,6 @@ __global__ void __launch_bounds__(kRowThreads) attn_prologue_bwd_kernel(const Pr
 // the double-angle recurrence (abs. error <= 2^5 * 1 ulp ~ 4e-6, far below bf16 resolution), computed by 9 lanes and
 // shared through shared memory; LayerNorm affine terms live in registers; feature gradients use 16-byte vector
 // reductions (red.global.add.v4.f32).
-__device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d)
-{
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-
 // lanes 0..8: fill pe[src*S + slot] for geometry scalar `src` = lane
 __device__ __forceinline__ void pe_fill(float x, int L, float *dst)
 {

@@ -95,12 +95,20 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const WgradParams 
                 tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + h * 256 + col0, v);
                 tmem_ld_wait();
                 if (ai < p.a_valid) {
+                    float *rowp = p.c + (size_t)ai * p.ldc + col0;
+                    if (!p.transpose_out && col0 + 32 <= p.b_valid && (((uintptr_t)rowp) & 15) == 0) {
+                        // 32 consecutive, 16-byte aligned floats of one gradient row: eight vector reductions
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int bi = col0 + j;
-                        if (bi < p.b_valid) {
-                            float *dst = p.transpose_out ? p.c + (size_t)bi * p.ldc + ai : p.c + (size_t)ai * p.ldc + bi;
-                            atomicAdd(dst, __uint_as_float(v[j]));
+                        for (int j = 0; j < 32; j += 4)
+                            red_add_v4(rowp + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int bi = col0 + j;
+                            if (bi < p.b_valid) {
+                                float *dst = p.transpose_out ? p.c + (size_t)bi * p.ldc + ai : p.c + (size_t)ai * p.ldc + bi;
+                                atomicAdd(dst, __uint_as_float(v[j]));
+                            }
                         }
                     }
                 }

@@ -236,6 +236,14 @@ class Blocked:
         out.buf = buf
         return out
 
+    def rows_view(self, r0, r1):
+        """Rows [r0, r1) (multiples of 128) as a Blocked over the same storage: a tile is contiguous in this layout."""
+        assert r0 % 128 == 0 and (r1 % 128 == 0 or r1 == self.rows_pad) and 0 <= r0 < r1 <= self.rows_pad
+        if r0 == 0 and r1 == self.rows_pad:
+            return self
+        per_row = self.cols_pad * 2
+        return Blocked.wrap(self.buf[r0 * per_row:r1 * per_row], min(self.rows, r1) - r0 if self.rows > r0 else r1 - r0, self.cols, self.cols_pad)
+
     @staticmethod
     def from_f32(t, cols_pad=None):
         t = _f32c(t)

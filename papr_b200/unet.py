@@ -161,30 +161,30 @@ def _pool(src, src_cb0, cbs, dst):
              nbytes=src.H * src.W * cbs * 128.0 * 2)
 
 
-def _wgrad(a, a_cb0, a_valid, b, b_copy, b_cb0, b_valid, row_shift, out):
-    """out (a_valid, ldc) += sum_rows A[row, a] * B[row + row_shift, b] over the raster rows of `a`."""
-    ops.call("papr_conv_wgrad_bf16", a.mid(a_cb0) + a.G0 * 128, a.plane_bytes, a_valid,
-             b.ptr(copy=b_copy, cb=b_cb0, row=b.G0 + row_shift), b.plane_bytes, b_valid, out.data_ptr(), out.stride(0), a.L,
-             flops=2.0 * a.H * a.W * a_valid * b_valid, nbytes=a.L * 128.0 * ((a_valid + 127) // 128 * 2 + (b_valid + 63) // 64))
+def _wgrad(a, a_cb0, a_valid, b, b_cb0, b_valid, ntaps, out, tap_stride):
+    """out[tap] (a_valid, ldc) += sum_rows A[row, a] * B_tap[row, b] over the raster rows of `a` (all taps in one launch)."""
+    b_ptr = b.ptr(copy=0, cb=b_cb0, row=b.G0) if ntaps == 9 else b.mid(b_cb0) + b.G0 * 128
+    ops.call("papr_conv_wgrad_bf16", a.mid(a_cb0) + a.G0 * 128, a.plane_bytes, a_valid, b_ptr, b.plane_bytes, b.copy_bytes, b_valid,
+             ntaps, b.Wp, out.data_ptr(), out.stride(-2), tap_stride, a.L,
+             flops=2.0 * a.H * a.W * a_valid * b_valid * ntaps,
+             nbytes=a.L * 128.0 * ntaps * ((a_valid + 127) // 128 * 2 + (b_valid + 63) // 64))
 
 
 def _conv_wgrad(dz, x, co, ci):
     """Weight gradient of a 3x3 convolution: dz (Cout channels, unshifted copy clean), x (3-copy input) -> (Cout, Cin, 3, 3)."""
     g = torch.zeros((9, co, ci), dtype=torch.float32, device=dz.buf.device)
-    for tap in range(9):
-        dy, dx = tap // 3 - 1, tap % 3 - 1
-        for a0 in range(0, co, 256):
-            for b0 in range(0, ci, 256):
-                _wgrad(dz, a0 // 64, min(256, co - a0), x, dx + 1, b0 // 64, min(256, ci - b0), dy * x.Wp, g[tap, a0:, b0:])
+    for a0 in range(0, co, 256):
+        for b0 in range(0, ci, 256):
+            _wgrad(dz, a0 // 64, min(256, co - a0), x, b0 // 64, min(256, ci - b0), 9, g[:, a0:, b0:], g.stride(0))
     return g.permute(1, 2, 0).reshape(co, ci, 3, 3)
 
 
 def _gemm_wgrad(a, a_ch, b, b_ch):
-    """(a_ch, b_ch) = A^T B for two single-copy maps of one raster (1x1 / transposed convolutions)."""
+    """(a_ch, b_ch) = A^T B for two maps of one raster (1x1 / transposed convolutions)."""
     g = torch.zeros((a_ch, b_ch), dtype=torch.float32, device=a.buf.device)
     for a0 in range(0, a_ch, 256):
         for b0 in range(0, b_ch, 256):
-            _wgrad(a, a0 // 64, min(256, a_ch - a0), b, 1 if b.copies == 3 else 0, b0 // 64, min(256, b_ch - b0), 0, g[a0:, b0:])
+            _wgrad(a, a0 // 64, min(256, a_ch - a0), b, b0 // 64, min(256, b_ch - b0), 1, g[a0:, b0:], 0)
     return g
 
 
