@@ -170,7 +170,7 @@ def run_reference(args, rank):
         "cpu_baseline": {"value": rays_s, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": rays_s, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    _emit(json.dumps(line))
 
 
 # ----------------------------------------------------------------------------------------------- our arm
@@ -417,7 +417,7 @@ def main():
         line["cpu_baseline"] = {"value": rays_s, "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": f"one {args.cpu_tile}x{args.cpu_tile}-ray tile (the reference's test.py tile) of the frame, "
                                           f"P={args.points}, fwd+bwd (MSE), fp32 oracle port, {sec:.2f} s/step"}
-    print(json.dumps(line))
+    _emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
@@ -462,5 +462,22 @@ def run_caterpillar(tag, dev, rank, world, build_model, timed, steps):
             "points": int(model.points.shape[0])}
 
 
+def _emit(line):
+    """The contract is ONE JSON line on stdout: everything else that libraries print there (NCCL's version banner, ...)
+    was sent to stderr by _quiet_stdout()."""
+    os.write(_REAL_STDOUT, (line + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
+def _quiet_stdout():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
 if __name__ == "__main__":
+    _quiet_stdout()
     main()
