@@ -442,3 +442,70 @@ def synthetic_rays(H, W, coord_scale, n_views=1, seed=1, radius=4.0, camera_angl
     h1 = H if h1 is None else h1
     w1 = W if w1 is None else w1
     return rays_o.contiguous(), rays_d[:, h0:h1, w0:w1].contiguous(), c2w
+
+
+# ----------------------------------------------------------------------------- LPIPS / VGG16
+VGG16_CFG = [(3, 64), (64, 64), "P", (64, 128), (128, 128), "P", (128, 256), (256, 256), (256, 256), "P",
+             (256, 512), (512, 512), (512, 512), "P", (512, 512), (512, 512), (512, 512)]
+VGG16_TAPS = (1, 3, 6, 9, 12)          # conv index (0-based over the 13 convs) whose ReLU output LPIPS reads: relu1_2 ... relu5_3
+VGG16_FEATURE_INDEX = (0, 2, 5, 7, 10, 12, 14, 17, 19, 21, 24, 26, 28)      # torchvision vgg16().features index of each conv
+
+
+def init_lpips_params(seed=1, lin_path=None):
+    """Seeded stand-in for the ImageNet VGG16 weights (not available offline) with torchvision's shapes, keyed like the
+    reference's LPNet state dict (models/lpips.py:8-28: net.slice{1..5}.{features index}.{weight,bias}), plus the learnt
+    LPIPS linear weights lins.{k}.weight (loaded from the reference's vgg.pth when lin_path is given, else seeded)."""
+    g = torch.Generator().manual_seed(seed)
+    P = {}
+    slices = {0: 1, 2: 1, 5: 2, 7: 2, 10: 3, 12: 3, 14: 3, 17: 4, 19: 4, 21: 4, 24: 5, 26: 5, 28: 5}
+    ci = 0
+    for item in VGG16_CFG:
+        if item == "P":
+            continue
+        cin, cout = item
+        idx = VGG16_FEATURE_INDEX[ci]
+        std = math.sqrt(2.0 / (cin * 9))                       # kaiming-normal keeps activations O(1) through 13 layers
+        P[f"net.slice{slices[idx]}.{idx}.weight"] = torch.randn(cout, cin, 3, 3, generator=g) * std
+        P[f"net.slice{slices[idx]}.{idx}.bias"] = 0.05 * torch.randn(cout, generator=g)
+        ci += 1
+    if lin_path is not None and os.path.exists(lin_path):
+        w = torch.load(lin_path, map_location="cpu")
+        for k in range(5):
+            P[f"lins.{k}.weight"] = w[f"lin{k}.model.1.weight"].float().clone()
+    else:
+        for k, c in enumerate((64, 128, 256, 512, 512)):
+            P[f"lins.{k}.weight"] = torch.rand(1, c, 1, 1, generator=g) * 0.5
+    return P
+
+
+def vgg16_features(params, x):
+    """models/lpips.py:8-48: the five ReLU taps of torchvision's vgg16().features."""
+    slices = {0: 1, 2: 1, 5: 2, 7: 2, 10: 3, 12: 3, 14: 3, 17: 4, 19: 4, 21: 4, 24: 5, 26: 5, 28: 5}
+    outs, ci = [], 0
+    for item in VGG16_CFG:
+        if item == "P":
+            x = F.max_pool2d(x, 2)
+            continue
+        idx = VGG16_FEATURE_INDEX[ci]
+        x = torch.relu(F.conv2d(x, params[f"net.slice{slices[idx]}.{idx}.weight"], params[f"net.slice{slices[idx]}.{idx}.bias"], padding=1))
+        if ci in VGG16_TAPS:
+            outs.append(x)
+        ci += 1
+    return outs
+
+
+def lpips(params, in0, in1):
+    """models/lpips.py:103-125 (LPNet.forward): in0, in1 (N,H,W,3) in [0,1] -> scalar."""
+    shift = torch.tensor([-.030, -.088, -.188], dtype=in0.dtype, device=in0.device)[None, :, None, None]
+    scale = torch.tensor([.458, .448, .450], dtype=in0.dtype, device=in0.device)[None, :, None, None]
+    a = ((2 * in0.permute(0, 3, 1, 2) - 1) - shift) / scale
+    b = ((2 * in1.permute(0, 3, 1, 2) - 1) - shift) / scale
+    fa, fb = vgg16_features(params, a), vgg16_features(params, b)
+
+    def norm(t, eps=1e-10):
+        return t / (torch.sqrt(torch.sum(t ** 2, dim=1, keepdim=True) + eps) + eps)
+    val = 0
+    for k in range(5):
+        d = (norm(fa[k]) - norm(fb[k])) ** 2
+        val = val + torch.sum(params[f"lins.{k}.weight"] * d, 1, keepdim=True).mean([2, 3], keepdim=True)
+    return val.squeeze().mean()
