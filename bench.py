@@ -312,8 +312,35 @@ def main():
     render_e2e()
     ms_render_e2e = timed(render_e2e, steps)
 
-    # ---- configs[3] / configs[4]: Caterpillar-shaped frame, rows sharded over the ranks (strong scaling)
+    # ---- the reference's full training loss (default.yml:155-158: mse + 0.01 lpips) on the same step: LPIPS/VGG16 on the
+    # library's conv kernels, seeded-random trunk (ImageNet weights are not available offline)
     extra = {}
+    if not args.no_extra_configs:
+        try:
+            import warnings
+            from papr_b200.lpips import get_loss
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                loss_fn = get_loss(cfg.training.losses, lin_path=os.path.join(ROOT, "vgg.pth")).to(dev)
+
+            def lpips_step():
+                model.clear_grad()
+                out = model.last_act(model(resident["rays_o"], resident["rays_d"], resident["c2w"], step=-1))
+                loss_fn(out, resident["target"]).backward()
+                if world > 1:
+                    bucket[0] = allreduce_gradients(model, bucket[0])
+                model.step()
+            for _ in range(2):
+                lpips_step()
+            ms_lp = timed(lpips_step, min(steps, 3))
+            extra["with_lpips"] = {"ms_per_step": ms_lp, "rays_per_s": rays_per_step / ms_lp * 1e3,
+                                   "loss": "mse 1.0 + lpips 0.01 (VGG16 trunk on papr_conv_bf16, seeded-random weights)"}
+            del loss_fn
+        except Exception as e:
+            extra["with_lpips"] = {"error": repr(e)[:300]}
+        torch.cuda.empty_cache()
+
+    # ---- configs[3] / configs[4]: Caterpillar-shaped frame, rows sharded over the ranks (strong scaling)
     if not args.no_extra_configs:
         del model
         bucket[0] = None
