@@ -307,11 +307,14 @@ typedef struct papr_raster {
  * in_planes points at plane 0 of copy dx = -1 (ntaps = 9) or of the only copy (ntaps = 1); w_image holds ntaps*cbs blocks of
  * N x 128 B (papr_pack_weight_batch layout over K = ntaps*cbs*64).  Output: unshifted planes (out_planes, ceil(N/64) of
  * them, written as whole 128-row tiles INCLUDING padding rows -- papr_unet_spread re-establishes the zero border) and / or
- * fp32 rows out_f32[tile*128 + r][ld_f32].  32 <= N <= 256, N % 32 == 0.
+ * fp32 rows out_f32[tile*128 + r][ld_f32].  addend_f32 (same row indexing, ld_addend) is added to the accumulator before bias /
+ * activation: the partial sums of the fp32 parity mode (three-way bf16 split of both operands, six launches).
+ * 32 <= N <= 256, N % 32 == 0.
  */
 int papr_conv_bf16(const void *in_planes, int64_t in_copy_bytes, int64_t in_plane_bytes, int64_t in_row0, int cbs, int ntaps,
                    int Wp, int sign, const void *w_image, const float *bias, int N, int act, float slope, void *out_planes,
-                   int64_t out_plane_bytes, int64_t out_row0, float *out_f32, int64_t ld_f32, int64_t n_tiles, void *stream);
+                   int64_t out_plane_bytes, int64_t out_row0, float *out_f32, int64_t ld_f32, const float *addend_f32,
+                   int64_t ld_addend, int64_t n_tiles, void *stream);
 /*
  * Weight gradient of a convolution (autograd of the same lines), all taps in one launch:
  *     C[tap][a][b] += sum_rows A[row][a] * B(copy dx(tap))[row + dy(tap)*Wp][b]        over `rows` raster rows (multiple of 64)

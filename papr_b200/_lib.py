@@ -37,7 +37,7 @@ SIGNATURES = {
     "papr_pack_weight_batch": [_ptr, _i32, _ptr],
     "papr_knn": [_ptr, _i64, _ptr, _i64, _i32, _ptr, _ptr, _ptr],
     "papr_prune_compact": [_ptr, _ptr, _ptr, _i64, _i32, _f32, _i32, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
-    "papr_conv_bf16": [_ptr, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _ptr, _ptr, _i32, _i32, _f32, _ptr, _i64, _i64, _ptr, _i64, _i64, _ptr],
+    "papr_conv_bf16": [_ptr, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _ptr, _ptr, _i32, _i32, _f32, _ptr, _i64, _i64, _ptr, _i64, _ptr, _i64, _i64, _ptr],
     "papr_conv_wgrad_bf16": [_ptr, _i64, _i32, _ptr, _i64, _i64, _i32, _i32, _i32, _ptr, _i64, _i64, _i64, _ptr],
     "papr_unet_pack_input": [_ptr, _i64, _i32, _ptr, _ptr, _ptr, _ptr, _i32, _i32, _ptr],
     "papr_unet_unpack": [_ptr, _ptr, _i32, _ptr, _i64, _i32, _ptr],

@@ -36,6 +36,8 @@ struct ConvParams {
     int64_t y_plane_bytes, y_row0;
     float *y_f32;              // fp32 row-major [n_tiles*128, ldy] or null
     int64_t ldy;
+    const float *addend;       // fp32 row-major [n_tiles*128, ld_add] added to the accumulator before bias / activation, or null
+    int64_t ld_add;
     int64_t n_tiles;
     int cbs, ntaps, Wp, sign, N, nblk_out, stages, b_bytes;
     float slope;
@@ -139,6 +141,27 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(const ConvParams 
                 if (!second) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v1[j] = 0;
+                }
+                if (p.addend) {      // partial sums of the split-bf16 fp32 mode (papr_b200/unet_fp32.py)
+                    const float4 *src = reinterpret_cast<const float4 *>(p.addend + grow * p.ld_add + col0);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 a = __ldg(src + j);
+                        v0[4 * j] = __float_as_uint(__uint_as_float(v0[4 * j]) + a.x);
+                        v0[4 * j + 1] = __float_as_uint(__uint_as_float(v0[4 * j + 1]) + a.y);
+                        v0[4 * j + 2] = __float_as_uint(__uint_as_float(v0[4 * j + 2]) + a.z);
+                        v0[4 * j + 3] = __float_as_uint(__uint_as_float(v0[4 * j + 3]) + a.w);
+                    }
+                    if (second) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 a = __ldg(src + 8 + j);
+                            v1[4 * j] = __float_as_uint(__uint_as_float(v1[4 * j]) + a.x);
+                            v1[4 * j + 1] = __float_as_uint(__uint_as_float(v1[4 * j + 1]) + a.y);
+                            v1[4 * j + 2] = __float_as_uint(__uint_as_float(v1[4 * j + 2]) + a.z);
+                            v1[4 * j + 3] = __float_as_uint(__uint_as_float(v1[4 * j + 3]) + a.w);
+                        }
+                    }
                 }
                 uint32_t dummy = 0;
                 epilogue_math<EPI>(v0, bias_s, col0, p.slope, 0u, dummy);
@@ -322,10 +345,12 @@ __global__ void __launch_bounds__(kCwThreads, 1) conv_wgrad_kernel(const ConvWgr
 
 extern "C" int papr_conv_bf16(const void *in_planes, int64_t in_copy_bytes, int64_t in_plane_bytes, int64_t in_row0, int cbs, int ntaps,
                               int Wp, int sign, const void *w_image, const float *bias, int N, int act, float slope, void *out_planes,
-                              int64_t out_plane_bytes, int64_t out_row0, float *out_f32, int64_t ld_f32, int64_t n_tiles, void *stream)
+                              int64_t out_plane_bytes, int64_t out_row0, float *out_f32, int64_t ld_f32, const float *addend_f32,
+                              int64_t ld_addend, int64_t n_tiles, void *stream)
 {
     using namespace papr;
     if (!in_planes || !w_image || (!out_planes && !out_f32)) return PAPR_ERR_INVALID_ARGUMENT;
+    if (addend_f32 && (ld_addend < N || ld_addend % 4)) return PAPR_ERR_INVALID_ARGUMENT;
     if (n_tiles <= 0 || N < 32 || N > 256 || N % 32 || cbs < 1 || (ntaps != 1 && ntaps != 9) || (sign != 1 && sign != -1)) return PAPR_ERR_INVALID_ARGUMENT;
     if (ntaps == 9 && (Wp < 8 || Wp % 8 || in_row0 < Wp + 1)) return PAPR_ERR_INVALID_ARGUMENT;
     if (out_f32 && (ld_f32 < N || ld_f32 % 4)) return PAPR_ERR_INVALID_ARGUMENT;
@@ -333,7 +358,7 @@ extern "C" int papr_conv_bf16(const void *in_planes, int64_t in_copy_bytes, int6
     ConvParams p;
     p.a = (const uint8_t *)in_planes; p.a_copy_bytes = in_copy_bytes; p.a_plane_bytes = in_plane_bytes; p.a_row0 = in_row0;
     p.w = (const uint8_t *)w_image; p.bias = bias; p.y = (uint8_t *)out_planes; p.y_plane_bytes = out_plane_bytes; p.y_row0 = out_row0;
-    p.y_f32 = out_f32; p.ldy = ld_f32; p.n_tiles = n_tiles; p.cbs = cbs; p.ntaps = ntaps; p.Wp = Wp; p.sign = sign; p.N = N;
+    p.y_f32 = out_f32; p.ldy = ld_f32; p.addend = addend_f32; p.ld_add = ld_addend; p.n_tiles = n_tiles; p.cbs = cbs; p.ntaps = ntaps; p.Wp = Wp; p.sign = sign; p.N = N;
     p.nblk_out = (N + 63) / 64; p.slope = slope;
     p.b_bytes = (N * 128 + 1023) & ~1023;
     const int fixed = 1024 + 2 * kBlockBytes + 1280;

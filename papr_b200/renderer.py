@@ -3,9 +3,11 @@
 Same module tree as the reference so checkpoints interchange (renderer.inc.double_conv.0.*, renderer.down{1,2}.
 maxpool_conv.1.double_conv.0.*, renderer.up{1,2}.{up,conv.double_conv.0}.*, renderer.outc.conv.*); the modules below only
 OWN the parameters.  On the product path (CUDA, bf16) the forward and backward run on the library's implicit-GEMM tcgen05
-convolution kernels (papr_b200/unet.py, csrc/conv.cu, csrc/unet_raster.cu) -- no cuDNN.  The torch modules are executed
-only in the fp32 parity mode and for FiLM at an inner stage (affine_layer 1..5, which no shipped config uses).  Only the
-shipped variant (single conv blocks, transposed-conv upsampling, no normalisation) exists.
+convolution kernels (papr_b200/unet.py, csrc/conv.cu, csrc/unet_raster.cu) -- no cuDNN; the fp32 parity mode runs the
+same kernels at fp32 accuracy through a three-way bf16 split (papr_b200/unet_fp32.py).  The torch modules are executed
+only for FiLM at an inner stage (affine_layer 1..5, which no shipped config uses) in bf16, on the CPU, or with
+`own_kernels = False` (A/B measurements).  Only the shipped variant (single conv blocks, transposed-conv upsampling, no
+normalisation) exists.
 """
 import torch
 import torch.nn as nn
@@ -90,6 +92,9 @@ class SmallUNet(nn.Module):
                 g, b = gamma.reshape(-1, C).float(), beta.reshape(-1, C).float()
             out = U.UNetFn.apply(x, g, b, torch.is_grad_enabled(), *U.parameter_list(self))
             return self.last_act(out)
+        if x.is_cuda and self.compute_dtype == torch.float32 and self.own_kernels:
+            from .unet_fp32 import unet_forward_fp32      # parity mode: split-bf16 convolutions on the same tensor-core kernels
+            return unet_forward_fp32(self, x, gamma, beta)
         amp = x.is_cuda and self.compute_dtype != torch.float32
         with torch.autocast(device_type="cuda", dtype=self.compute_dtype, enabled=amp):
             if amp:

@@ -115,8 +115,9 @@ class _Weights:
 
 
 # ----------------------------------------------------------------------------------------------------- kernel wrappers
-def _conv(src, src_ptr, cbs, ntaps, sign, tiles, bias, act, out, out_cb0=0, out_f32=None):
-    """One convolution over all output-channel tiles.  src_ptr: plane 0 of copy dx=-1 (3x3) or of the unshifted copy (1x1)."""
+def _conv(src, src_ptr, cbs, ntaps, sign, tiles, bias, act, out, out_cb0=0, out_f32=None, addend=None):
+    """One convolution over all output-channel tiles.  src_ptr: plane 0 of copy dx=-1 (3x3) or of the unshifted copy (1x1).
+    addend: fp32 (rows, ld) partial sums added before bias / activation (same column tiling as out_f32)."""
     n0 = 0
     flops = 0.0
     for img, N, n in tiles:
@@ -129,6 +130,7 @@ def _conv(src, src_ptr, cbs, ntaps, sign, tiles, bias, act, out, out_cb0=0, out_
                  out.ptr(cb=out_cb0 + n0 // 64) if out is not None else None, out.plane_bytes if out is not None else 0,
                  out.G0 if out is not None else 0,
                  out_f32.data_ptr() + n0 * 4 if out_f32 is not None else None, out_f32.stride(0) if out_f32 is not None else 0,
+                 addend.data_ptr() + n0 * 4 if addend is not None else None, addend.stride(0) if addend is not None else 0,
                  src.n_tiles, flops=2.0 * src.H * src.W * n * cbs * 64 * ntaps,
                  nbytes=src.L * 128.0 * (cbs * (3 if ntaps == 9 else 1) + N / 64))
         n0 += n

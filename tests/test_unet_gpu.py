@@ -93,6 +93,41 @@ def test_unet_gradients_match_oracle_autograd(H, W, film, batch):
         assert r <= 1.5 * r_lib + 1e-2 and cos >= 0.99, (name, r, r_lib, cos)
 
 
+@pytest.mark.parametrize("H,W,film", [(24, 32, False), (13, 10, True)])
+def test_unet_parity_mode_is_fp32_accurate(H, W, film):
+    """compute_dtype = fp32: the same conv kernels through the three-way bf16 split (papr_b200/unet_fp32.py) against the fp32
+    oracle -- forward 1e-5 of scale, every gradient 2e-4 of scale -- with torch's convolutions poisoned."""
+    import torch.nn.functional as F
+    m = _unet(affine_layer=0 if film else -1, seed=2)
+    m.compute_dtype = torch.float32
+    g = torch.Generator(device="cuda").manual_seed(8)
+    x = torch.randn(1, 32, H, W, device="cuda", generator=g, requires_grad=True)
+    gamma = (1 + 0.2 * torch.randn(32, device="cuda", generator=g)).requires_grad_(True) if film else None
+    beta = (0.2 * torch.randn(32, device="cuda", generator=g)).requires_grad_(True) if film else None
+    tgt = torch.randn(1, 3, H, W, device="cuda", generator=g)
+    real_conv2d, real_convt = F.conv2d, F.conv_transpose2d
+    try:
+        F.conv2d = F.conv_transpose2d = None            # any library convolution on this path would raise
+        out = m(x, gamma=gamma, beta=beta)
+        ((out - tgt) ** 2).mean().backward()
+    finally:
+        F.conv2d, F.conv_transpose2d = real_conv2d, real_convt
+    P = {k: v.requires_grad_(True) for k, v in _oracle_params(m).items()}
+    xc = x.detach().cpu().requires_grad_(True)
+    gc = gamma.detach().cpu().requires_grad_(True) if film else None
+    bc = beta.detach().cpu().requires_grad_(True) if film else None
+    want = O.unet(P, xc, gc, bc, 0 if film else -1)
+    ((want - tgt.cpu()) ** 2).mean().backward()
+    e = float((out.detach().cpu() - want.detach()).abs().max()) / float(want.abs().max())
+    print(f"unet fp32 mode {H}x{W}: forward max-abs/scale {e:.2e}")
+    assert e <= 1e-5
+    checks = [("x", x.grad.cpu(), xc.grad)] + ([("gamma", gamma.grad.cpu(), gc.grad), ("beta", beta.grad.cpu(), bc.grad)] if film else [])
+    checks += [(n, p.grad.cpu(), P["renderer." + n].grad) for n, p in m.named_parameters()]
+    for name, a, b in checks:
+        r = float((a - b).abs().max()) / max(float(b.abs().max()), 1e-30)
+        assert r <= 2e-4, (name, r)
+
+
 def test_unet_through_the_model_no_library_convolution(monkeypatch):
     """The product path must not touch torch's convolution: PAPR.forward + backward with conv2d / conv_transpose2d poisoned."""
     from papr_b200.model import PAPR
