@@ -38,7 +38,19 @@ inline cudaError_t ensure_dyn_smem(SmemAttrOnce &once, Kernel kernel, int bytes)
     return e;
 }
 
-constexpr int kNumSMs = 148;   // B200
+// SM count of the current device (148 on B200), queried once per device: persistent kernels size their grids with it
+inline int num_sms()
+{
+    static int cached[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (!cached[dev]) {
+        int n = 0;
+        cached[dev] = (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) ? n : 148;
+    }
+    return cached[dev];
+}
+#define kNumSMs (::papr::num_sms())
 
 // 16-byte vector reduction into global memory (sm_90+): one instruction instead of four scalar atomics
 __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d)

@@ -232,8 +232,14 @@ class PAPR(nn.Module):
 
     @property
     def select_k_ind(self):
-        """int64 indices as the reference exposes them (model.py:464)."""
-        return None if self._idx32 is None else self._idx32.long()
+        """int64 indices as the reference exposes them (model.py:464); converted once per selection, on first access."""
+        if self._idx32 is None:
+            return None
+        cached = getattr(self, "_idx64", None)
+        if cached is None or cached[0] is not self._idx32:
+            cached = (self._idx32, self._idx32.long())
+            self._idx64 = cached
+        return cached[1]
 
     @property
     def selected_points(self):
