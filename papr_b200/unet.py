@@ -82,36 +82,65 @@ def _pad_k(t, k):
 
 
 class _Weights:
-    """bf16 weight images of every UNet layer (forward and data-gradient orientation), one batched pack launch."""
+    """bf16 weight images of every UNet layer (forward and data-gradient orientation) in PERSISTENT buffers: fp32 staging
+    matrices with fixed addresses, the images, padded biases and the device-side descriptor table are built once per set of
+    parameter tensors; `refresh` then costs one small copy per matrix plus ONE papr_pack_weight_batch launch -- and no
+    host-to-device copy (a pageable one would synchronise the stream and stop the host from running ahead)."""
 
-    def __init__(self, p, need_grad):
-        descs, self.keep = [], []
-        self.fwd, self.bwd = {}, {}
+    def __init__(self, params):
+        self.key = tuple(t.data_ptr() for t in params)
+        self.stage, self.views = [], []          # staging matrix, function producing the source view from the live weights
+        self.fwd, self.bwd, self.bias = {}, {}, {}
+        descs = []
 
-        def add(table, name, mat):
-            tiles, d, keepalive = _pack_matrix(mat)
+        def add(table, name, shape, view_fn):
+            mat = torch.zeros(shape, dtype=torch.float32, device=params[0].device)
+            tiles, d, _ = _pack_matrix(mat)
             table[name] = tiles
             descs.extend(d)
-            self.keep.append(keepalive)
+            self.stage.append(mat)
+            self.views.append(view_fn)
 
-        for name in ("inc", "down1", "down2", "up1c", "up2c"):
-            w = p[name + ".w"]                                        # (Cout, Cin, 3, 3)
-            co, ci = w.shape[:2]
-            cip, cop = (ci + 63) // 64 * 64, (co + 63) // 64 * 64
-            add(self.fwd, name, _pad_k(w.permute(0, 2, 3, 1), cip).reshape(co, 9 * cip))
-            if need_grad:                                             # W'[ci][tap*Cout + co]
-                add(self.bwd, name, _pad_k(w.permute(1, 2, 3, 0), cop).reshape(ci, 9 * cop))
-        for name in ("up1t", "up2t"):
-            w = p[name + ".w"]                                        # ConvTranspose2d: (Cin, Cout, 2, 2)
-            ci, co = w.shape[:2]
-            add(self.fwd, name, w.permute(2, 3, 1, 0).reshape(4 * co, ci))
-            if need_grad:
-                add(self.bwd, name, w.permute(0, 2, 3, 1).reshape(ci, 4 * co))
-        w = p["outc.w"]                                               # (3, 128, 1, 1)
-        add(self.fwd, "outc", w.reshape(w.shape[0], w.shape[1]))
-        if need_grad:
-            add(self.bwd, "outc", _pad_k(w.reshape(w.shape[0], w.shape[1]).t(), 64))
-        self.table = _launch_pack(descs, w.device)
+        for i, (name, _) in enumerate(_NAMES):
+            w = params[2 * i]
+            if name in ("inc", "down1", "down2", "up1c", "up2c"):                         # (Cout, Cin, 3, 3)
+                co, ci = w.shape[:2]
+                cip, cop = (ci + 63) // 64 * 64, (co + 63) // 64 * 64
+                add(self.fwd, name, (co, 9 * cip), lambda t, ci=ci, cip=cip: (t.permute(0, 2, 3, 1), (t.shape[0], 9, cip), ci))
+                add(self.bwd, name, (ci, 9 * cop), lambda t, co=co, cop=cop: (t.permute(1, 2, 3, 0), (t.shape[1], 9, cop), co))
+            elif name in ("up1t", "up2t"):                                                 # ConvTranspose2d: (Cin, Cout, 2, 2)
+                ci, co = w.shape[:2]
+                add(self.fwd, name, (4 * co, ci), lambda t: (t.permute(2, 3, 1, 0), (4 * t.shape[1], 1, t.shape[0]), t.shape[0]))
+                add(self.bwd, name, (ci, 4 * co), lambda t: (t.permute(0, 2, 3, 1), (t.shape[0], 1, 4 * t.shape[1]), 4 * t.shape[1]))
+            else:                                                                          # outc (3, 128, 1, 1)
+                co, ci = w.shape[:2]
+                add(self.fwd, name, (co, ci), lambda t: (t.reshape(t.shape[0], t.shape[1]), (t.shape[0], 1, t.shape[1]), t.shape[1]))
+                add(self.bwd, name, (ci, 64), lambda t: (t.reshape(t.shape[0], t.shape[1]).t(), (t.shape[1], 1, 64), t.shape[0]))
+            self.bias[name] = []
+            n0 = 0
+            for _, N, n in (self.fwd[name] if name not in ("up1t", "up2t") else []):      # the pixel shuffle adds the convT biases
+                self.bias[name].append((torch.zeros(N, dtype=torch.float32, device=w.device), n0, n))
+                n0 += n
+        self.n_descs = len(descs)
+        arr = (PackDesc * len(descs))(*descs)
+        self.table = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(params[0].device)      # once per parameter set
+
+    def refresh(self, params):
+        """Re-read the live parameters into the staging matrices and rebuild every image (one launch)."""
+        k = 0
+        for i, (name, _) in enumerate(_NAMES):
+            w, b = params[2 * i].detach(), params[2 * i + 1].detach()
+            for _ in range(2):
+                src, shape3, valid = self.views[k](w)
+                dst = self.stage[k].view(shape3)
+                if src.dim() == 4:          # (rows, 3, 3, C) -> (rows, 9, C_pad)
+                    dst[:, :, :valid].copy_(src.reshape(shape3[0], shape3[1], valid))
+                else:
+                    dst[:, 0, :valid].copy_(src)
+                k += 1
+            for buf, n0, n in self.bias[name]:
+                buf[:n].copy_(b[n0:n0 + n])
+        ops.call("papr_pack_weight_batch", self.table.data_ptr(), self.n_descs, nbytes=sum(6.0 * m.numel() for m in self.stage))
 
 
 # ----------------------------------------------------------------------------------------------------- kernel wrappers
@@ -119,10 +148,11 @@ def _conv(src, src_ptr, cbs, ntaps, sign, tiles, bias, act, out, out_cb0=0, out_
     """One convolution over all output-channel tiles.  src_ptr: plane 0 of copy dx=-1 (3x3) or of the unshifted copy (1x1).
     addend: fp32 (rows, ld) partial sums added before bias / activation (same column tiling as out_f32)."""
     n0 = 0
-    flops = 0.0
-    for img, N, n in tiles:
+    for ti, (img, N, n) in enumerate(tiles):
         b = None
-        if bias is not None:
+        if isinstance(bias, list):           # padded per-tile biases kept by _Weights
+            b = bias[ti][0]
+        elif bias is not None:
             b = torch.zeros(N, dtype=torch.float32, device=img.device)
             b[:n] = bias[n0:n0 + n]
         ops.call("papr_conv_bf16", src_ptr, src.copy_bytes, src.plane_bytes, src.G0, cbs, ntaps, src.Wp, sign, img.data_ptr(),
@@ -205,33 +235,33 @@ def unet_forward_image(x_hwc, p, W, gamma, beta, keep):
              beta.data_ptr() if beta is not None else None, P0.ptr(), _ref(P0.raster()), 3, 1, nbytes=H * Wd * (4.0 * Cin + 384))
     U2 = Planes(H, Wd, 256, 3, dev)
     T = Planes(H, Wd, 128, 1, dev, zero=False)
-    _conv(P0, P0.ptr(), 1, 9, 1, W.fwd["inc"], p["inc.b"], True, T)
+    _conv(P0, P0.ptr(), 1, 9, 1, W.fwd["inc"], W.bias["inc"], True, T)
     _spread(T, 0, 2, dst=U2, dst_cb0=0)
     P1 = Planes(H2, W2, 128, 3, dev)
     _pool(U2, 0, 2, P1)
     U1 = Planes(H2, W2, 512, 3, dev)
     T = Planes(H2, W2, 256, 1, dev, zero=False)
-    _conv(P1, P1.ptr(), 2, 9, 1, W.fwd["down1"], p["down1.b"], True, T)
+    _conv(P1, P1.ptr(), 2, 9, 1, W.fwd["down1"], W.bias["down1"], True, T)
     _spread(T, 0, 4, dst=U1, dst_cb0=0)
     P2 = Planes(H3, W3, 256, 3, dev)
     _pool(U1, 0, 4, P2)
     X3 = Planes(H3, W3, 512, 1, dev, zero=False)
-    _conv(P2, P2.ptr(), 4, 9, 1, W.fwd["down2"], p["down2.b"], True, X3)
+    _conv(P2, P2.ptr(), 4, 9, 1, W.fwd["down2"], W.bias["down2"], True, X3)
     # up1: transposed convolution = 1x1 GEMM to (a, b, co) channels + pixel shuffle into the upper planes of U1 (the concat)
     T = Planes(H3, W3, 1024, 1, dev, zero=False)
     _conv(X3, X3.ptr(), 8, 1, 1, W.fwd["up1t"], None, False, T)
     ops.call("papr_unet_convt_scatter", T.ptr(), _ref(T.raster()), 256, p["up1t.b"].data_ptr(), U1.ptr(), _ref(U1.raster()), 4, 3,
              (H2 - 2 * H3) // 2, (W2 - 2 * W3) // 2, nbytes=H2 * W2 * 256 * 8.0)
     Y1 = Planes(H2, W2, 256, 1, dev, zero=False)
-    _conv(U1, U1.ptr(), 8, 9, 1, W.fwd["up1c"], p["up1c.b"], True, Y1)
+    _conv(U1, U1.ptr(), 8, 9, 1, W.fwd["up1c"], W.bias["up1c"], True, Y1)
     T = Planes(H2, W2, 512, 1, dev, zero=False)
     _conv(Y1, Y1.ptr(), 4, 1, 1, W.fwd["up2t"], None, False, T)
     ops.call("papr_unet_convt_scatter", T.ptr(), _ref(T.raster()), 128, p["up2t.b"].data_ptr(), U2.ptr(), _ref(U2.raster()), 2, 3,
              (H - 2 * H2) // 2, (Wd - 2 * W2) // 2, nbytes=H * Wd * 128 * 8.0)
     Y2 = Planes(H, Wd, 128, 1, dev, zero=False)
-    _conv(U2, U2.ptr(), 4, 9, 1, W.fwd["up2c"], p["up2c.b"], True, Y2)
+    _conv(U2, U2.ptr(), 4, 9, 1, W.fwd["up2c"], W.bias["up2c"], True, Y2)
     out = torch.empty((Y2.L, 32), dtype=torch.float32, device=dev)
-    _conv(Y2, Y2.ptr(), 2, 1, 1, W.fwd["outc"], p["outc.b"], False, None, out_f32=out)
+    _conv(Y2, Y2.ptr(), 2, 1, 1, W.fwd["outc"], W.bias["outc"], False, None, out_f32=out)
     rgb = out[: (H + 2) * Y2.Wp].view(H + 2, Y2.Wp, 32)[1:H + 1, 1:Wd + 1, :3]
     saved = (P0, U2, P1, U1, P2, X3, Y1, Y2) if keep else None
     return rgb, saved
@@ -321,7 +351,7 @@ class UNetFn(torch.autograd.Function):
         if Cin > 32 or H < 4 or Wd < 4:
             raise NotImplementedError("the UNet kernels take up to 32 input channels and images of at least 4 x 4 pixels")
         keep = grad_enabled and any(ctx.needs_input_grad)
-        W = _Weights(p, keep)
+        W = _weights_for(params)
         xh = x.detach().permute(0, 2, 3, 1).contiguous().float()
         outs, saved = [], []
         for b in range(Bn):
@@ -362,6 +392,21 @@ class UNetFn(torch.autograd.Function):
             flat += [grads[short + ".w"], grads[short + ".b"]]
         ctx.saved = None
         return (d_x, d_gamma, d_beta, None, *flat)
+
+
+_WEIGHT_CACHE = {}
+
+
+def _weights_for(params):
+    """The persistent weight-image set of these parameter tensors, refreshed from their current values."""
+    key = tuple(t.data_ptr() for t in params)
+    W = _WEIGHT_CACHE.get(key)
+    if W is None:
+        if len(_WEIGHT_CACHE) > 8:
+            _WEIGHT_CACHE.clear()
+        W = _WEIGHT_CACHE[key] = _Weights(params)
+    W.refresh(params)
+    return W
 
 
 def parameter_list(module):
