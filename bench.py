@@ -60,7 +60,7 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+                                          "-lms", "50"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
@@ -75,6 +75,10 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, pw, reasons = [], [], [], set()
         try:
+            if os.path.getsize(self.path) == 0:      # a run shorter than nvidia-smi's start-up: one query right after it
+                r = subprocess.run(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=20)
+                open(self.path, "w").write(r.stdout)
             for line in open(self.path):
                 f = [x.strip() for x in line.split(",")]
                 if len(f) < 9:
@@ -254,13 +258,14 @@ def main():
         model.step()
         return loss, out
 
+    # clocks are sampled from before the warm-up (nvidia-smi needs a moment to start) to the end of the timed region
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(warmup):
         train_step(resident)
     torch.cuda.synchronize()
 
     # ---- timed region: device-resident inputs, per-kernel CUDA events on the launching stream
-    sampler = ClockSampler(local)
-    sampler.start()
     ops.STATS.reset()
     ops.STATS.timing = True
     ms_step = timed(lambda: train_step(resident), steps)
