@@ -210,7 +210,18 @@ def main():
     H = W = args.hw
 
     def timed(fn, n):
-        """n calls between barrier + synchronize on both sides, CUDA events; returns max-over-ranks ms per call."""
+        """n calls between barrier + synchronize on both sides, CUDA events; returns max-over-ranks ms per call.
+        The cyclic garbage collector is held off inside the region (a generation-2 pass over the interpreter's heap takes
+        tens of ms and would land on an arbitrary step); it runs between regions."""
+        import gc
+        gc.collect()
+        gc.disable()
+        try:
+            return _timed(fn, n)
+        finally:
+            gc.enable()
+
+    def _timed(fn, n):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
