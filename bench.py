@@ -221,7 +221,19 @@ def main():
         finally:
             gc.enable()
 
+    alloc_log = {}
+
     def _timed(fn, n):
+        st0 = torch.cuda.memory_stats(dev)
+        try:
+            return _timed_inner(fn, n)
+        finally:
+            st1 = torch.cuda.memory_stats(dev)
+            alloc_log[getattr(fn, "__name__", "step") + "#" + str(len(alloc_log))] = {
+                "cudaMalloc": st1.get("num_device_alloc", 0) - st0.get("num_device_alloc", 0),
+                "cudaFree": st1.get("num_device_free", 0) - st0.get("num_device_free", 0)}
+
+    def _timed_inner(fn, n):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -445,7 +457,8 @@ def main():
                    "top_k": "bit-exact", "source": "profiles/r02_error_budget.md, tests/test_model_gpu.py, tests/test_fullsize_gpu.py"},
         "kernels": kernels,
         "memory": {"peak_allocated_gb": torch.cuda.max_memory_allocated(dev) / 1e9, "reserved_gb": torch.cuda.memory_reserved(dev) / 1e9,
-                   "alloc_retries": torch.cuda.memory_stats(dev).get("num_alloc_retries", 0)},
+                   "alloc_retries": torch.cuda.memory_stats(dev).get("num_alloc_retries", 0),
+                   "device_allocs_in_timed_regions": alloc_log},
     }
     line.update(extra)
     if world == 1 and not args.no_gpu_reference:
