@@ -30,7 +30,7 @@
 
 namespace papr {
 
-constexpr int kStkThreads = 672;     // 4 control warps + 2 x 8 epilogue warps + 1 LSU stash writer
+constexpr int kStkThreads = 640;     // 4 control warps + 2 x 8 epilogue warps
 constexpr int kStkMaxLayers = 8;
 constexpr int kSlotBytes = 4 * kBlockBytes;      // one 128 x 256 bf16 tile
 constexpr int kStkMaxSmem = 232448;
@@ -145,7 +145,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kStkThreads, 1) stac
                     uint8_t *out = p.L[l].out_blocked;
                     const bool stash = out != nullptr;
                     const int ng = (p.L[l].N + 63) >> 6;
-                    const int ng_tma = ng - min(p.lsu_groups, ng - 1);      // the last groups go through the LSU writer (warp 20)
+                    const int ng_tma = ng - min(p.lsu_groups, ng - 1);      // the last groups go through the LSU writer warp
                     for (int s = 0; s < 2; ++s) {
                         if (stash) {
                             mbar_wait(&st_ready[s], sj & 1);
@@ -167,8 +167,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kStkThreads, 1) stac
             }
             bulk_wait<0>();
         }
-    } else if (warp == 20) {
-        // Second stash writer: the bulk-store path of an SM moves 31 B/clk (profiles/r01_stack_kernel_study.md), exactly what
+    } else if (warp == (rank == 0 ? 3 : 1)) {
+        // Second stash writer (the warp that is idle in this CTA: the relay warp of the leader, the issuer warp of the peer): the bulk-store path of an SM moves 31 B/clk (profiles/r01_stack_kernel_study.md), exactly what
         // a job's 64 KB of stash needs, and it is shared with the weight loads.  This warp sends the last `lsu_groups` 16 KB
         // blocks of every stashed tile through the load/store unit instead (coalesced 512-byte ld.shared / st.global pairs;
         // the shared-memory block is byte-identical to the global one).
@@ -279,7 +279,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kStkThreads, 1) stac
                 }
             }
         }
-    } else if (warp >= 4 && warp < 20) {
+    } else if (warp >= 4) {
         // Sixteen epilogue warps drain the jobs in issue order; warp (g, quad) owns 64-column group g of the tile for
         // the TMEM lane quadrant quad (== warp % 4), so one job is four independent 128-thread groups.
         const int ew = warp - 4;
