@@ -53,7 +53,7 @@ struct StackLayerDev {
 struct StackParams {
     const uint8_t *x;          // tile-blocked input [rows, kblk0*64]
     int64_t n_tiles;
-    int n_layers, kblk0, stages, any_stash, store_depth, lsu_groups;
+    int n_layers, kblk0, stages, any_stash, store_depth;
     float slope;
     long long *trace;          // debug: per-job clock stamps of cluster 0 (null in production)
     StackLayerDev L[kStkMaxLayers];
@@ -86,8 +86,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kStkThreads, 1) stac
     if (threadIdx.x == 0) {
         for (int i = 0; i < 8; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); mbar_init(&pw_full[i], 1); }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&in_full[i], 1); mbar_init(&pin_full[i], 1); mbar_init(&in_free[i], writer_on_last ? 18 : 16);
-            mbar_init(&st_ready[i], 16); mbar_init(&st_done[i], 2);
+            mbar_init(&in_full[i], 1); mbar_init(&pin_full[i], 1); mbar_init(&in_free[i], writer_on_last ? 17 : 16);
+            mbar_init(&st_ready[i], 16); mbar_init(&st_done[i], 1);
             mbar_init(&act_ready[i], 32); mbar_init(&acc_full[i], 1);
         }
         fence_barrier_init();
@@ -145,13 +145,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kStkThreads, 1) stac
                     uint8_t *out = p.L[l].out_blocked;
                     const bool stash = out != nullptr;
                     const int ng = (p.L[l].N + 63) >> 6;
-                    const int ng_tma = ng - min(p.lsu_groups, ng - 1);      // the last groups go through the LSU writer warp
                     for (int s = 0; s < 2; ++s) {
                         if (stash) {
                             mbar_wait(&st_ready[s], sj & 1);
                             const int64_t tile = 4 * q + 2 * s + rank;
                             if (tile < p.n_tiles) {
-                                for (int g = 0; g < ng_tma; ++g) {
+                                for (int g = 0; g < ng; ++g) {
                                     bulk_s2g(out + ((size_t)tile * ng + g) * kBlockBytes, act + s * kSlotBytes + g * kBlockBytes, kBlockBytes);
                                     bulk_commit();
                                     if (p.store_depth > 1) bulk_wait_read<1>(); else bulk_wait_read<0>();
@@ -166,44 +165,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kStkThreads, 1) stac
                 }
             }
             bulk_wait<0>();
-        }
-    } else if (warp == (rank == 0 ? 3 : 1)) {
-        // Second stash writer (the warp that is idle in this CTA: the relay warp of the leader, the issuer warp of the peer): the bulk-store path of an SM moves 31 B/clk (profiles/r01_stack_kernel_study.md), exactly what
-        // a job's 64 KB of stash needs, and it is shared with the weight loads.  This warp sends the last `lsu_groups` 16 KB
-        // blocks of every stashed tile through the load/store unit instead (coalesced 512-byte ld.shared / st.global pairs;
-        // the shared-memory block is byte-identical to the global one).
-        uint32_t sj = 0;
-        for (int64_t q = cluster_id; q < n_quads; q += n_clusters) {
-            for (int l = 0; l < L; ++l) {
-                uint8_t *out = p.L[l].out_blocked;
-                const bool stash = out != nullptr;
-                const int ng = (p.L[l].N + 63) >> 6;
-                const int ng_tma = ng - min(p.lsu_groups, ng - 1);
-                for (int s = 0; s < 2; ++s) {
-                    if (stash) {
-                        mbar_wait(&st_ready[s], sj & 1);
-                        const int64_t tile = 4 * q + 2 * s + rank;
-                        if (tile < p.n_tiles) {
-                            for (int g = ng_tma; g < ng; ++g) {
-                                const uint32_t src = smem_u32(act) + (uint32_t)(s * kSlotBytes + g * kBlockBytes) + (uint32_t)lane * 16u;
-                                uint4 *dst = reinterpret_cast<uint4 *>(out + ((size_t)tile * ng + g) * kBlockBytes) + lane;
-#pragma unroll 8
-                                for (int it = 0; it < kBlockBytes / 512; ++it) {
-                                    uint4 v;
-                                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(src + (uint32_t)it * 512u));
-                                    dst[it * 32] = v;
-                                }
-                            }
-                        }
-                        __syncwarp();
-                        if (lane == 0) {
-                            mbar_arrive(&st_done[s]);
-                            if (l == L - 1) mbar_arrive(&in_free[s]);
-                        }
-                    }
-                }
-                if (stash) ++sj;
-            }
         }
     } else if (warp == 3) {
         if (lane == 0 && rank == 1) {       // relay: tell the leader that this CTA's TMA data has landed
@@ -463,7 +424,6 @@ extern "C" int papr_stack_bf16(const void *x, int K0, const papr_stack_layer *la
     p.x = (const uint8_t *)x; p.n_tiles = rows / kTileRows; p.n_layers = n_layers; p.kblk0 = (K0 + 63) / 64; p.slope = slope;
     p.any_stash = 0;
     { static int depth = -1; if (depth < 0) { const char *e = getenv("PAPR_STACK_STORE_DEPTH"); depth = e ? atoi(e) : 2; } p.store_depth = depth; }
-    { static int lsu = -1; if (lsu < 0) { const char *e = getenv("PAPR_STACK_LSU_GROUPS"); lsu = e ? atoi(e) : 0; if (lsu < 0 || lsu > 3) lsu = 0; } p.lsu_groups = lsu; }
     p.trace = g_stack_trace;
     int K = K0;
     for (int l = 0; l < n_layers; ++l) {
