@@ -389,7 +389,8 @@ def main():
     zero = dict(launches=0, ms=0.0, flops=0.0, bytes=0.0)
     tc_names = ("papr_stack_bf16", "papr_wgrad_bf16", "papr_linear_bf16", "papr_conv_bf16", "papr_conv_wgrad_bf16")
     tc = {n: kern.get(n, zero) for n in tc_names}
-    sel = kern.get("papr_select_topk", zero)
+    sel_name = next((n for n in ("papr_select_topk_grid", "papr_select_topk_sorted", "papr_select_topk") if n in kern), None)
+    sel = kern.get(sel_name, zero)
     stack = tc["papr_stack_bf16"]
     stack_ms = max(stack["ms"], 1e-9)
     achieved = stack["flops"] / (stack_ms * 1e-3) / 1e12
@@ -443,9 +444,10 @@ def main():
         "step_roofline": {"algorithmic_tflop_per_step": rays_per_step / world * FLOP_PER_RAY_TRAIN / 1e12,
                           "achieved_tflops_per_gpu": rays_per_step / world * FLOP_PER_RAY_TRAIN / (ms_step * 1e-3) / 1e12,
                           "frac_of_bf16_sustained": rays_per_step / world * FLOP_PER_RAY_TRAIN / (ms_step * 1e-3) / 1e12 / peaks["tf_sustained"]},
-        "select": {"ms_per_step": sel["ms"] / steps, "pairs_per_s": sel["flops"] / 17.0 / max(sel["ms"], 1e-9) * 1e3,
+        "select": {"kernel": sel_name, "ms_per_step": sel["ms"] / steps, "pairs_per_s": sel["flops"] / 17.0 / max(sel["ms"], 1e-9) * 1e3,
                    "fp32_tflops_17flop": sel["flops"] / max(sel["ms"], 1e-9) / 1e9,
-                   "algorithmic_hbm_gbs": sel["bytes"] / max(sel["ms"], 1e-9) / 1e6},
+                   "algorithmic_hbm_gbs": sel["bytes"] / max(sel["ms"], 1e-9) / 1e6,
+                   "note": "pairs = rays x points of the exhaustive scan the culled kernel replaces (equivalent rate, most pairs are never visited)"},
         "render": {"ms_per_frame": ms_render, "frame": f"{H}x{W}", "rows_per_gpu": h1 - h0,
                    "frac_of_gemm_floor": (H * W * FLOP_PER_RAY_FWD / world / (peaks["tf_sustained"] * 1e12) * 1e3) / ms_render,
                    "e2e_ms_per_frame": ms_render_e2e, "e2e_h2d_bytes": stripe_bytes, "e2e_d2h_bytes": rgb_host.numel() * 4,
