@@ -301,15 +301,31 @@ def main():
 
     # ---- end to end, as train.py:163-179 runs a step: host (pinned) rays/target copied in, and BOTH the loss and the
     # rendered image copied back to the host every step
-    out_host = torch.empty((1, H, W, 3), dtype=torch.float32).pin_memory()
+    # (papr_b200.staging.StepPipeline: same copies every step, software-pipelined -- the host reads step i-1's loss and
+    # image while step i runs, uploads go through a copy stream).  The plain blocking loop is timed next to it.
+    from papr_b200.staging import StepPipeline
+
+    def e2e_fn(b):
+        loss, out = train_step(b)
+        return loss.detach().reshape(1), out.detach()
+    pipe = StepPipeline(e2e_fn, dev)
+    seen = []
 
     def e2e_step():
+        res = pipe.submit(host)
+        if res is not None:
+            seen.append(float(res[0]))      # the loss of the previous step, on the host
+    e2e_step()
+    ms_e2e = timed(e2e_step, steps)
+    seen.append(float(pipe.flush()[0]))
+    out_host = torch.empty((1, H, W, 3), dtype=torch.float32).pin_memory()
+
+    def e2e_blocking():
         b = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
         loss, out = train_step(b)
         out_host.copy_(out.detach(), non_blocking=True)
         return loss.item()          # synchronises: the image copy above is complete as well
-    e2e_step()
-    ms_e2e = timed(e2e_step, steps)
+    ms_e2e_blocking = timed(e2e_blocking, min(steps, 5))
     h2d = sum(v.numel() * v.element_size() for v in host.values())
     d2h = 4 + out_host.numel() * out_host.element_size()
 
@@ -330,15 +346,27 @@ def main():
     host_stripe = host["rays_d"][:, h0:h1].contiguous().pin_memory()
     rgb_host = torch.empty((1, r1 - r0, W, 3), dtype=torch.float32).pin_memory()
 
-    def render_e2e():       # test.py:76-104 for one frame: rays in from the host, the finished RGB stripe back out
+    def render_fn(b):       # test.py:76-104 for one frame: rays in from the host, the finished RGB stripe back out
+        with torch.no_grad():
+            return model(b["rays_o"], b["rays_d"], None, step=-1)[:, r0 - h0:r1 - h0]
+    rpipe = StepPipeline(render_fn, dev)
+    host_frame = {"rays_o": host["rays_o"], "rays_d": host_stripe}
+
+    def render_e2e():
+        rpipe.submit(host_frame)
+    render_e2e()
+    ms_render_e2e = timed(render_e2e, steps)
+    rgb_last = rpipe.flush()
+    assert rgb_last.shape == rgb_host.shape
+
+    def render_blocking():
         with torch.no_grad():
             rd = host_stripe.to(dev, non_blocking=True)
             ro = host["rays_o"].to(dev, non_blocking=True)
             rgb = model(ro, rd, None, step=-1)[:, r0 - h0:r1 - h0]
             rgb_host.copy_(rgb, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-    render_e2e()
-    ms_render_e2e = timed(render_e2e, steps)
+    ms_render_blocking = timed(render_blocking, min(steps, 5))
 
     # ---- the reference's full training loss (default.yml:155-158: mse + 0.01 lpips) on the same step: LPIPS/VGG16 on the
     # library's conv kernels, seeded-random trunk (ImageNet weights are not available offline)
@@ -437,8 +465,11 @@ def main():
         "clocks": clocks,
         "e2e": {"value": rays_per_step / ms_e2e * 1e3, "unit": UNIT, "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "blocking_loop_ms_per_step": ms_e2e_blocking,
                 "what": "PAPR.forward/backward/step through the public model API with pinned-host rays + target copied in and the "
-                        "loss AND the rendered image copied back every step (train.py:163-179)"},
+                        "loss AND the rendered image copied back to the host every step (train.py:163-179), staged by "
+                        "papr_b200.staging.StepPipeline (the host reads step i-1's results while step i runs); "
+                        "blocking_loop_ms_per_step = the same with upload / loss.item() in line"},
         "gpu_launches": launches,
         "roofline": roofline,
         "step_roofline": {"algorithmic_tflop_per_step": rays_per_step / world * FLOP_PER_RAY_TRAIN / 1e12,
@@ -450,7 +481,7 @@ def main():
                    "note": "pairs = rays x points of the exhaustive scan the culled kernel replaces (equivalent rate, most pairs are never visited)"},
         "render": {"ms_per_frame": ms_render, "frame": f"{H}x{W}", "rows_per_gpu": h1 - h0,
                    "frac_of_gemm_floor": (H * W * FLOP_PER_RAY_FWD / world / (peaks["tf_sustained"] * 1e12) * 1e3) / ms_render,
-                   "e2e_ms_per_frame": ms_render_e2e, "e2e_h2d_bytes": stripe_bytes, "e2e_d2h_bytes": rgb_host.numel() * 4,
+                   "e2e_ms_per_frame": ms_render_e2e, "e2e_blocking_ms_per_frame": ms_render_blocking, "e2e_h2d_bytes": stripe_bytes, "e2e_d2h_bytes": rgb_host.numel() * 4,
                    "kernels_ms": {k: v["ms"] / steps for k, v in kern_render.items()}},
         "parity": {"stated_bf16_tolerance": {"attn": 2e-3, "bkg_weight": 7e-3, "fused_rel": 1.5e-2, "rgb": 9e-3},
                    "measured_bf16_worst": {"attn": 8.3e-4, "bkg_weight": 3.2e-3, "fused_rel": 7.5e-3, "rgb": 4.3e-3,

@@ -119,6 +119,11 @@ int papr_linear_bf16(const void *x, const void *w_image, const float *bias, void
  */
 int papr_wgrad_bf16(const void *a_blocked, int a_cols, const void *b_blocked, int b_cols, float *c, int64_t ldc,
                     int a_valid, int b_valid, int transpose_out, int64_t rows, void *stream);
+/* Same, on at most max_ctas SMs (0 = all), so that it can share the GPU with a papr_stack_bf16_ex launch on another
+ * stream: in the backward pass the dgrad of one slice of rows (HBM-write bound) overlaps the weight gradients of the
+ * previous slice (HBM-read bound). */
+int papr_wgrad_bf16_ex(const void *a_blocked, int a_cols, const void *b_blocked, int b_cols, float *c, int64_t ldc,
+                       int a_valid, int b_valid, int transpose_out, int64_t rows, int max_ctas, void *stream);
 
 /*
  * Per-ray CUDA-core stages.  Rows are (ray, candidate) pairs, row = ray*K + k; M = R*K rows, padded to 128.
@@ -204,6 +209,9 @@ typedef struct papr_stack_layer {
 
 int papr_stack_bf16(const void *x, int K0, const papr_stack_layer *layers, int n_layers, int64_t rows, float slope,
                     void *stream);
+/* Same, on at most max_ctas SMs (0 = all; rounded down to whole CTA pairs). */
+int papr_stack_bf16_ex(const void *x, int K0, const papr_stack_layer *layers, int n_layers, int64_t rows, float slope,
+                       int max_ctas, void *stream);
 
 /*
  * Per-ray query tail -- replaces the query stack's output LayerNorm, w_q, and the part of AttentionLayer that depends

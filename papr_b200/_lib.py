@@ -30,9 +30,11 @@ SIGNATURES = {
     "papr_blend_bwd": [_ptr] * 7 + [_i64, _i64, _i32, _i32, _i32, _i32] + [_ptr] * 5,
     "papr_key_score_bwd": [_ptr] * 5 + [_i64, _i32, _f32] + [_ptr] * 6,
     "papr_stack_bf16": [_ptr, _i32, _ptr, _i32, _i64, _f32, _ptr],
+    "papr_stack_bf16_ex": [_ptr, _i32, _ptr, _i32, _i64, _f32, _i32, _ptr],
     "papr_query_tail_fwd": [_ptr, _ptr, _f32, _f32, _i64, _ptr, _ptr, _ptr, _ptr],
     "papr_query_tail_bwd": [_ptr, _ptr, _ptr, _ptr, _i64, _ptr, _f32, _i64, _ptr, _ptr, _ptr, _ptr],
     "papr_wgrad_bf16": [_ptr, _i32, _ptr, _i32, _ptr, _i64, _i32, _i32, _i32, _i64, _ptr],
+    "papr_wgrad_bf16_ex": [_ptr, _i32, _ptr, _i32, _ptr, _i64, _i32, _i32, _i32, _i64, _i32, _ptr],
     "papr_adam_step": [_ptr, _ptr, _ptr, _i32, _i64, _ptr, _ptr, _ptr, _ptr, _i32, _f32, _ptr],
     "papr_pack_weight_batch": [_ptr, _i32, _ptr],
     "papr_knn": [_ptr, _i64, _ptr, _i64, _i32, _ptr, _ptr, _ptr],

@@ -20,6 +20,7 @@ library's own tensor-core kernels at fp32 accuracy through a three-way bf16 spli
 1e-5 assertions of the tests exercise linear_kernel / wgrad_kernel themselves.  The bf16 path is the product.
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -284,7 +285,21 @@ def _pad_bias(b, N):
 
 
 FUSE_STACKS = True      # one cta_group::2 launch per MLP stack (papr_stack_bf16) instead of one launch per layer
-BWD_SLICE_ROWS = 8 << 20    # rows per backward slice of a stack (bounds the dZ stash, see _stack_backward)
+# backward schedule of a stack (see _stack_backward); the environment overrides are tuning knobs for tools/ only
+BWD_SLICE_ROWS = int(os.environ.get("PAPR_BWD_SLICE_ROWS", 8 << 20))    # rows per slice (bounds the dZ stash)
+# dgrad of slice s+1 || weight gradients of slice s on two streams.  OFF: measured slower on B200 (113.8 vs 110.5 ms per step;
+# the step is power-capped, so running the HBM-bound and the tensor-bound kernel together only lowers the clocks)
+BWD_OVERLAP = os.environ.get("PAPR_BWD_OVERLAP", "0") != "0"
+BWD_DGRAD_CTAS = int(os.environ.get("PAPR_BWD_DGRAD_CTAS", 88))  # SMs given to the dgrad stack kernel while both run
+BWD_WGRAD_CTAS = int(os.environ.get("PAPR_BWD_WGRAD_CTAS", 60))  # ... and to the weight-gradient kernel
+_SIDE_STREAMS = {}
+
+
+def _side_stream(dev):
+    key = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _SIDE_STREAMS[key]
 
 
 def _stack_forward_fused(x, weights, biases, slope, n_in0, save, last_f32, images=None):
@@ -361,12 +376,17 @@ def _stack_backward(dz, inputs, bits_list, weights, slope, g_bias_last, in_valid
     gbs[-1] = g_bias_last
     if FUSE_STACKS and not skip_layers and n_layers <= 8 and all(w.shape[0] == 256 for w in weights[:-1]):
         # dgrad of the whole stack in one launch per slice of rows; the per-layer dZ tiles it stashes feed the weight-gradient
-        # launches and are dropped before the next slice starts, so at most BWD_SLICE_ROWS rows of dZ stash (512 B per row
-        # and layer) are alive next to the forward stash -- at 800x800 (two slices) that is ~130 GB of peak instead of ~155 GB.
+        # launches of that slice.  The two are software-pipelined over the slices on two streams: the dgrad of slice s+1
+        # (bound by the HBM WRITE rate of its dZ stash, ~3.9 TB/s) runs on BWD_DGRAD_CTAS SMs while the weight gradients of
+        # slice s (bound by HBM reads) run on the other BWD_WGRAD_CTAS SMs, so the tensor pipe and both HBM directions are
+        # busy at once.  Two sets of dZ buffers alternate, so at most 2 x BWD_SLICE_ROWS rows of dZ stash (512 B per row
+        # and layer) are alive next to the forward stash.
         dev = weights[0].device
         rows_pad = dz.rows_pad
         n_slices = max(1, -(-rows_pad // BWD_SLICE_ROWS))
         per = -(-(rows_pad // 128) // n_slices) * 128
+        n_slices = -(-rows_pad // per)
+        overlap = BWD_OVERLAP and n_slices > 1
         Nd0 = in_pad
         d_in = ops.Blocked(dz.rows, Nd0, dev)
         for i in range(1, n_layers):
@@ -377,12 +397,19 @@ def _stack_backward(dz, inputs, bits_list, weights, slope, g_bias_last, in_valid
                 ops.pack_weight(weights[i], weights[i].shape[1] if i > 0 else in_pad, (weights[i].shape[0] + 15) // 16 * 16,
                                 transpose=True, replicas=ops.WEIGHT_REPLICAS) for i in range(n_layers)]
         K0 = (weights[-1].shape[0] + 15) // 16 * 16
-        for r0 in range(0, rows_pad, per):
+        main = torch.cuda.current_stream(dev)
+        side = _side_stream(dev) if overlap else main
+        sets = [[ops.Blocked(per, weights[i].shape[1], dev) for i in range(1, n_layers)] for _ in range(2 if overlap else 1)]
+        consumed = [None] * len(sets)        # event: the weight gradients have read this set of dZ buffers
+        for si, r0 in enumerate(range(0, rows_pad, per)):
             r1 = min(r0 + per, rows_pad)
+            bufs = sets[si % len(sets)]
+            if consumed[si % len(sets)] is not None:
+                main.wait_event(consumed[si % len(sets)])
             layers, dzs = [], [dz.rows_view(r0, r1)]
             for i in range(n_layers - 1, -1, -1):
                 Nd = weights[i].shape[1] if i > 0 else in_pad
-                ob = ops.Blocked(r1 - r0, Nd, dev) if i > 0 else d_in.rows_view(r0, r1)
+                ob = bufs[i - 1].rows_view(0, r1 - r0) if i > 0 else d_in.rows_view(r0, r1)
                 spec = dict(w_image=imgs[i], N=Nd, out_blocked=ob)
                 if i > 0:
                     spec["colsum"] = gbs[i - 1]
@@ -390,15 +417,26 @@ def _stack_backward(dz, inputs, bits_list, weights, slope, g_bias_last, in_valid
                         spec["sign_bits_in"] = bits_list[i - 1][r0:r1]
                 layers.append(spec)
                 dzs.append(ob)
-            ops.stack_bf16(dzs[0], K0, layers, slope=slope or 0.0)
-            for i in range(n_layers - 1, -1, -1):
-                n_out, n_in = weights[i].shape
-                dzi, xi = dzs[n_layers - 1 - i], inputs[i].rows_view(r0, r1)
-                if n_out < 128:
-                    ops.wgrad_bf16(xi, dzi, gWs[i], n_in, n_out, transpose_out=True)
-                else:
-                    ops.wgrad_bf16(dzi, xi, gWs[i], n_out, n_in)
+            ops.stack_bf16(dzs[0], K0, layers, slope=slope or 0.0, max_ctas=BWD_DGRAD_CTAS if overlap else 0)
+            if overlap:
+                produced = torch.cuda.Event()
+                produced.record(main)
+                side.wait_event(produced)
+            with torch.cuda.stream(side):
+                for i in range(n_layers - 1, -1, -1):
+                    n_out, n_in = weights[i].shape
+                    dzi, xi = dzs[n_layers - 1 - i], inputs[i].rows_view(r0, r1)
+                    cap = BWD_WGRAD_CTAS if overlap else 0
+                    if n_out < 128:
+                        ops.wgrad_bf16(xi, dzi, gWs[i], n_in, n_out, transpose_out=True, max_ctas=cap)
+                    else:
+                        ops.wgrad_bf16(dzi, xi, gWs[i], n_out, n_in, max_ctas=cap)
+                if overlap:
+                    consumed[si % len(sets)] = torch.cuda.Event()
+                    consumed[si % len(sets)].record(side)
             del layers, dzs
+        if overlap:
+            main.wait_stream(side)
         return d_in, gWs, gbs
     d_in_extra = None          # fp32 gradient reaching the stack input through skip connections
     for i in range(n_layers - 1, -1, -1):

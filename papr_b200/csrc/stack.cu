@@ -53,7 +53,7 @@ struct StackLayerDev {
 struct StackParams {
     const uint8_t *x;          // tile-blocked input [rows, kblk0*64]
     int64_t n_tiles;
-    int n_layers, kblk0, stages, any_stash, store_depth;
+    int n_layers, kblk0, stages, any_stash, store_depth, dbg_ring;
     float slope;
     long long *trace;          // debug: per-job clock stamps of cluster 0 (null in production)
     StackLayerDev L[kStkMaxLayers];
@@ -150,8 +150,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kStkThreads, 1) stac
                             mbar_wait(&st_ready[s], sj & 1);
                             const int64_t tile = 4 * q + 2 * s + rank;
                             if (tile < p.n_tiles) {
+                                const int64_t dtile = p.dbg_ring ? tile % p.dbg_ring : tile;
                                 for (int g = 0; g < ng; ++g) {
-                                    bulk_s2g(out + ((size_t)tile * ng + g) * kBlockBytes, act + s * kSlotBytes + g * kBlockBytes, kBlockBytes);
+                                    bulk_s2g(out + ((size_t)dtile * ng + g) * kBlockBytes, act + s * kSlotBytes + g * kBlockBytes, kBlockBytes);
                                     bulk_commit();
                                     if (p.store_depth > 1) bulk_wait_read<1>(); else bulk_wait_read<0>();
                                 }
@@ -417,6 +418,12 @@ extern "C" void papr_debug_stack_trace(long long *buf) { g_stack_trace = buf; }
 extern "C" int papr_stack_bf16(const void *x, int K0, const papr_stack_layer *layers, int n_layers, int64_t rows, float slope,
                                void *stream)
 {
+    return papr_stack_bf16_ex(x, K0, layers, n_layers, rows, slope, 0, stream);
+}
+
+extern "C" int papr_stack_bf16_ex(const void *x, int K0, const papr_stack_layer *layers, int n_layers, int64_t rows, float slope,
+                                  int max_ctas, void *stream)
+{
     using namespace papr;
     if (!x || !layers || n_layers < 1 || n_layers > kStkMaxLayers) return PAPR_ERR_INVALID_ARGUMENT;
     if (rows <= 0 || rows % kTileRows || K0 < 16 || K0 > 256 || K0 % 16) return PAPR_ERR_INVALID_ARGUMENT;
@@ -425,6 +432,7 @@ extern "C" int papr_stack_bf16(const void *x, int K0, const papr_stack_layer *la
     p.any_stash = 0;
     { static int depth = -1; if (depth < 0) { const char *e = getenv("PAPR_STACK_STORE_DEPTH"); depth = e ? atoi(e) : 2; } p.store_depth = depth; }
     p.trace = g_stack_trace;
+    { static int ring = -1; if (ring < 0) { const char *e = getenv("PAPR_DBG_STACK_RING"); ring = e ? atoi(e) : 0; } p.dbg_ring = ring; }
     int K = K0;
     for (int l = 0; l < n_layers; ++l) {
         const papr_stack_layer &h = layers[l];
@@ -455,7 +463,9 @@ extern "C" int papr_stack_bf16(const void *x, int K0, const papr_stack_layer *la
     static SmemAttrOnce once1;
     PAPR_CUDA_TRY(ensure_dyn_smem(once1, stack_kernel<false>, kStkMaxSmem));
     const int64_t n_quads = (p.n_tiles + 3) / 4;
-    const int grid = (int)(2 * (n_quads < kNumSMs / 2 ? n_quads : kNumSMs / 2));
+    int grid = (int)(2 * (n_quads < kNumSMs / 2 ? n_quads : kNumSMs / 2));
+    { static int cap = -1; if (cap < 0) { const char *e = getenv("PAPR_DBG_STACK_GRID"); cap = e ? atoi(e) : 0; } if (cap > 0 && grid > cap) grid = cap; }
+    if (max_ctas >= 2 && grid > max_ctas) grid = max_ctas & ~1;        // CTA pairs: leave the other SMs to a concurrent kernel
     if (slope == 0.f) stack_kernel<true><<<grid, kStkThreads, smem, (cudaStream_t)stream>>>(p);
     else stack_kernel<false><<<grid, kStkThreads, smem, (cudaStream_t)stream>>>(p);
     return check_launch();

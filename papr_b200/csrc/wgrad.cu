@@ -7,6 +7,7 @@
 // whole a_width x b_width fp32 product in TMEM (up to 2 x 256 columns = all 512) for the entire kernel; only at the
 // end is it drained once and added atomically into the fp32 gradient.
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 namespace papr {
 
@@ -125,6 +126,12 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const WgradParams 
 extern "C" int papr_wgrad_bf16(const void *a_blocked, int a_cols, const void *b_blocked, int b_cols, float *c, int64_t ldc,
                                int a_valid, int b_valid, int transpose_out, int64_t rows, void *stream)
 {
+    return papr_wgrad_bf16_ex(a_blocked, a_cols, b_blocked, b_cols, c, ldc, a_valid, b_valid, transpose_out, rows, 0, stream);
+}
+
+extern "C" int papr_wgrad_bf16_ex(const void *a_blocked, int a_cols, const void *b_blocked, int b_cols, float *c, int64_t ldc,
+                                  int a_valid, int b_valid, int transpose_out, int64_t rows, int max_ctas, void *stream)
+{
     using namespace papr;
     if (!a_blocked || !b_blocked || !c) return PAPR_ERR_INVALID_ARGUMENT;
     if (rows <= 0 || rows % kTileRows || a_cols % 64 || b_cols % 64 || a_cols <= 0 || b_cols <= 0) return PAPR_ERR_INVALID_ARGUMENT;
@@ -144,7 +151,9 @@ extern "C" int papr_wgrad_bf16(const void *a_blocked, int a_cols, const void *b_
     const int smem = 1024 + p.stages * stage_bytes + 1024;
     static SmemAttrOnce once;
     PAPR_CUDA_TRY(ensure_dyn_smem(once, wgrad_kernel, 232448));
-    const int grid = (int)(p.n_units < kNumSMs ? p.n_units : kNumSMs);
+    int grid = (int)(p.n_units < kNumSMs ? p.n_units : kNumSMs);
+    { static int cap = -1; if (cap < 0) { const char *e = getenv("PAPR_DBG_WGRAD_GRID"); cap = e ? atoi(e) : 0; } if (cap > 0 && grid > cap) grid = cap; }
+    if (max_ctas >= 1 && grid > max_ctas) grid = max_ctas;
     wgrad_kernel<<<grid, kWgThreads, smem, (cudaStream_t)stream>>>(p);
     return check_launch();
 }

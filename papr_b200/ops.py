@@ -46,7 +46,7 @@ def call(name, *args, flops=0.0, nbytes=0.0, kernels=1):
         e0.record()
         status = fn(*args, _stream())
         e1.record()
-        STATS.records.append((name, e0, e1, flops, nbytes))
+        STATS.records.append((name.removesuffix("_ex"), e0, e1, flops, nbytes))
     else:
         status = fn(*args, _stream())
     check(status, name)
@@ -303,16 +303,16 @@ def linear_bf16(x, w_image, N, K, bias=None, act=False, slope=0.0, out_blocked=T
     return yb, yf, bits
 
 
-def wgrad_bf16(a, b, out, a_valid, b_valid, transpose_out=False):
-    """out[a,b] += sum_rows A[row,a] B[row,b]  (out fp32, atomically accumulated)."""
+def wgrad_bf16(a, b, out, a_valid, b_valid, transpose_out=False, max_ctas=0):
+    """out[a,b] += sum_rows A[row,a] B[row,b]  (out fp32, atomically accumulated), on at most max_ctas SMs (0 = all)."""
     assert a.rows_pad == b.rows_pad
-    call("papr_wgrad_bf16", a.data_ptr(), a.cols_pad, b.data_ptr(), b.cols_pad, out.data_ptr(), out.stride(0),
-         a_valid, b_valid, int(transpose_out), a.rows_pad, flops=2.0 * a.rows * a_valid * b_valid,
+    call("papr_wgrad_bf16_ex", a.data_ptr(), a.cols_pad, b.data_ptr(), b.cols_pad, out.data_ptr(), out.stride(0),
+         a_valid, b_valid, int(transpose_out), a.rows_pad, int(max_ctas), flops=2.0 * a.rows * a_valid * b_valid,
          nbytes=2.0 * a.rows_pad * (128 * ((a_valid + 127) // 128) + pad_cols(b_valid)))
     return out
 
 
-def stack_bf16(x, K0, layers, slope=0.0):
+def stack_bf16(x, K0, layers, slope=0.0, max_ctas=0):
     """Fused MLP stack (papr_stack_bf16).  `layers`: list of dicts with keys w_image, N and optionally bias, act,
     out_blocked (Blocked), out_f32 (tensor), sign_bits_out (tensor), sign_bits_in (tensor), colsum (tensor)."""
     import ctypes
@@ -337,8 +337,8 @@ def stack_bf16(x, K0, layers, slope=0.0):
                                 + (4.0 * l["N"] if l.get("out_f32") is not None else 0)
                                 + (8.0 * pad_cols(l["N"]) / 64 if (l.get("sign_bits_out") is not None or l.get("sign_bits_in") is not None) else 0))
         K = l["N"]
-    call("papr_stack_bf16", x.data_ptr(), K0, ctypes.cast(arr, ctypes.c_void_p), len(layers), x.rows_pad, float(slope),
-         flops=flops, nbytes=nbytes)
+    call("papr_stack_bf16_ex", x.data_ptr(), K0, ctypes.cast(arr, ctypes.c_void_p), len(layers), x.rows_pad, float(slope),
+         int(max_ctas), flops=flops, nbytes=nbytes)
 
 
 # --------------------------------------------------------------------------- bookkeeping / ray generation

@@ -215,3 +215,45 @@ def test_exposure_resampling_and_render_outputs_match_reference_procedure():
     want_depth = (out["attn"].squeeze(-1)[..., :20] * dist).sum(-1)
     assert torch.allclose(out["depth"], want_depth, rtol=1e-5, atol=1e-5) and float(out["depth"].min()) >= 0
     assert float((out["bkg_mask"] - out["attn"][..., 20, 0]).abs().max()) == 0
+
+
+def test_step_pipeline_matches_the_blocking_loop():
+    """papr_b200.staging.StepPipeline: pinned-host batches in, loss + image out one iteration late -- the same numbers as
+    upload / step / loss.item() in line (train.py:163-179)."""
+    from papr_b200.staging import StepPipeline
+    from papr_b200.scene import synthetic_scene
+
+    def run(pipelined):
+        model, cfg = _model()
+        hosts = [{k: v.pin_memory() for k, v in synthetic_scene(24, 32, cfg.dataset.coord_scale, n_views=1, seed=s).items()}
+                 for s in (1, 2, 3, 4)]
+
+        def step(b):
+            model.clear_grad()
+            out = model.last_act(model(b["rays_o"], b["rays_d"], b["c2w"], step=-1))
+            loss = torch.mean((out - b["target"]) ** 2)
+            loss.backward()
+            model.step()
+            return loss.detach().reshape(1), out.detach()
+        res = []
+        if pipelined:
+            pipe = StepPipeline(step, "cuda")
+            for h in hosts:
+                r = pipe.submit(h)
+                if r is not None:
+                    res.append((r[0].clone(), r[1].clone()))
+            r = pipe.flush()
+            res.append((r[0].clone(), r[1].clone()))
+            assert pipe.h2d_bytes == sum(v.numel() * v.element_size() for v in hosts[0].values())
+            assert pipe.d2h_bytes == 4 + 24 * 32 * 3 * 4
+        else:
+            for h in hosts:
+                loss, out = step({k: v.cuda() for k, v in h.items()})
+                res.append((loss.cpu(), out.cpu()))
+        return res
+    a, b = run(False), run(True)
+    assert len(a) == len(b) == 4
+    for (la, oa), (lb, ob) in zip(a, b):
+        # identical kernels in the same order; only float atomics in the gradient accumulation can differ between runs
+        assert abs(float(la) - float(lb)) <= 1e-5 * max(1.0, abs(float(la)))
+        assert (oa - ob).abs().max().item() <= 2e-3
