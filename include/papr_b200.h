@@ -100,7 +100,7 @@ int papr_pack_weight(const float *w, int64_t ld, int src_rows, int src_cols, int
  * One Linear layer, replaces nn.Linear + activation inside models/mlp.py:53-58 (and w_k/w_q of attn.py:217-218):
  *   Y = act(X W^T + bias)    X: tile-blocked bf16 [rows, ceil(K/64)*64];  fp32 accumulation in TMEM.
  * Outputs (any combination): y_blocked tile-blocked bf16 [rows, ceil(N/64)*64]; y_f32 fp32 row-major (ldy);
- * sign_bits_out [rows, ceil(N/64)] u64, bit j of word g = 1 when the pre-activation of column 64g+j has its sign bit clear (> 0, or exactly +0);
+ * sign_bits_out u64 [rows/128][ceil(N/64)][128] (tile, 64-column group, row within the tile), bit j of word g = 1 when the pre-activation of column 64g+j has its sign bit clear (> 0, or exactly +0);
  * colsum[N] += column sums of the bf16 output (bias gradients).
  * Backward use (dgrad): X = dZ, weight image packed with transpose=1, sign_bits_in = the forward layer's sign bits:
  * output column j is multiplied by 1 (bit set) or `slope` (bit clear), i.e. by act'(.) of relu/leakyrelu.
@@ -124,6 +124,11 @@ int papr_wgrad_bf16(const void *a_blocked, int a_cols, const void *b_blocked, in
  * previous slice (HBM-read bound). */
 int papr_wgrad_bf16_ex(const void *a_blocked, int a_cols, const void *b_blocked, int b_cols, float *c, int64_t ldc,
                        int a_valid, int b_valid, int transpose_out, int64_t rows, int max_ctas, void *stream);
+/* The same, plus the bias gradient on the side: a_colsum[a_valid] (fp32, may be NULL) += the column sums of A over all
+ * rows -- with A = dZ that is autograd's `grad_bias = dZ.sum(0)` of the Linear layer (reference models/mlp.py:53), read
+ * from the tiles the kernel streams anyway instead of in the dgrad epilogue. */
+int papr_wgrad_bias_bf16(const void *a_blocked, int a_cols, const void *b_blocked, int b_cols, float *c, int64_t ldc,
+                         int a_valid, int b_valid, int transpose_out, int64_t rows, int max_ctas, float *a_colsum, void *stream);
 
 /*
  * Per-ray CUDA-core stages.  Rows are (ray, candidate) pairs, row = ray*K + k; M = R*K rows, padded to 128.
@@ -196,8 +201,8 @@ typedef struct papr_stack_layer {
     void *out_blocked;            /* tile-blocked bf16 [rows, ceil(N/64)*64] or NULL */
     float *out_f32;               /* fp32 row-major [rows, ld_f32] or NULL */
     int64_t ld_f32;
-    uint64_t *sign_bits_out;      /* [rows, ceil(N/64)] or NULL */
-    const uint64_t *sign_bits_in; /* [rows, ceil(N/64)] or NULL */
+    uint64_t *sign_bits_out;      /* [rows/128][ceil(N/64)][128] or NULL */
+    const uint64_t *sign_bits_in; /* [rows/128][ceil(N/64)][128] or NULL */
     float *colsum;                /* [N] accumulated, or NULL */
     int32_t N;
     int32_t act;                  /* 0 none, 1 relu/leakyrelu(slope) */
@@ -212,6 +217,30 @@ int papr_stack_bf16(const void *x, int K0, const papr_stack_layer *layers, int n
 /* Same, on at most max_ctas SMs (0 = all; rounded down to whole CTA pairs). */
 int papr_stack_bf16_ex(const void *x, int K0, const papr_stack_layer *layers, int n_layers, int64_t rows, float slope,
                        int max_ctas, void *stream);
+
+/*
+ * Stage a12, fused -- the whole backward of one MLP stack in one launch: the dgrad of every layer (as papr_stack_bf16 run
+ * on `dgrad_layers`, which are in dgrad order: the transposed image of the LAST forward layer first; sign_bits_in and
+ * colsum as there) plus every weight gradient gw[i] += dZ_i^T X_i.  Replaces autograd's Linear backward over the
+ * reference models/mlp.py:47-59 loop.  The per-layer dZ tiles are handed from the dgrad CTAs to the weight-gradient CTAs
+ * through `workspace` (kept in L2) instead of being written to and re-read from HBM; only the LAST dgrad layer's
+ * out_blocked (the gradient of the stack input) is written -- out_blocked of the others is ignored.
+ *   dz: tile-blocked bf16 gradient of the stack output, K0 = its valid width (multiple of 16); hidden widths are 256.
+ *   wgrad_layers[i], i in FORWARD order: x_blocked = the input of forward layer i (x_cols wide), gw (n_out, ldw) fp32.
+ *   producer_ctas: SMs given to the dgrad side (0 = default split); workspace: papr_stack_bwd_workspace_bytes() bytes,
+ *   1 KB aligned, reusable by the next call on the same stream.  ReLU / no activation only (slope 0).
+ */
+typedef struct {
+    const void *x_blocked;
+    int x_cols;
+    float *gw;
+    int64_t ldw;
+    int n_out, n_in;
+} papr_wgrad_layer;
+
+int64_t papr_stack_bwd_workspace_bytes(void);
+int papr_stack_bwd_fused(const void *dz, int K0, const papr_stack_layer *dgrad_layers, const papr_wgrad_layer *wgrad_layers,
+                         int n_layers, int64_t rows, int producer_ctas, void *workspace, int64_t workspace_bytes, void *stream);
 
 /*
  * Per-ray query tail -- replaces the query stack's output LayerNorm, w_q, and the part of AttentionLayer that depends

@@ -34,7 +34,10 @@ SIGNATURES = {
     "papr_query_tail_fwd": [_ptr, _ptr, _f32, _f32, _i64, _ptr, _ptr, _ptr, _ptr],
     "papr_query_tail_bwd": [_ptr, _ptr, _ptr, _ptr, _i64, _ptr, _f32, _i64, _ptr, _ptr, _ptr, _ptr],
     "papr_wgrad_bf16": [_ptr, _i32, _ptr, _i32, _ptr, _i64, _i32, _i32, _i32, _i64, _ptr],
+    "papr_stack_bwd_workspace_bytes": [],
+    "papr_stack_bwd_fused": [_ptr, _i32, _ptr, _ptr, _i32, _i64, _i32, _ptr, _i64, _ptr],
     "papr_wgrad_bf16_ex": [_ptr, _i32, _ptr, _i32, _ptr, _i64, _i32, _i32, _i32, _i64, _i32, _ptr],
+    "papr_wgrad_bias_bf16": [_ptr, _i32, _ptr, _i32, _ptr, _i64, _i32, _i32, _i32, _i64, _i32, _ptr, _ptr],
     "papr_adam_step": [_ptr, _ptr, _ptr, _i32, _i64, _ptr, _ptr, _ptr, _ptr, _i32, _f32, _ptr],
     "papr_pack_weight_batch": [_ptr, _i32, _ptr],
     "papr_knn": [_ptr, _i64, _ptr, _i64, _i32, _ptr, _ptr, _ptr],
@@ -49,7 +52,7 @@ SIGNATURES = {
     "papr_unet_convt_gather": [_ptr, _ptr, _i32, _i32, _ptr, _ptr, _i32, _i32, _ptr, _ptr],
     "papr_generate_rays": [_ptr, _i64, _i32, _i32, _f32, _f32, _i32, _i32, _i32, _i32, _f32, _ptr, _ptr, _ptr],
 }
-_RESTYPE = {"papr_status_string": _c.c_char_p, "papr_last_cuda_error": _c.c_char_p}
+_RESTYPE = {"papr_status_string": _c.c_char_p, "papr_last_cuda_error": _c.c_char_p, "papr_stack_bwd_workspace_bytes": _i64}
 
 
 class StackLayer(ctypes.Structure):
@@ -57,6 +60,12 @@ class StackLayer(ctypes.Structure):
     _fields_ = [("w_image", _ptr), ("bias", _ptr), ("out_blocked", _ptr), ("out_f32", _ptr), ("ld_f32", _i64),
                 ("sign_bits_out", _ptr), ("sign_bits_in", _ptr), ("colsum", _ptr), ("N", ctypes.c_int32),
                 ("act", ctypes.c_int32), ("w_replicas", ctypes.c_int32), ("_pad", ctypes.c_int32), ("w_replica_stride", _i64)]
+
+
+class WgradLayer(ctypes.Structure):
+    """papr_wgrad_layer of include/papr_b200.h"""
+    _fields_ = [("x_blocked", _ptr), ("x_cols", ctypes.c_int32), ("gw", _ptr), ("ldw", _i64), ("n_out", ctypes.c_int32),
+                ("n_in", ctypes.c_int32)]
 
 
 class AdamGroup(ctypes.Structure):

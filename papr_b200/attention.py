@@ -290,6 +290,12 @@ BWD_SLICE_ROWS = int(os.environ.get("PAPR_BWD_SLICE_ROWS", 8 << 20))    # rows p
 # dgrad of slice s+1 || weight gradients of slice s on two streams.  OFF: measured slower on B200 (113.8 vs 110.5 ms per step;
 # the step is power-capped, so running the HBM-bound and the tensor-bound kernel together only lowers the clocks)
 BWD_OVERLAP = os.environ.get("PAPR_BWD_OVERLAP", "0") != "0"
+# the whole backward of a stack in one launch, dZ handed over through L2 (papr_stack_bwd_fused); ReLU / linear stacks only
+BWD_FUSED = os.environ.get("PAPR_BWD_FUSED", "0") != "0"
+# bias gradients of the hidden layers from the weight-gradient kernel (idle warps sum the dZ tiles it streams anyway)
+# instead of the dgrad epilogue, where the column sums cost 12% of the kernel
+WGRAD_BIAS = os.environ.get("PAPR_WGRAD_BIAS", "1") != "0"
+BWD_PROD_CTAS = int(os.environ.get("PAPR_BWD_PROD_CTAS", 0))     # SMs on the dgrad side of the fused launch (0 = library default)
 BWD_DGRAD_CTAS = int(os.environ.get("PAPR_BWD_DGRAD_CTAS", 88))  # SMs given to the dgrad stack kernel while both run
 BWD_WGRAD_CTAS = int(os.environ.get("PAPR_BWD_WGRAD_CTAS", 60))  # ... and to the weight-gradient kernel
 _SIDE_STREAMS = {}
@@ -383,10 +389,12 @@ def _stack_backward(dz, inputs, bits_list, weights, slope, g_bias_last, in_valid
         # and layer) are alive next to the forward stash.
         dev = weights[0].device
         rows_pad = dz.rows_pad
-        n_slices = max(1, -(-rows_pad // BWD_SLICE_ROWS))
+        # one launch for everything, dZ handed over through L2: no dZ stash, so no slicing either
+        fused_bwd = BWD_FUSED and n_layers >= 2 and not slope and all(w.shape[1] <= 256 for w in weights)
+        n_slices = 1 if fused_bwd else max(1, -(-rows_pad // BWD_SLICE_ROWS))
         per = -(-(rows_pad // 128) // n_slices) * 128
         n_slices = -(-rows_pad // per)
-        overlap = BWD_OVERLAP and n_slices > 1
+        overlap = BWD_OVERLAP and n_slices > 1 and not fused_bwd
         Nd0 = in_pad
         d_in = ops.Blocked(dz.rows, Nd0, dev)
         for i in range(1, n_layers):
@@ -399,7 +407,8 @@ def _stack_backward(dz, inputs, bits_list, weights, slope, g_bias_last, in_valid
         K0 = (weights[-1].shape[0] + 15) // 16 * 16
         main = torch.cuda.current_stream(dev)
         side = _side_stream(dev) if overlap else main
-        sets = [[ops.Blocked(per, weights[i].shape[1], dev) for i in range(1, n_layers)] for _ in range(2 if overlap else 1)]
+        sets = [[None if fused_bwd else ops.Blocked(per, weights[i].shape[1], dev) for i in range(1, n_layers)]
+                for _ in range(2 if overlap else 1)]
         consumed = [None] * len(sets)        # event: the weight gradients have read this set of dZ buffers
         for si, r0 in enumerate(range(0, rows_pad, per)):
             r1 = min(r0 + per, rows_pad)
@@ -409,14 +418,21 @@ def _stack_backward(dz, inputs, bits_list, weights, slope, g_bias_last, in_valid
             layers, dzs = [], [dz.rows_view(r0, r1)]
             for i in range(n_layers - 1, -1, -1):
                 Nd = weights[i].shape[1] if i > 0 else in_pad
-                ob = bufs[i - 1].rows_view(0, r1 - r0) if i > 0 else d_in.rows_view(r0, r1)
+                ob = (None if fused_bwd else bufs[i - 1].rows_view(0, r1 - r0)) if i > 0 else d_in.rows_view(r0, r1)
                 spec = dict(w_image=imgs[i], N=Nd, out_blocked=ob)
                 if i > 0:
-                    spec["colsum"] = gbs[i - 1]
+                    if fused_bwd or not WGRAD_BIAS:
+                        spec["colsum"] = gbs[i - 1]       # bias gradient in the dgrad epilogue
                     if slope is not None:
                         spec["sign_bits_in"] = bits_list[i - 1][r0:r1]
                 layers.append(spec)
                 dzs.append(ob)
+            if fused_bwd:
+                # one launch: dgrad CTAs hand every dZ tile to weight-gradient CTAs through L2 (csrc/stack_bwd.cu)
+                ops.stack_bwd_fused(dzs[0], K0, layers, [dict(x=inputs[i].rows_view(r0, r1), gw=gWs[i], n_out=weights[i].shape[0],
+                                                               n_in=weights[i].shape[1]) for i in range(n_layers)],
+                                    producer_ctas=BWD_PROD_CTAS)
+                continue
             ops.stack_bf16(dzs[0], K0, layers, slope=slope or 0.0, max_ctas=BWD_DGRAD_CTAS if overlap else 0)
             if overlap:
                 produced = torch.cuda.Event()
@@ -430,7 +446,9 @@ def _stack_backward(dz, inputs, bits_list, weights, slope, g_bias_last, in_valid
                     if n_out < 128:
                         ops.wgrad_bf16(xi, dzi, gWs[i], n_in, n_out, transpose_out=True, max_ctas=cap)
                     else:
-                        ops.wgrad_bf16(dzi, xi, gWs[i], n_out, n_in, max_ctas=cap)
+                        # ... and the bias gradient of a hidden layer: the column sums of the dZ tiles streamed here
+                        ops.wgrad_bf16(dzi, xi, gWs[i], n_out, n_in, max_ctas=cap,
+                                       a_colsum=gbs[i] if (WGRAD_BIAS and i < n_layers - 1) else None)
                 if overlap:
                     consumed[si % len(sets)] = torch.cuda.Event()
                     consumed[si % len(sets)].record(side)

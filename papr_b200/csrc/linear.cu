@@ -26,7 +26,7 @@ struct LinearParams {
     const float *bias;       // [N] or null
     uint8_t *y_blocked;      // blocked bf16 [M, nblk_out*64] or null
     float *y_f32;            // row-major [M, ldy] or null
-    uint64_t *bits_out;      // [M, nblk_out] sign bits of the pre-activation (bit j of word g: column 64g+j > 0) or null
+    uint64_t *bits_out;      // [M/128][nblk_out][128] sign bits of the pre-activation (bit j of word g: column 64g+j > 0) or null
     const uint64_t *bits_in; // dgrad: multiply column j by act'(.) read from these bits, or null
     float *colsum;           // [N] += column sums of the bf16 output (atomic), or null
     const float *addend;     // fp32 row-major [M, ld_add] added to the accumulator before bias/activation, or null
@@ -123,8 +123,8 @@ __global__ void __launch_bounds__(kLinThreads, 1) linear_kernel(const LinearPara
             const int64_t grow = tile * kTileRows + row;
             uint64_t din[2] = {0, 0};
             if (EPI == EPI_MASK) {
-                if (set < ngroups) din[0] = p.bits_in[grow * p.nblk_out + set];
-                if (set + 2 < ngroups) din[1] = p.bits_in[grow * p.nblk_out + set + 2];
+                if (set < ngroups) din[0] = p.bits_in[(tile * p.nblk_out + set) * kTileRows + row];
+                if (set + 2 < ngroups) din[1] = p.bits_in[(tile * p.nblk_out + set + 2) * kTileRows + row];
             }
             mbar_wait(&tfull[acc], (uint32_t)((it >> 1) & 1));
             tc_fence_after();
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(kLinThreads, 1) linear_kernel(const LinearPara
                 uint32_t blo = 0, bhi = 0;
                 epilogue_math<EPI>(v0, bias_s, col0, p.slope, (uint32_t)din[gi], blo);
                 if (second) epilogue_math<EPI>(v1, bias_s, col0 + 32, p.slope, (uint32_t)(din[gi] >> 32), bhi);
-                if (EPI == EPI_BIAS_ACT_BITS) p.bits_out[grow * p.nblk_out + g] = ((uint64_t)bhi << 32) | blo;
+                if (EPI == EPI_BIAS_ACT_BITS) p.bits_out[(tile * p.nblk_out + g) * kTileRows + row] = ((uint64_t)bhi << 32) | blo;
                 if (p.y_f32) {
                     float4 *dst = reinterpret_cast<float4 *>(p.y_f32 + grow * p.ldy + col0);
 #pragma unroll

@@ -18,6 +18,7 @@ struct WgradParams {
     const uint8_t *a;   // blocked bf16 [rows, a_blk*64]
     const uint8_t *b;   // blocked bf16 [rows, b_blk*64]
     float *c;           // fp32 [.., ldc], accumulated atomically
+    float *a_colsum;    // [a_valid] += column sums of A over all rows (the bias gradient when A = dZ), or null
     int64_t n_units;    // half tiles
     int a_blk, b_blk, a_halves, a_used_blk, Nb, ldc, stages, transpose_out, a_valid, b_valid;
 };
@@ -35,7 +36,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const WgradParams 
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        // a stage is free again once its MMAs have completed and -- with a_colsum -- the four summing warps have read it
+        for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], p.a_colsum ? 5 : 1); }
         mbar_init(done, 1);
         fence_barrier_init();
     }
@@ -87,6 +89,34 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const WgradParams 
     } else if (warp >= 4 && has_work) {
         const int ew = warp - 4;
         const int row = ew * 32 + lane;
+        if (p.a_colsum) {
+            // Bias gradient on the side: thread t owns columns 2t, 2t+1 of A and adds them up over the 64 rows of every
+            // stage from the swizzled shared-memory image (a warp reads one 128-byte row per instruction: conflict-free).
+            // The kernel is HBM-bound, these warps are otherwise idle until the drain.
+            const int t = ew * 32 + lane;
+            const bool live = 2 * t < p.a_used_blk * 64;
+            const uint32_t blk_off = (uint32_t)(t >> 5) * kHalfBytes + (uint32_t)(lane & 3) * 4u;
+            const uint32_t chunk = (uint32_t)(lane >> 2);
+            float s0 = 0.f, s1 = 0.f;
+            int s = 0; uint32_t ph = 0;
+            for (int64_t u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+                mbar_wait(&full[s], ph);
+                if (live) {
+                    const uint32_t base = smem_u32(ring + s * stage_bytes) + blk_off;
+#pragma unroll 8
+                    for (uint32_t r = 0; r < 64; ++r) {
+                        uint32_t w2;
+                        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w2) : "r"(base + r * 128u + ((chunk ^ (r & 7u)) << 4)));
+                        s0 += bf16_lo(w2); s1 += bf16_hi(w2);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[s]);
+                if (++s == p.stages) { s = 0; ph ^= 1; }
+            }
+            if (live && 2 * t < p.a_valid) atomicAdd(p.a_colsum + 2 * t, s0);
+            if (live && 2 * t + 1 < p.a_valid) atomicAdd(p.a_colsum + 2 * t + 1, s1);
+        }
         mbar_wait(done, 0);
         tc_fence_after();
         for (int h = 0; h < p.a_halves; ++h) {
@@ -132,12 +162,20 @@ extern "C" int papr_wgrad_bf16(const void *a_blocked, int a_cols, const void *b_
 extern "C" int papr_wgrad_bf16_ex(const void *a_blocked, int a_cols, const void *b_blocked, int b_cols, float *c, int64_t ldc,
                                   int a_valid, int b_valid, int transpose_out, int64_t rows, int max_ctas, void *stream)
 {
+    return papr_wgrad_bias_bf16(a_blocked, a_cols, b_blocked, b_cols, c, ldc, a_valid, b_valid, transpose_out, rows, max_ctas,
+                                nullptr, stream);
+}
+
+extern "C" int papr_wgrad_bias_bf16(const void *a_blocked, int a_cols, const void *b_blocked, int b_cols, float *c, int64_t ldc,
+                                    int a_valid, int b_valid, int transpose_out, int64_t rows, int max_ctas, float *a_colsum,
+                                    void *stream)
+{
     using namespace papr;
     if (!a_blocked || !b_blocked || !c) return PAPR_ERR_INVALID_ARGUMENT;
     if (rows <= 0 || rows % kTileRows || a_cols % 64 || b_cols % 64 || a_cols <= 0 || b_cols <= 0) return PAPR_ERR_INVALID_ARGUMENT;
     if (a_valid < 1 || a_valid > a_cols || a_valid > 256 || b_valid < 1 || b_valid > b_cols || b_valid > 256) return PAPR_ERR_INVALID_ARGUMENT;
     WgradParams p;
-    p.a = (const uint8_t *)a_blocked; p.b = (const uint8_t *)b_blocked; p.c = c;
+    p.a = (const uint8_t *)a_blocked; p.b = (const uint8_t *)b_blocked; p.c = c; p.a_colsum = a_colsum;
     p.n_units = rows / 64;
     p.a_blk = a_cols / 64; p.b_blk = b_cols / 64;
     p.a_halves = (a_valid + 127) / 128;                 // M = 128 per MMA: 1 or 2 row-halves of the product

@@ -36,6 +36,10 @@ class LaunchStats:
 STATS = LaunchStats()
 
 
+# entry points that are variants of one kernel are accounted under one name
+_STAT_NAME = {"papr_wgrad_bf16_ex": "papr_wgrad_bf16", "papr_wgrad_bias_bf16": "papr_wgrad_bf16", "papr_stack_bf16_ex": "papr_stack_bf16"}
+
+
 def call(name, *args, flops=0.0, nbytes=0.0, kernels=1):
     """Invoke one C-ABI entry point on the current stream (the stream pointer is appended).  `kernels`: how many kernels
     the entry point launches (for the launch count bench.py reports)."""
@@ -46,7 +50,7 @@ def call(name, *args, flops=0.0, nbytes=0.0, kernels=1):
         e0.record()
         status = fn(*args, _stream())
         e1.record()
-        STATS.records.append((name.removesuffix("_ex"), e0, e1, flops, nbytes))
+        STATS.records.append((_STAT_NAME.get(name, name), e0, e1, flops, nbytes))
     else:
         status = fn(*args, _stream())
     check(status, name)
@@ -280,6 +284,19 @@ def pack_weight(w, N, K, transpose=False, scale=1.0, replicas=1):
     return img
 
 
+def sign_bits_rowmajor(bits):
+    """Sign-bit words as a (rows_pad, words) tensor indexed [row, 64-column group].  The kernels keep them as
+    [128-row tile][group][row] so that a warp reads / writes 256 contiguous bytes; this is for tests and tools."""
+    rp, ng = bits.shape
+    return bits.view(rp // 128, ng, 128).permute(0, 2, 1).reshape(rp, ng)
+
+
+def sign_bits_from_rowmajor(rm):
+    """Inverse of sign_bits_rowmajor: (rows_pad, words) [row, group] -> the kernels' [tile][group][row] storage."""
+    rp, ng = rm.shape
+    return rm.view(rp // 128, 128, ng).permute(0, 2, 1).contiguous().view(rp, ng)
+
+
 def linear_bf16(x, w_image, N, K, bias=None, act=False, slope=0.0, out_blocked=True, out_f32=False,
                 sign_bits_out=False, sign_bits_in=None, colsum=None, addend=None):
     """Y = act(X W^T + b) on tcgen05 (see papr_linear_bf16).  Returns (Blocked|None, f32|None, bits|None)."""
@@ -303,11 +320,15 @@ def linear_bf16(x, w_image, N, K, bias=None, act=False, slope=0.0, out_blocked=T
     return yb, yf, bits
 
 
-def wgrad_bf16(a, b, out, a_valid, b_valid, transpose_out=False, max_ctas=0):
-    """out[a,b] += sum_rows A[row,a] B[row,b]  (out fp32, atomically accumulated), on at most max_ctas SMs (0 = all)."""
+def wgrad_bf16(a, b, out, a_valid, b_valid, transpose_out=False, max_ctas=0, a_colsum=None):
+    """out[a,b] += sum_rows A[row,a] B[row,b]  (out fp32, atomically accumulated), on at most max_ctas SMs (0 = all);
+    a_colsum (fp32 [a_valid], optional) += sum_rows A[row, :] -- the bias gradient when A is dZ."""
     assert a.rows_pad == b.rows_pad
-    call("papr_wgrad_bf16_ex", a.data_ptr(), a.cols_pad, b.data_ptr(), b.cols_pad, out.data_ptr(), out.stride(0),
-         a_valid, b_valid, int(transpose_out), a.rows_pad, int(max_ctas), flops=2.0 * a.rows * a_valid * b_valid,
+    if a_colsum is not None:
+        assert a_colsum.dtype == torch.float32 and a_colsum.is_contiguous() and a_colsum.numel() >= a_valid
+    call("papr_wgrad_bias_bf16", a.data_ptr(), a.cols_pad, b.data_ptr(), b.cols_pad, out.data_ptr(), out.stride(0),
+         a_valid, b_valid, int(transpose_out), a.rows_pad, int(max_ctas), a_colsum.data_ptr() if a_colsum is not None else None,
+         flops=2.0 * a.rows * a_valid * b_valid,
          nbytes=2.0 * a.rows_pad * (128 * ((a_valid + 127) // 128) + pad_cols(b_valid)))
     return out
 
@@ -339,6 +360,58 @@ def stack_bf16(x, K0, layers, slope=0.0, max_ctas=0):
         K = l["N"]
     call("papr_stack_bf16_ex", x.data_ptr(), K0, ctypes.cast(arr, ctypes.c_void_p), len(layers), x.rows_pad, float(slope),
          int(max_ctas), flops=flops, nbytes=nbytes)
+
+
+_BWD_WORKSPACE = {}
+
+
+def _bwd_workspace(dev):
+    """The L2-resident hand-over ring of papr_stack_bwd_fused, one per device (launches on a stream reuse it in order)."""
+    key = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
+    if key not in _BWD_WORKSPACE:
+        n = int(lib().papr_stack_bwd_workspace_bytes())
+        _BWD_WORKSPACE[key] = torch.empty(n + 1024, dtype=torch.uint8, device=dev)
+    buf = _BWD_WORKSPACE[key]
+    off = (-buf.data_ptr()) % 1024
+    return buf.data_ptr() + off, buf.numel() - off
+
+
+def stack_bwd_fused(dz, K0, layers, wlayers, producer_ctas=0):
+    """Backward of a whole MLP stack in one launch (papr_stack_bwd_fused).  `layers`: the dgrad layer list of stack_bf16
+    (dgrad order; out_blocked needed for the last one only); `wlayers` in forward order: dicts x (Blocked), gw (fp32
+    (n_out, n_in) tensor), n_out, n_in."""
+    import ctypes
+    from ._lib import StackLayer, WgradLayer
+    n = len(layers)
+    arr = (StackLayer * n)()
+    warr = (WgradLayer * n)()
+    flops, nbytes = 0.0, 2.0 * dz.rows_pad * dz.cols_pad
+    K = K0
+    for i, l in enumerate(layers):
+        def ptr(key):
+            v = l.get(key)
+            return v.data_ptr() if v is not None else None
+        arr[i].w_image = ptr("w_image")
+        arr[i].out_blocked = ptr("out_blocked") if i == n - 1 else None
+        arr[i].sign_bits_in, arr[i].colsum = ptr("sign_bits_in"), ptr("colsum")
+        arr[i].N, arr[i].act = int(l["N"]), 0
+        img = l["w_image"]
+        arr[i].w_replicas = img.shape[0] if img.dim() == 2 else 1
+        arr[i].w_replica_stride = img.stride(0) if img.dim() == 2 else 0
+        flops += 2.0 * dz.rows * l["N"] * K
+        nbytes += dz.rows_pad * (8.0 * pad_cols(l["N"]) / 64 if l.get("sign_bits_in") is not None else 0)
+        K = l["N"]
+    nbytes += 2.0 * dz.rows_pad * pad_cols(layers[-1]["N"])
+    for i, w in enumerate(wlayers):
+        assert w["x"].rows_pad == dz.rows_pad and w["gw"].dtype == torch.float32
+        warr[i].x_blocked, warr[i].x_cols = w["x"].data_ptr(), w["x"].cols_pad
+        warr[i].gw, warr[i].ldw = w["gw"].data_ptr(), w["gw"].stride(0)
+        warr[i].n_out, warr[i].n_in = int(w["n_out"]), int(w["n_in"])
+        flops += 2.0 * dz.rows * w["n_out"] * w["n_in"]
+        nbytes += 2.0 * dz.rows_pad * w["x"].cols_pad
+    ws, ws_bytes = _bwd_workspace(dz.buf.device)
+    call("papr_stack_bwd_fused", dz.data_ptr(), K0, ctypes.cast(arr, ctypes.c_void_p), ctypes.cast(warr, ctypes.c_void_p), n,
+         dz.rows_pad, int(producer_ctas), ws, ws_bytes, flops=flops, nbytes=nbytes, kernels=1)
 
 
 # --------------------------------------------------------------------------- bookkeeping / ray generation

@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_abi_library_exports_every_declared_symbol(built_library):
     from papr_b200 import _lib
     header = open(os.path.join(ROOT, "include", "papr_b200.h")).read()
-    declared = set(re.findall(r"^(?:int|const char \*)\s*(papr_[a-z0-9_]+)\s*\(", header, re.M))
+    declared = set(re.findall(r"^(?:int|int64_t|const char \*)\s*(papr_[a-z0-9_]+)\s*\(", header, re.M))
     assert declared, "no declarations found"
     handle = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:

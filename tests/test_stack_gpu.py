@@ -49,7 +49,7 @@ def test_stack_forward_matches_per_layer(rows, dims):
         a, b = outs[i].to_f32(), ref_out[i].to_f32()
         assert torch.equal(a, b), f"layer {i}: max diff {(a - b).abs().max().item()}"
         if bits_l[i] is not None:
-            assert torch.equal(bits_l[i][:rows], ref_bits[i][:rows]), f"sign bits of layer {i}"
+            assert torch.equal(ops.sign_bits_rowmajor(bits_l[i])[:rows], ops.sign_bits_rowmajor(ref_bits[i])[:rows]), f"sign bits of layer {i}"
     assert torch.equal(layers[-1]["out_f32"][:rows], ref_f32[:rows])
 
 
@@ -129,3 +129,37 @@ def test_stack_inference_mode_at_scale(rows, dims, last_f32):
         assert torch.equal(layers[-1]["out_f32"][:rows], yf[:rows])
     else:
         assert torch.equal(layers[-1]["out_blocked"].to_f32(), yb.to_f32())
+
+
+@pytest.mark.parametrize("rows", [128 * 5, 128 * 300 + 9, 128 * 4 * 74 * 3 + 77])
+@pytest.mark.parametrize("dims,relu", [((117, 256, 256, 256, 256, 256, 256), True), ((142, 256, 256, 256, 256, 256, 256, 256, 32), True),
+                                       ((39, 256, 256), True), ((117, 256, 256, 256), False)])
+def test_fused_backward_matches_two_kernel_backward(rows, dims, relu, monkeypatch):
+    """papr_stack_bwd_fused (dgrad CTAs hand dZ tiles to weight-gradient CTAs through L2, one launch) against the dgrad stack
+    launch followed by per-layer papr_wgrad_bf16: the input gradient bit for bit, weight / bias gradients up to the fp32
+    summation order."""
+    from papr_b200 import attention as A, ops
+    ws, bs = _weights(dims, rows % 1000 + len(dims))
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = ops.Blocked.from_f32(torch.randn(rows, dims[0], device="cuda", generator=g))
+    slope = 0.0 if relu else None
+    in_pad = ops.pad_cols(dims[0])
+    inputs, bits, out = A._stack_forward_fused(x, ws, bs, slope, dims[0], True, False)
+    dz = ops.Blocked.from_f32(torch.randn(rows, dims[-1], device="cuda", generator=g) * 0.1)
+    res = []
+    for fused in (False, True):
+        monkeypatch.setattr(A, "BWD_FUSED", fused)
+        d_in, gWs, gbs = A._stack_backward(dz, inputs, bits, ws, slope, None, dims[0], in_pad)
+        torch.cuda.synchronize()
+        res.append((d_in.to_f32(), gWs, gbs))
+    (d0, gW0, gb0), (d1, gW1, gb1) = res
+    assert torch.equal(d0, d1), f"input gradient: max diff {(d0 - d1).abs().max().item()}"
+    for i, (a, b) in enumerate(zip(gW0, gW1)):
+        scale = max(a.abs().max().item(), 1e-6)
+        assert (a - b).abs().max().item() <= 1e-4 * scale, f"gW[{i}]: {(a - b).abs().max().item()} of {scale}"
+        assert a.abs().max().item() > 0
+    for i, (a, b) in enumerate(zip(gb0, gb1)):
+        if a is None:
+            assert b is None
+            continue
+        assert (a - b).abs().max().item() <= 1e-3 * max(1.0, a.abs().max().item()), f"gb[{i}]"

@@ -45,7 +45,7 @@ def test_linear_forward(N, K, rows):
     assert err < 1e-2, f"bf16 output err {err}"
     # sign bits
     j = torch.arange(N, device="cuda")
-    got_bits = (bits[:rows][:, j // 64] >> (j % 64)) & 1
+    got_bits = (ops.sign_bits_rowmajor(bits)[:rows][:, j // 64] >> (j % 64)) & 1
     safe = pre.abs() > 1e-3
     assert torch.equal(got_bits[safe], (pre > 0).long()[safe])
 
@@ -65,6 +65,7 @@ def test_linear_dgrad_mask_and_colsum():
         # int64 holds bit 63 as the sign bit
         val = (sel[:, :63] << sh[:63]).sum(1) + torch.where(sel[:, 63] > 0, torch.tensor(-2 ** 63, device="cuda"), torch.tensor(0, device="cuda"))
         bits[:rows, wd] = val
+    bits = ops.sign_bits_from_rowmajor(bits)
     img = ops.pack_weight(w, K, N, transpose=True)     # image of W^T: "out" = K, reduction = N
     colsum = torch.zeros(K, device="cuda")
     yb, _, _ = ops.linear_bf16(ops.Blocked.from_f32(dz), img, K, N, sign_bits_in=bits, slope=0.0, colsum=colsum)
@@ -92,6 +93,23 @@ def test_wgrad(A, B, tr, rows):
         want = want.t()
     err = (out - 1.0 - want).abs().max().item()
     assert err < 2e-3 * rows ** 0.5, err
+
+
+@pytest.mark.parametrize("A,rows", [(256, 128 * 301 + 17), (256, 64), (100, 5000)])
+def test_wgrad_bias_column_sums(A, rows):
+    """papr_wgrad_bias_bf16: the weight gradient unchanged and, on the side, the column sums of A (bias gradient)."""
+    from papr_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(A + rows)
+    a = torch.randn(rows, A, device="cuda", generator=g)
+    b = torch.randn(rows, 192, device="cuda", generator=g)
+    ab, bb = ops.Blocked.from_f32(a), ops.Blocked.from_f32(b)
+    ref = ops.wgrad_bf16(ab, bb, torch.zeros((A, 192), device="cuda"), A, 192)
+    cs = torch.full((A,), 2.0, device="cuda")
+    out = ops.wgrad_bf16(ab, bb, torch.zeros((A, 192), device="cuda"), A, 192, a_colsum=cs)
+    torch.cuda.synchronize()
+    assert (out - ref).abs().max().item() <= 1e-4 * max(1.0, ref.abs().max().item())
+    want = _bf(a).double().sum(0)
+    assert (cs.double() - 2.0 - want).abs().max().item() <= 1e-4 * rows ** 0.5 + 1e-3
 
 
 def test_linear_addend_split_k():

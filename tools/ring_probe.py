@@ -55,13 +55,13 @@ def main():
         fl = 2.0 * rows * 256 * 256 * L
         print(f"stack fwd+stash ring={ring} grid={os.environ.get('PAPR_DBG_STACK_GRID', 'all')}: {ms:7.3f} ms  {fl / ms / 1e9:7.1f} TFLOP/s  "
               f"stash {rows * 512.0 * L / ms / 1e6:7.1f} GB/s")
-    elif what == "dgrad":
-        layers = [dict(w_image=imgs[i], N=256, out_blocked=outs[i], sign_bits_in=bits[i], colsum=bs[i]) for i in range(L)]
+    elif what in ("dgrad", "dgrad_nocs"):
+        layers = [dict(w_image=imgs[i], N=256, out_blocked=outs[i], sign_bits_in=bits[i], colsum=bs[i] if what == "dgrad" else None) for i in range(L)]
         for b_ in bits:
             b_.random_()
         ms = timed(lambda: ops.stack_bf16(x, 256, layers))
         fl = 2.0 * rows * 256 * 256 * L
-        print(f"stack dgrad ring={ring} grid={os.environ.get('PAPR_DBG_STACK_GRID', 'all')}: {ms:7.3f} ms  {fl / ms / 1e9:7.1f} TFLOP/s")
+        print(f"stack {what} ring={ring} grid={os.environ.get('PAPR_DBG_STACK_GRID', 'all')}: {ms:7.3f} ms  {fl / ms / 1e9:7.1f} TFLOP/s")
     elif what == "wgrad":
         full = [ops.Blocked(rows, 256, dev) for _ in range(2)]
         gw = torch.zeros(256, 256, device=dev)
