@@ -1197,8 +1197,14 @@ __global__ void __launch_bounds__(kRowThreads, 4) key_score_bwd_kernel(const Sco
         for (int e = 0; e < 8; ++e) { uas += ua[e]; zs[e] = 0.f; }
         const float ua_mean = warp_sum(uas) * (1.f / 256.f);
         float dss = 0.f;
-        uint4 nxt = make_uint4(0, 0, 0, 0);
-        if (!p.h5_f32) nxt = *reinterpret_cast<const uint4 *>(p.h5 + blocked_chunk_offset(ray * p.K, lane, 4));
+        // bf16 rows are fetched three candidates ahead (12 registers): one 512-byte row in flight per warp leaves the kernel
+        // latency-bound at ~2.9 TB/s (ncu: long_scoreboard 12 of 17 stall cycles per issue)
+        uint4 pf0 = make_uint4(0, 0, 0, 0), pf1 = pf0, pf2 = pf0;
+        if (!p.h5_f32) {
+            pf0 = *reinterpret_cast<const uint4 *>(p.h5 + blocked_chunk_offset(ray * p.K, lane, 4));
+            if (1 < p.K) pf1 = *reinterpret_cast<const uint4 *>(p.h5 + blocked_chunk_offset(ray * p.K + 1, lane, 4));
+            if (2 < p.K) pf2 = *reinterpret_cast<const uint4 *>(p.h5 + blocked_chunk_offset(ray * p.K + 2, lane, 4));
+        }
         float ds_n = p.d_score_in[ray * p.K];
         float4 st_n = *reinterpret_cast<const float4 *>(p.stats + ray * p.K * 4);
         for (int k = 0; k < p.K; ++k) {
@@ -1208,8 +1214,9 @@ __global__ void __launch_bounds__(kRowThreads, 4) key_score_bwd_kernel(const Sco
             float h[8], y[8];
             if (p.h5_f32) load_row8(p, row, lane, h);
             else {
-                const uint4 cur = nxt;
-                if (k + 1 < p.K) nxt = *reinterpret_cast<const uint4 *>(p.h5 + blocked_chunk_offset(row + 1, lane, 4));
+                const uint4 cur = pf0;
+                pf0 = pf1; pf1 = pf2;
+                if (k + 3 < p.K) pf2 = *reinterpret_cast<const uint4 *>(p.h5 + blocked_chunk_offset(row + 3, lane, 4));
                 unpack8(cur, h);
             }
             if (k + 1 < p.K) { ds_n = p.d_score_in[row + 1]; st_n = *reinterpret_cast<const float4 *>(p.stats + (row + 1) * 4); }

@@ -66,6 +66,7 @@ struct StackParams {
     const uint8_t *x;          // tile-blocked input [rows, kblk0*64]
     int64_t n_tiles;
     int n_layers, kblk0, stages, any_stash, store_depth, dbg_ring;
+    int share_w;               // 1: one weight stream per layer, read by the jobs of both slots (a stage is released by slot 1)
     float slope;
     long long *trace;          // debug: per-job clock stamps of cluster 0 (null in production)
     StackRing rg;              // used by layers with ring == 1
@@ -169,6 +170,7 @@ __device__ __forceinline__ void stack_body(const StackParams &p, const int64_t c
                                          kBlockBytes, &in_full[s]);
                         }
                         const uint8_t *wsrc = Ld.w + (size_t)(cluster_id % Ld.w_reps) * Ld.w_rep_stride + (size_t)rank * chunk_bytes;
+                        if (p.share_w && s == 1) continue;
                         for (int kc = 0; kc < Ld.kblk; kc += kStageBlocks) {
                             const int nc = min(kStageBlocks, Ld.kblk - kc);
                             mbar_wait(&w_empty[st], ph ^ 1);
@@ -246,6 +248,7 @@ __device__ __forceinline__ void stack_body(const StackParams &p, const int64_t c
                 for (int l = 0; l < L; ++l) {
                     for (int s = 0; s < 2; ++s) {
                         if (l == 0) { mbar_wait(&in_full[s], (uint32_t)(qi & 1)); mbar_arrive_remote(&pin_full[s], 0); }
+                        if (p.share_w && s == 1) continue;
                         for (int kc = 0; kc < p.L[l].kblk; kc += kStageBlocks) {
                             mbar_wait(&w_full[st], ph);
                             mbar_arrive_remote(&pw_full[st], 0);
@@ -266,23 +269,31 @@ __device__ __forceinline__ void stack_body(const StackParams &p, const int64_t c
                 for (int l = 0; l < L; ++l, ++jn) {
                     const int kblk = p.L[l].kblk, k_steps = p.L[l].k_steps;
                     const uint32_t idesc = umma_idesc(256, p.L[l].N, false, false);
+                    const int st_l = st; const uint32_t ph_l = ph;        // share_w: slot 1 walks the layer's weight stages again
 #pragma unroll 1
                     for (int s = 0; s < 2; ++s) {
+                        if (p.share_w) { st = st_l; ph = ph_l; }
                         if (l == 0) {
                             mbar_wait(&in_full[s], (uint32_t)(qi & 1));
                             mbar_wait_cluster(&pin_full[s], (uint32_t)(qi & 1));
                         }
+                        const bool tr_m = p.trace && blockIdx.x == 0 && qi < 4 && lane == 0;
+                        long long t_w = 0, t_a = tr_m ? clock64() : 0;
                         if (jn > 0) mbar_wait_cluster(&act_ready[s], (jn - 1) & 1);
                         tc_fence_after();
-                        if (p.trace && blockIdx.x == 0 && qi < 4 && lane == 0) p.trace[((qi * 16 + l) * 2 + s) * 8 + 0] = clock64();
+                        if (tr_m) { p.trace[((qi * 16 + l) * 2 + s) * 8 + 0] = clock64(); p.trace[2048 + ((qi * 16 + l) * 2 + s) * 2] = clock64() - t_a; }
                         const uint32_t d = tmem_base + s * 256;
                         const uint64_t a_desc0 = umma_desc(a_base + s * kSlotBytes, 16, 1024);
                         uint32_t acc = 0;
 #pragma unroll 1
                         for (int kc = 0; kc < kblk; kc += kStageBlocks) {
-                            mbar_wait(&w_full[st], ph);
-                            mbar_wait_cluster(&pw_full[st], ph);
-                            tc_fence_after();
+                            const long long t_w0 = tr_m ? clock64() : 0;
+                            if (!p.share_w || s == 0) {
+                                mbar_wait(&w_full[st], ph);
+                                mbar_wait_cluster(&pw_full[st], ph);
+                                tc_fence_after();
+                            }
+                            if (tr_m) t_w += clock64() - t_w0;
                             // a K step of 16 bf16 = 32 B = +2 in the descriptor's address field; a 64-wide block = 16 KB
                             const uint64_t ad = a_desc0 + (uint64_t)(kc * (kBlockBytes >> 4));
                             const uint64_t bd = umma_desc(ring_base + st * kStageBytes, 16, 1024);
@@ -300,7 +311,7 @@ __device__ __forceinline__ void stack_body(const StackParams &p, const int64_t c
                                         umma2_bf16(d, ad + off, bd + off, idesc, k ? 1u : acc);
                                     }
                                 }
-                                umma2_commit(&w_empty[st]);
+                                if (!p.share_w || s == 1) umma2_commit(&w_empty[st]);
                             }
                             __syncwarp();
                             acc = 1;
@@ -308,7 +319,7 @@ __device__ __forceinline__ void stack_body(const StackParams &p, const int64_t c
                         }
                         if (elect_one()) umma2_commit(&acc_full[s]);
                         __syncwarp();
-                        if (p.trace && blockIdx.x == 0 && qi < 4 && lane == 0) p.trace[((qi * 16 + l) * 2 + s) * 8 + 1] = clock64();
+                        if (tr_m) { p.trace[((qi * 16 + l) * 2 + s) * 8 + 1] = clock64(); p.trace[2048 + ((qi * 16 + l) * 2 + s) * 2 + 1] = t_w; }
                     }
                 }
             }
@@ -355,7 +366,7 @@ __device__ __forceinline__ void stack_body(const StackParams &p, const int64_t c
                     const int64_t tile = 4 * q + 2 * s + rank;
                     const bool valid = tile < p.n_tiles;
                     const int64_t grow = tile * kTileRows + row;
-                    const bool tr = p.trace && blockIdx.x < 2 && tq < 4 && ew == 0 && lane == 0;
+                    const bool tr = p.trace && blockIdx.x == 0 && tq < 4 && ew == 0 && lane == 0;
                     const uint64_t din = din_next;
                     {
                         int ln = l + s;
@@ -370,6 +381,7 @@ __device__ __forceinline__ void stack_body(const StackParams &p, const int64_t c
                         const uint32_t blk_s = blk0_s + (uint32_t)s * kSlotBytes;
                         const uint32_t taddr = tmem_base + lane_base + s * 256 + g * 64;
                         if (sj > 0 && to_act) mbar_wait(&st_done[s], (sj - 1) & 1);      // the writer has read this slot's last stashed tile
+                        if (tr) p.trace[((tq * 16 + l) * 2 + s) * 8 + 7] = clock64();
                         uint64_t dout = 0;
                         if (fast) {
                             // hidden layer, all 64 columns live: TMEM -> math -> bf16 -> this row's eight 16-byte chunks
@@ -437,7 +449,9 @@ __device__ __forceinline__ void stack_body(const StackParams &p, const int64_t c
                             }
                         }
                         if (Ld.bits_out && valid) Ld.bits_out[(tile * ngroups + g) * kTileRows + row] = dout;
+                        if (tr) p.trace[((tq * 16 + l) * 2 + s) * 8 + 5] = clock64();
                         if (to_act) fence_proxy_async();      // generic-proxy tile writes -> visible to tcgen05.mma / TMA store
+                        if (tr) p.trace[((tq * 16 + l) * 2 + s) * 8 + 6] = clock64();
                         if (to_act && Ld.colsum) {
                             asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
                             if (valid) {
@@ -492,6 +506,7 @@ static inline int fill_stack_params(StackParams &p, const void *x, int K0, const
     { static int depth = -1; if (depth < 0) { const char *e = getenv("PAPR_STACK_STORE_DEPTH"); depth = e ? atoi(e) : 2; } p.store_depth = depth; }
     p.trace = nullptr;
     p.dbg_ring = 0;
+    { static int v = -1; if (v < 0) { const char *e = getenv("PAPR_STACK_SHARE_W"); v = e ? atoi(e) : 0; } p.share_w = v; }
     p.rg.base = nullptr; p.rg.full = nullptr; p.rg.freed = nullptr; p.rg.slots = 1;
     int K = K0;
     for (int l = 0; l < n_layers; ++l) {

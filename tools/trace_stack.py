@@ -28,4 +28,17 @@ for q in range(2):
     for l in range(L):
         for s in range(2):
             r = [int(v) - t0 if int(v) else -1 for v in t[q, l, s]]
-            print(f"{q} {l} {s} | {r[0]:7d} {r[1]:7d} | {r[2]:7d} {r[3]:7d} {r[4]:7d} | {r[5]:7d} {r[6]:7d} {r[7]:7d} | waits {int(tw[q, l, s, 0]):5d} mma-issue {int(tw[q, l, s, 1]):5d} commit {int(tc[q, l, s]):5d}")
+            print(f"{q} {l} {s} | {r[0]:7d} {r[1]:7d} | {r[2]:7d} {r[3]:7d} {r[4]:7d} | {r[5]:7d} {r[6]:7d} {r[7]:7d} | issuer waited: tile {int(tw[q, l, s, 0]):5d} weights {int(tw[q, l, s, 1]):5d}")
+# steady state (second quad): job period from accumulator-complete stamps, issuer waits
+done = [int(t[1, l, s, 2]) for l in range(L) for s in range(2)]
+per = [(b - a) for a, b in zip(done[:-1], done[1:])]
+ww = [int(tw[1, l, s, 1]) for l in range(L) for s in range(2)]
+wt = [int(tw[1, l, s, 0]) for l in range(L) for s in range(2)]
+epi = [int(t[1, l, s, 3]) - int(t[1, l, s, 2]) for l in range(L) for s in range(2)]
+stw = [int(t[1, l, s, 7]) - int(t[1, l, s, 2]) for l in range(L) for s in range(2)]
+body = [int(t[1, l, s, 5]) - int(t[1, l, s, 7]) for l in range(L) for s in range(2)]
+fen = [int(t[1, l, s, 6]) - int(t[1, l, s, 5]) for l in range(L) for s in range(2)]
+arr = [int(t[1, l, s, 4]) - int(t[1, l, s, 3]) for l in range(L) for s in range(2)]
+print(f"   epilogue of warp 4: stash-read wait {sum(stw) / len(stw):5.0f}  drain+math+st.shared {sum(body) / len(body):5.0f}  fence.proxy.async {sum(fen) / len(fen):5.0f}  syncwarp+arrive {sum(arr) / len(arr):5.0f}")
+print(f"SUMMARY stash={int(stash)} nsplit={os.environ.get('PAPR_STACK_NSPLIT', '1')} share_w={os.environ.get('PAPR_STACK_SHARE_W', '0')} epi={os.environ.get('PAPR_DBG_STACK_EPI', '0')}: "
+      f"cycles/job {sum(per) / len(per):6.0f}  epilogue {sum(epi) / len(epi):6.0f}  issuer waits: tile {sum(wt) / len(wt):5.0f} weights {sum(ww) / len(ww):5.0f}  kernel {ms:.3f} ms")
