@@ -149,16 +149,26 @@ def view_grids(rays_o, rays_d, points, eps, G=None):
     none = ~ok.any(1, keepdim=True)
     hmin = torch.where(none, torch.full_like(hmin, -1.0), hmin)
     hmax = torch.where(none, torch.full_like(hmax, 1.0), hmax)
-    span = (hmax - hmin).clamp_min(1e-3)
-    gmin = hmin - 0.02 * span
-    cell = (span * 1.04) / G
-    icell = 1.0 / cell
     # points in every view's frame
     v = points.unsqueeze(0) - rays_o.unsqueeze(1)                         # (N,P,3): the kernel's v = p - o, rounded once
     vn2 = torch.addcmul(torch.addcmul(v[..., 0] * v[..., 0], v[..., 1], v[..., 1]), v[..., 2], v[..., 2])
     pw = torch.einsum("npj,nij->npi", v, B)
     valid = pw[..., 2].abs() > 1e-3 * vn2.sqrt()
     g = pw[..., :2] / torch.where(valid, pw[..., 2], torch.ones_like(pw[..., 2])).unsqueeze(-1)
+    # The grid covers the rays AND the points in front of the camera (at most two ray-spans beyond the rays on each side):
+    # when the rays are a stripe of the frame that misses the object (one rank of a row-sharded render), a grid over the
+    # rays alone would put every point into its semi-infinite border cells and the kernel would degenerate to a full scan.
+    span0 = (hmax - hmin).clamp_min(1e-3)
+    reach = 2.0 * span0.amax(-1, keepdim=True)
+    front = (valid & (pw[..., 2] > 0.25 * vn2.sqrt())).unsqueeze(-1)
+    pmin = torch.where(front, g, inf[:, :1].expand_as(g)).amin(1)
+    pmax = torch.where(front, g, -inf[:, :1].expand_as(g)).amax(1)
+    hmin = torch.maximum(torch.minimum(hmin, pmin), hmin - reach)
+    hmax = torch.minimum(torch.maximum(hmax, pmax), hmax + reach)
+    span = (hmax - hmin).clamp_min(1e-3)
+    gmin = hmin - 0.02 * span
+    cell = (span * 1.04) / G
+    icell = 1.0 / cell
     cxy = ((g - gmin.unsqueeze(1)) * icell.unsqueeze(1)).floor().clamp(0, G - 1)
     cxy = torch.where(valid.unsqueeze(-1), cxy, torch.zeros_like(cxy)).long()
     cid = (torch.arange(N, device=dev).unsqueeze(1) * G + cxy[..., 1]) * G + cxy[..., 0]          # (N,P)
