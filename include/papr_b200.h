@@ -386,6 +386,10 @@ int papr_unet_spread(const papr_spread_args *args, void *stream);
 /* MaxPool2d(2) (unet.py:45-53): unshifted planes at H x W -> planes at floor(H/2) x floor(W/2). */
 int papr_unet_pool(const void *src_planes, const papr_raster *geom, int src_cb0, void *dst_planes, const papr_raster *dst_geom,
                    int ncopies, int cbs, void *stream);
+/* Zeroes the part of a freshly allocated map that no raster kernel writes -- the guard rows and the frame of padding pixels
+ * of each (shifted) copy -- in place of a memset of the whole buffer; the producer of the map writes every interior pixel.
+ * (The zero padding is what nn.Conv2d(padding=1) of reference models/unet.py:20-33 adds.) */
+int papr_unet_zero_border(void *planes, const papr_raster *geom, int ncopies, int cbs, void *stream);
 /*
  * ConvTranspose2d(kernel 2, stride 2) (unet.py:60-76) = a 1x1 GEMM to 4*cout channels ordered (a, b, co) followed by this
  * pixel shuffle (+ bias, + the F.pad offset of unet.py:70-74); the gather is its inverse for the backward pass (colsum: the

@@ -49,6 +49,7 @@ SIGNATURES = {
     "papr_unet_spread": [_ptr, _ptr],
     "papr_unet_pool": [_ptr, _ptr, _i32, _ptr, _ptr, _i32, _i32, _ptr],
     "papr_unet_convt_scatter": [_ptr, _ptr, _i32, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _ptr],
+    "papr_unet_zero_border": [_ptr, _ptr, _i32, _i32, _ptr],
     "papr_unet_convt_gather": [_ptr, _ptr, _i32, _i32, _ptr, _ptr, _i32, _i32, _ptr, _ptr],
     "papr_generate_rays": [_ptr, _i64, _i32, _i32, _f32, _f32, _i32, _i32, _i32, _i32, _f32, _ptr, _ptr, _ptr],
 }

@@ -23,17 +23,22 @@ class Planes:
     """A feature map of one image in the pixel-plane layout: uint8 (copies, planes of 64 channels, rows, 128)."""
 
     def __init__(self, H, W, C, copies, device, zero=True):
+        """zero: True = memset the whole buffer; "border" = zero only what no raster kernel writes; False = leave as is."""
         self.H, self.W, self.C, self.copies = H, W, C, copies
         self.cbs = (C + 63) // 64
         self.Wp = (W + 2 + 7) // 8 * 8
         self.L = ((H + 2) * self.Wp + 127) // 128 * 128
         self.G0 = (self.Wp + 8 + 127) // 128 * 128
         self.S = self.G0 + self.L + self.G0
-        alloc = torch.zeros if zero else torch.empty
+        alloc = torch.zeros if zero is True else torch.empty
         self.buf = alloc((copies, self.cbs, self.S, 128), dtype=torch.uint8, device=device)
         self.plane_bytes = self.S * 128
         self.copy_bytes = self.cbs * self.plane_bytes
         self.n_tiles = self.L // 128
+        if zero == "border":
+            # the producer of this map writes EVERY interior pixel of every channel block: only the guard rows and the
+            # padding frame need zeros (papr_unet_zero_border), 3% of the bytes a full memset would write
+            ops.call("papr_unet_zero_border", self.ptr(), _ref(self.raster()), copies, self.cbs, nbytes=0.03 * self.buf.numel())
 
     def ptr(self, copy=0, cb=0, row=0):
         return self.buf.data_ptr() + copy * self.copy_bytes + cb * self.plane_bytes + row * 128
@@ -230,20 +235,20 @@ def unet_forward_image(x_hwc, p, W, gamma, beta, keep):
     H, Wd, Cin = x_hwc.shape
     dev = x_hwc.device
     H2, W2, H3, W3 = H // 2, Wd // 2, H // 4, Wd // 4
-    P0 = Planes(H, Wd, 64, 3, dev)
+    P0 = Planes(H, Wd, 64, 3, dev, zero="border")
     ops.call("papr_unet_pack_input", x_hwc.data_ptr(), x_hwc.stride(1), Cin, gamma.data_ptr() if gamma is not None else None,
              beta.data_ptr() if beta is not None else None, P0.ptr(), _ref(P0.raster()), 3, 1, nbytes=H * Wd * (4.0 * Cin + 384))
-    U2 = Planes(H, Wd, 256, 3, dev)
+    U2 = Planes(H, Wd, 256, 3, dev, zero="border" if (H == 2 * H2 and Wd == 2 * W2) else True)   # odd sizes: the up-sampled half has an unwritten rim
     T = Planes(H, Wd, 128, 1, dev, zero=False)
     _conv(P0, P0.ptr(), 1, 9, 1, W.fwd["inc"], W.bias["inc"], True, T)
     _spread(T, 0, 2, dst=U2, dst_cb0=0)
-    P1 = Planes(H2, W2, 128, 3, dev)
+    P1 = Planes(H2, W2, 128, 3, dev, zero="border")
     _pool(U2, 0, 2, P1)
-    U1 = Planes(H2, W2, 512, 3, dev)
+    U1 = Planes(H2, W2, 512, 3, dev, zero="border" if (H2 == 2 * H3 and W2 == 2 * W3) else True)
     T = Planes(H2, W2, 256, 1, dev, zero=False)
     _conv(P1, P1.ptr(), 2, 9, 1, W.fwd["down1"], W.bias["down1"], True, T)
     _spread(T, 0, 4, dst=U1, dst_cb0=0)
-    P2 = Planes(H3, W3, 256, 3, dev)
+    P2 = Planes(H3, W3, 256, 3, dev, zero="border")
     _pool(U1, 0, 4, P2)
     X3 = Planes(H3, W3, 512, 1, dev, zero=False)
     _conv(P2, P2.ptr(), 4, 9, 1, W.fwd["down2"], W.bias["down2"], True, X3)
@@ -275,7 +280,7 @@ def unet_backward_image(d_rgb, p, W, saved, Cin, need_input_grad):
     dev = d_rgb.device
     g = {}
     d_rgb = d_rgb.contiguous()
-    dO = Planes(H, Wd, 128, 1, dev)
+    dO = Planes(H, Wd, 128, 1, dev, zero="border")
     ops.call("papr_unet_pack_input", d_rgb.data_ptr(), d_rgb.stride(1), 3, None, None, dO.ptr(), _ref(dO.raster()), 1, 2,
              nbytes=H * Wd * (12.0 + 256))
     # outc (1x1)
@@ -283,7 +288,7 @@ def unet_backward_image(d_rgb, p, W, saved, Cin, need_input_grad):
     g["outc.b"] = d_rgb.sum((0, 1))
     T = Planes(H, Wd, 256, 1, dev, zero=False)
     _conv(dO, dO.ptr(), 1, 1, 1, W.bwd["outc"], None, False, T)
-    dZ = Planes(H, Wd, 128, 3, dev)
+    dZ = Planes(H, Wd, 128, 3, dev, zero="border")
     g["up2c.b"] = torch.zeros(128, device=dev)
     _spread(T, 0, 2, dst=dZ, mask=Y2, colsum=g["up2c.b"])
     # up2.conv (256 -> 128)
@@ -298,7 +303,7 @@ def unet_backward_image(d_rgb, p, W, saved, Cin, need_input_grad):
     g["up2t.w"] = _gemm_wgrad(Q, 512, Y1, 256).reshape(2, 2, 128, 256).permute(3, 2, 0, 1)
     T2 = Planes(H2, W2, 512, 1, dev, zero=False)
     _conv(Q, Q.ptr(), 8, 1, 1, W.bwd["up2t"], None, False, T2)
-    dZ = Planes(H2, W2, 256, 3, dev)
+    dZ = Planes(H2, W2, 256, 3, dev, zero="border")
     g["up1c.b"] = torch.zeros(256, device=dev)
     _spread(T2, 0, 4, dst=dZ, mask=Y1, colsum=g["up1c.b"])
     # up1.conv (512 -> 256)
@@ -312,21 +317,21 @@ def unet_backward_image(d_rgb, p, W, saved, Cin, need_input_grad):
     g["up1t.w"] = _gemm_wgrad(Q, 1024, X3, 512).reshape(2, 2, 256, 512).permute(3, 2, 0, 1)
     T3 = Planes(H3, W3, 512, 1, dev, zero=False)
     _conv(Q, Q.ptr(), 16, 1, 1, W.bwd["up1t"], None, False, T3)
-    dZ = Planes(H3, W3, 512, 3, dev)
+    dZ = Planes(H3, W3, 512, 3, dev, zero="border")
     g["down2.b"] = torch.zeros(512, device=dev)
     _spread(T3, 0, 8, dst=dZ, mask=X3, colsum=g["down2.b"])
     # down2.conv (256 -> 512) and the pool in front of it
     g["down2.w"] = _conv_wgrad(dZ, P2, 512, 256)
     Tp = Planes(H3, W3, 256, 1, dev, zero=False)
     _conv(dZ, dZ.ptr(), 8, 9, -1, W.bwd["down2"], None, False, Tp)
-    dZ = Planes(H2, W2, 256, 3, dev)
+    dZ = Planes(H2, W2, 256, 3, dev, zero="border")
     g["down1.b"] = torch.zeros(256, device=dev)
     _spread(T2, 0, 4, dst=dZ, pool_grad=Tp, pool_ref=U1, pool_ref_cb0=0, mask=U1, mask_cb0=0, colsum=g["down1.b"])
     # down1.conv (128 -> 256) and its pool
     g["down1.w"] = _conv_wgrad(dZ, P1, 256, 128)
     Tp = Planes(H2, W2, 128, 1, dev, zero=False)
     _conv(dZ, dZ.ptr(), 4, 9, -1, W.bwd["down1"], None, False, Tp)
-    dZ = Planes(H, Wd, 128, 3, dev)
+    dZ = Planes(H, Wd, 128, 3, dev, zero="border")
     g["inc.b"] = torch.zeros(128, device=dev)
     _spread(dSkip1, 0, 2, dst=dZ, pool_grad=Tp, pool_ref=U2, pool_ref_cb0=0, mask=U2, mask_cb0=0, colsum=g["inc.b"])
     # inc (Cin -> 128)

@@ -10,6 +10,16 @@ from papr_b200.config import make_config
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def _poisoned_allocator():
+    """Fresh `torch.empty` memory is NaN (bf16 0xFFFF) for every test in this file: the feature maps are allocated without a
+    memset and only their padding frame is zeroed (papr_unet_zero_border), so anything a kernel relies on but nobody wrote
+    shows up as NaN instead of passing on zero-initialised pages."""
+    poison = torch.full((1 << 28,), 0xFF, dtype=torch.uint8, device="cuda")
+    del poison
+    yield
+
+
 def _unet(affine_layer=-1, seed=0):
     from papr_b200.renderer import SmallUNet
     torch.manual_seed(seed)

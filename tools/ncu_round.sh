@@ -10,4 +10,4 @@ HW=400 WARM=1 RENDER=1 timeout 900 ncu --set full --clock-control none --import-
     -k regex:"stack_kernel|wgrad_kernel|select_grid|conv_kernel|conv_wgrad" -c 24 -o gpurun_out/prof_main_${TAG} python tools/profile_step.py > gpurun_out/ncu_${TAG}_b.log 2>&1
 timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --profile-from-start off \
     -k regex:"stack_kernel|wgrad_kernel|linear_kernel|conv_kernel|conv_wgrad" --csv --log-file gpurun_out/traffic_${TAG}.csv env RENDER=0 python tools/profile_step.py > gpurun_out/ncu_${TAG}_c.log 2>&1
-tail -1 gpurun_out/ncu_${TAG}_a.log gpurun_out/ncu_${TAG}_b.log gpurun_out/ncu_${TAG}_c.log
+tail -n 1 gpurun_out/ncu_${TAG}_a.log gpurun_out/ncu_${TAG}_b.log gpurun_out/ncu_${TAG}_c.log || true
