@@ -17,6 +17,7 @@ reference : the CPU oracle (oracle/papr_oracle.py, a pinned restatement of the r
 Prints ONE JSON line.
 """
 import argparse
+import gc
 import json
 import os
 import statistics
@@ -409,6 +410,8 @@ def main():
         bucket[0] = None
         torch.cuda.empty_cache()
         for tag in ("c4", "c5"):
+            gc.collect()                    # the previous leg's model sits in reference cycles (closures): free it first
+            torch.cuda.empty_cache()
             try:
                 extra[tag] = run_caterpillar(tag, dev, rank, world, build_model, timed, min(steps, 3))
             except Exception as e:          # extra legs must not take the headline down

@@ -778,7 +778,15 @@ class ProximityAttention(nn.Module):
                 per_row *= 6
             need = N * H * W * K * per_row
             if need > 0.8 * free:
-                ray_chunk = max(4096, int(0.4 * free / (K * per_row)) // 128 * 128)
+                # Equal chunks sized from the device's TOTAL memory, so that every step of a run allocates the same block
+                # sizes (a chunk size that follows the momentary free memory makes the caching allocator free and
+                # re-allocate segments every step: 24 cudaMalloc + 57 synchronising cudaFree per step, 2.3x slower);
+                # only when even that does not fit is the chunk cut to what is free right now.
+                total = torch.cuda.get_device_properties(rd.device).total_memory
+                n_chunks = max(2, -(-need // int(0.3 * total)))
+                ray_chunk = -(-(-(-(N * H * W) // n_chunks)) // 128) * 128
+                if ray_chunk * K * per_row > 0.5 * free:
+                    ray_chunk = max(4096, int(0.4 * free / (K * per_row)) // 128 * 128)
         with torch.cuda.device(rd.device):      # the C ABI launches on the current device
             if precision != "fp32":
                 self.weight_images.refresh()    # one launch: every weight image of the three stacks, both directions
