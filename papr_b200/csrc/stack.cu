@@ -3,10 +3,10 @@
 
 namespace papr {
 
-template <bool RELU>
+template <bool RELU, bool TRACE = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kStkThreads, 1) stack_kernel(const __grid_constant__ StackParams p)
 {
-    stack_body<RELU>(p, blockIdx.x >> 1, gridDim.x >> 1);
+    stack_body<RELU, TRACE>(p, blockIdx.x >> 1, gridDim.x >> 1);
 }
 
 }  // namespace papr
@@ -39,6 +39,12 @@ extern "C" int papr_stack_bf16_ex(const void *x, int K0, const papr_stack_layer 
     int grid = (int)(2 * (n_quads < kNumSMs / 2 ? n_quads : kNumSMs / 2));
     { static int cap = -1; if (cap < 0) { const char *e = getenv("PAPR_DBG_STACK_GRID"); cap = e ? atoi(e) : 0; } if (cap > 0 && grid > cap) grid = cap; }
     if (max_ctas >= 2 && grid > max_ctas) grid = max_ctas & ~1;        // CTA pairs: leave the other SMs to a concurrent kernel
+    if (p.trace) {       // tools/trace_stack.py: the relu kernel with its clock stamps compiled in
+        static SmemAttrOnce once2;
+        PAPR_CUDA_TRY(ensure_dyn_smem(once2, stack_kernel<true, true>, kStkMaxSmem));
+        stack_kernel<true, true><<<grid, kStkThreads, smem, (cudaStream_t)stream>>>(p);
+        return check_launch();
+    }
     if (slope == 0.f) stack_kernel<true><<<grid, kStkThreads, smem, (cudaStream_t)stream>>>(p);
     else stack_kernel<false><<<grid, kStkThreads, smem, (cudaStream_t)stream>>>(p);
     return check_launch();

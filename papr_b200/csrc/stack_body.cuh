@@ -39,6 +39,8 @@ constexpr int kStkMaxSmem = 232448;
 constexpr int kStageBlocks = 1;                  // 64-wide K blocks per weight-ring stage (4 MMAs each)
 constexpr int kStageBytes = kStageBlocks * kBlockBytes;
 
+constexpr uint32_t kModeOutBlocked = 1, kModeOutF32 = 2, kModeBitsOut = 4, kModeBitsIn = 8, kModeColsum = 16, kModeAct = 32, kModeBias = 64;
+
 struct StackLayerDev {
     const uint8_t *w;          // weight image [kblk][N rows][128 B]
     const float *bias;         // [N] or null
@@ -50,6 +52,7 @@ struct StackLayerDev {
     int64_t ld_f32;
     int64_t w_rep_stride;      // byte distance between identical copies of the weight image
     int N, kblk, k_steps, act, w_reps;
+    uint32_t mode;             // kMode* flags of the fields above | N << 16: all the epilogue loop reads per job
     int ring;                  // 1: the stash of this layer goes to this CTA's slot ring (see StackRing), not to out_blocked
 };
 
@@ -65,7 +68,7 @@ struct StackRing {
 struct StackParams {
     const uint8_t *x;          // tile-blocked input [rows, kblk0*64]
     int64_t n_tiles;
-    int n_layers, kblk0, stages, any_stash, store_depth, dbg_ring;
+    int n_layers, kblk0, stages, any_stash, any_bits_in, store_depth, dbg_ring;
     int share_w;               // 1: one weight stream per layer, read by the jobs of both slots (a stage is released by slot 1)
     float slope;
     long long *trace;          // debug: per-job clock stamps of cluster 0 (null in production)
@@ -109,7 +112,7 @@ __device__ __forceinline__ void bulk_wait_keep(int newest)    // all but the `ne
 }
 
 // The CTA-pair body; `cluster_id` of `n_clusters` pairs walk the tile quads (the launch may hold other CTAs besides).
-template <bool RELU>
+template <bool RELU, bool TRACE = false>
 __device__ __forceinline__ void stack_body(const StackParams &p, const int64_t cluster_id, const int64_t n_clusters)
 {
     extern __shared__ uint8_t smem_raw[];
@@ -277,7 +280,7 @@ __device__ __forceinline__ void stack_body(const StackParams &p, const int64_t c
                             mbar_wait(&in_full[s], (uint32_t)(qi & 1));
                             mbar_wait_cluster(&pin_full[s], (uint32_t)(qi & 1));
                         }
-                        const bool tr_m = p.trace && blockIdx.x == 0 && qi < 4 && lane == 0;
+                        const bool tr_m = TRACE && p.trace && blockIdx.x == 0 && qi < 4 && lane == 0;
                         long long t_w = 0, t_a = tr_m ? clock64() : 0;
                         if (jn > 0) mbar_wait_cluster(&act_ready[s], (jn - 1) & 1);
                         tc_fence_after();
@@ -327,60 +330,67 @@ __device__ __forceinline__ void stack_body(const StackParams &p, const int64_t c
     } else if (warp >= 4) {
         // Sixteen epilogue warps drain the jobs in issue order; warp (g, quad) owns 64-column group g of the tile for
         // the TMEM lane quadrant quad (== warp % 4), so one job is four independent 128-thread groups.
+        // The loop around the drain is kept lean on purpose: at 16 warps on 4 schedulers every instruction per job costs four
+        // issue slots, and the epilogue (ncu source view, r02) was issue-bound at ~520 instructions per warp and job of
+        // which 180 were the drain itself -- per-layer facts come as one packed word (StackLayerDev::mode), barrier and
+        // tile addresses are computed once, indices stay 32-bit, the trace stamps are compiled out of the production kernel.
         const int ew = warp - 4;
         const int g = ew >> 2, quad = ew & 3;
         const int row = quad * 32 + lane;
-        const int sthr = row;                                  // thread index within the group
         const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
         const int bar_id = 1 + g;
         const uint32_t blk0_s = smem_u32(act) + (uint32_t)g * kBlockBytes;     // my column block of slot 0 (shared window)
         const uint32_t row_s = (uint32_t)row * 128u, sw = (uint32_t)row & 7u;
         const uint32_t vec0_s = smem_u32(vec_s) + (uint32_t)g * 256u;          // my 64 bias / column-sum entries of layer 0
+        const uint32_t acc_full_a = smem_u32(acc_full), st_done_a = smem_u32(st_done), st_ready_a = smem_u32(st_ready);
+        const uint32_t in_free_a = smem_u32(in_free);
+        const uint32_t act_ready_c = mapa_u32(smem_u32(act_ready), 0);         // the LEADER's barrier, cluster window
+        const uint32_t taddr0 = tmem_base + lane_base + (uint32_t)g * 64u;
+        const uint32_t n_tiles32 = (uint32_t)p.n_tiles;                        // rows < 2^31 * 128 is checked by the host
         uint32_t jn = 0;                 // jobs finished per slot (both slots advance in lockstep)
         uint32_t sj = 0;                 // stash jobs handed to the writer thread so far, per slot
 
-        // activation-derivative bits of the job after the current one are fetched one job ahead
-        auto fetch_bits = [&](int64_t q, int l, int s) -> uint64_t {
-            if (q >= n_quads) return 0;
-            const uint64_t *bi = p.L[l].bits_in;
-            const int ng = (p.L[l].N + 63) >> 6;
-            const int64_t tile = 4 * q + 2 * s + rank;
-            if (!bi || g >= ng || tile >= p.n_tiles) return 0;
-            return __ldg(bi + (tile * ng + g) * kTileRows + row);      // [tile][group][row]: a warp reads 256 contiguous bytes      // [tile][group][row]: a warp reads 256 contiguous bytes
+        // activation-derivative bits of the job after the current one are fetched one job ahead (dgrad launches only)
+        auto fetch_bits = [&](uint32_t tile, int l2) -> uint64_t {
+            const uint32_t m2 = p.L[l2].mode;
+            const uint32_t ng = ((m2 >> 16) + 63u) >> 6;
+            if (!(m2 & kModeBitsIn) || tile >= n_tiles32 || (uint32_t)g >= ng) return 0;
+            return __ldg(p.L[l2].bits_in + (size_t)((tile * ng + (uint32_t)g) * (uint32_t)kTileRows + (uint32_t)row));   // [tile][group][row]
         };
-        uint64_t din_next = fetch_bits(cluster_id, 0, 0);
+        uint64_t din_next = p.any_bits_in ? fetch_bits((uint32_t)(4 * cluster_id) + rank, 0) : 0;
 
         for (int64_t q = cluster_id; q < n_quads; q += n_clusters) {
-            const int64_t tq = (q - cluster_id) / n_clusters;
-            for (int l = 0; l < L; sj += p.L[l].out_blocked ? 1u : 0u, ++l, ++jn) {
-                const StackLayerDev Ld = p.L[l];
-                const int ngroups = (Ld.N + 63) >> 6;
+            const uint32_t tile0 = (uint32_t)(4 * q) + rank;                  // slot 0's tile; slot 1's is tile0 + 2
+            const int64_t tq = TRACE ? (q - cluster_id) / n_clusters : 0;
+            for (int l = 0; l < L; ++l, ++jn) {
+                const uint32_t mode = p.L[l].mode;
+                const int N = (int)(mode >> 16);
+                const int ngroups = (N + 63) >> 6;
                 const bool last = l == L - 1;
-                const bool to_act = !last || Ld.out_blocked != nullptr;
+                const bool stash = (mode & kModeOutBlocked) != 0;
+                const bool to_act = !last || stash;
                 const bool mine = g < ngroups;
-                const bool fast = to_act && !Ld.out_f32 && (g + 1) * 64 <= Ld.N && (RELU || !Ld.bits_in);
-                float *vec = vec_s + l * 256;
+                const bool fast = to_act && !(mode & kModeOutF32) && (g + 1) * 64 <= N && (RELU || !(mode & kModeBitsIn));
                 const uint32_t vec_sa = vec0_s + (uint32_t)l * 1024u;
 #pragma unroll 1
                 for (int s = 0; s < 2; ++s) {
-                    const int64_t tile = 4 * q + 2 * s + rank;
-                    const bool valid = tile < p.n_tiles;
-                    const int64_t grow = tile * kTileRows + row;
-                    const bool tr = p.trace && blockIdx.x == 0 && tq < 4 && ew == 0 && lane == 0;
+                    const uint32_t tile = tile0 + 2u * (uint32_t)s;
+                    const bool valid = tile < n_tiles32;
+                    const bool tr = TRACE && p.trace && blockIdx.x == 0 && tq < 4 && ew == 0 && lane == 0;
                     const uint64_t din = din_next;
-                    {
-                        int ln = l + s;
-                        int64_t qn = q;
-                        if (ln == L) { ln = 0; qn += n_clusters; }
-                        din_next = fetch_bits(qn, ln, s ^ 1);
+                    if (p.any_bits_in) {
+                        // the next job: slot 1 of this layer, or slot 0 of the next layer (of the next quad after the last)
+                        const bool wrap = s == 1 && last;
+                        din_next = fetch_bits(s == 0 ? tile0 + 2u : (wrap ? tile0 + 4u * (uint32_t)n_clusters : tile0),
+                                              s == 0 ? l : (wrap ? 0 : l + 1));
                     }
-                    mbar_wait(&acc_full[s], jn & 1);
+                    mbar_wait_a(acc_full_a + 8u * (uint32_t)s, jn & 1);
                     tc_fence_after();
-                    if (tr) p.trace[((tq * 16 + l) * 2 + s) * 8 + 2 + 3 * rank] = clock64();
+                    if (tr) p.trace[((tq * 16 + l) * 2 + s) * 8 + 2] = clock64();
                     if (mine) {
                         const uint32_t blk_s = blk0_s + (uint32_t)s * kSlotBytes;
-                        const uint32_t taddr = tmem_base + lane_base + s * 256 + g * 64;
-                        if (sj > 0 && to_act) mbar_wait(&st_done[s], (sj - 1) & 1);      // the writer has read this slot's last stashed tile
+                        const uint32_t taddr = taddr0 + (uint32_t)s * 256u;
+                        if (sj > 0 && to_act) mbar_wait_a(st_done_a + 8u * (uint32_t)s, (sj - 1) & 1);   // the writer has read this slot's last stashed tile
                         if (tr) p.trace[((tq * 16 + l) * 2 + s) * 8 + 7] = clock64();
                         uint64_t dout = 0;
                         if (fast) {
@@ -390,18 +400,18 @@ __device__ __forceinline__ void stack_body(const StackParams &p, const int64_t c
                                 uint32_t v[32], w[16];
                                 tmem_ld32(taddr + h * 32, v);
                                 tmem_ld_wait();
-                                if (Ld.bits_in) {
+                                if (mode & kModeBitsIn) {
                                     mask_pack_relu32(v, (uint32_t)(din >> (32 * h)), w);
-                                } else if (RELU && Ld.act) {
+                                } else if (RELU && (mode & kModeAct)) {
                                     uint32_t bits;
-                                    if (Ld.bits_out) bits = bias_relu_pack32<true>(v, vec_sa + h * 128, w);
+                                    if (mode & kModeBitsOut) bits = bias_relu_pack32<true>(v, vec_sa + h * 128, w);
                                     else bits = bias_relu_pack32<false>(v, vec_sa + h * 128, w);
                                     dout |= (uint64_t)bits << (32 * h);
                                 } else {
                                     uint32_t bits = 0;
-                                    if (Ld.bits_out) epilogue_math32<EPI_BIAS_ACT_BITS, RELU>(v, vec_sa + h * 128, p.slope, 0, bits);
-                                    else if (Ld.act) epilogue_math32<EPI_BIAS_ACT, RELU>(v, vec_sa + h * 128, p.slope, 0, bits);
-                                    else if (Ld.bias) epilogue_math32<EPI_BIAS, RELU>(v, vec_sa + h * 128, p.slope, 0, bits);
+                                    if (mode & kModeBitsOut) epilogue_math32<EPI_BIAS_ACT_BITS, RELU>(v, vec_sa + h * 128, p.slope, 0, bits);
+                                    else if (mode & kModeAct) epilogue_math32<EPI_BIAS_ACT, RELU>(v, vec_sa + h * 128, p.slope, 0, bits);
+                                    else if (mode & kModeBias) epilogue_math32<EPI_BIAS, RELU>(v, vec_sa + h * 128, p.slope, 0, bits);
                                     dout |= (uint64_t)bits << (32 * h);
 #pragma unroll
                                     for (int k = 0; k < 16; ++k) w[k] = pack_bf16(__uint_as_float(v[2 * k]), __uint_as_float(v[2 * k + 1]));
@@ -411,10 +421,11 @@ __device__ __forceinline__ void stack_body(const StackParams &p, const int64_t c
                                     sts_v4(blk_s + row_s + ((((uint32_t)(h * 4 + c)) ^ sw) << 4), w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
                             }
                         } else {
+                            const StackLayerDev &Ld = p.L[l];
 #pragma unroll 1
                             for (int h = 0; h < 2; ++h) {
                                 const int col0 = g * 64 + h * 32;
-                                if (col0 >= Ld.N) {
+                                if (col0 >= N) {
                                     if (to_act) {
 #pragma unroll
                                         for (int c = 0; c < 4; ++c) sts_v4(blk_s + row_s + ((((uint32_t)(h * 4 + c)) ^ sw) << 4), 0, 0, 0, 0);
@@ -426,12 +437,13 @@ __device__ __forceinline__ void stack_body(const StackParams &p, const int64_t c
                                 tmem_ld_wait();
                                 uint32_t bits = 0;
                                 const uint32_t dh = (uint32_t)(din >> (32 * h));
-                                if (Ld.bits_in) epilogue_math32<EPI_MASK, RELU>(v, vec_sa + h * 128, p.slope, dh, bits);
-                                else if (Ld.bits_out) epilogue_math32<EPI_BIAS_ACT_BITS, RELU>(v, vec_sa + h * 128, p.slope, 0, bits);
-                                else if (Ld.act) epilogue_math32<EPI_BIAS_ACT, RELU>(v, vec_sa + h * 128, p.slope, 0, bits);
-                                else if (Ld.bias) epilogue_math32<EPI_BIAS, RELU>(v, vec_sa + h * 128, p.slope, 0, bits);
+                                if (mode & kModeBitsIn) epilogue_math32<EPI_MASK, RELU>(v, vec_sa + h * 128, p.slope, dh, bits);
+                                else if (mode & kModeBitsOut) epilogue_math32<EPI_BIAS_ACT_BITS, RELU>(v, vec_sa + h * 128, p.slope, 0, bits);
+                                else if (mode & kModeAct) epilogue_math32<EPI_BIAS_ACT, RELU>(v, vec_sa + h * 128, p.slope, 0, bits);
+                                else if (mode & kModeBias) epilogue_math32<EPI_BIAS, RELU>(v, vec_sa + h * 128, p.slope, 0, bits);
                                 dout |= (uint64_t)bits << (32 * h);
-                                if (Ld.out_f32 && valid) {
+                                if ((mode & kModeOutF32) && valid) {
+                                    const int64_t grow = (int64_t)tile * kTileRows + row;
                                     float4 *dst = reinterpret_cast<float4 *>(Ld.out_f32 + grow * Ld.ld_f32 + col0);
 #pragma unroll
                                     for (int j = 0; j < 8; ++j)
@@ -448,15 +460,17 @@ __device__ __forceinline__ void stack_body(const StackParams &p, const int64_t c
                                 }
                             }
                         }
-                        if (Ld.bits_out && valid) Ld.bits_out[(tile * ngroups + g) * kTileRows + row] = dout;
+                        if ((mode & kModeBitsOut) && valid)
+                            p.L[l].bits_out[(size_t)((tile * (uint32_t)ngroups + (uint32_t)g) * (uint32_t)kTileRows + (uint32_t)row)] = dout;
                         if (tr) p.trace[((tq * 16 + l) * 2 + s) * 8 + 5] = clock64();
                         if (to_act) fence_proxy_async();      // generic-proxy tile writes -> visible to tcgen05.mma / TMA store
                         if (tr) p.trace[((tq * 16 + l) * 2 + s) * 8 + 6] = clock64();
-                        if (to_act && Ld.colsum) {
+                        if (to_act && (mode & kModeColsum)) {
                             asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
                             if (valid) {
                                 // thread (qq, ll) adds up columns 2*ll, 2*ll+1 over rows [32*qq, 32*qq+32) of the bf16 tile
-                                const uint32_t qq = (uint32_t)sthr >> 5, ll = (uint32_t)sthr & 31u;
+                                float *vec = vec_s + l * 256;
+                                const uint32_t qq = (uint32_t)row >> 5, ll = (uint32_t)row & 31u;
                                 const uint32_t cbase = blk_s + qq * 4096u + (ll & 3u) * 4u;
                                 float s0 = 0.f, s1 = 0.f;
 #pragma unroll 8
@@ -470,16 +484,17 @@ __device__ __forceinline__ void stack_body(const StackParams &p, const int64_t c
                             }
                         }
                     }
-                    if (tr) p.trace[((tq * 16 + l) * 2 + s) * 8 + 3 + 3 * rank] = clock64();
+                    if (tr) p.trace[((tq * 16 + l) * 2 + s) * 8 + 3] = clock64();
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) {
-                        if (Ld.out_blocked) mbar_arrive(&st_ready[s]);
-                        if (last) mbar_arrive(&in_free[s]);
-                        if (rank == 0) mbar_arrive(&act_ready[s]); else mbar_arrive_remote(&act_ready[s], 0);
+                        if (stash) mbar_arrive_a(st_ready_a + 8u * (uint32_t)s);
+                        if (last) mbar_arrive_a(in_free_a + 8u * (uint32_t)s);
+                        mbar_arrive_cluster_a(act_ready_c + 8u * (uint32_t)s);
                     }
-                    if (tr) p.trace[((tq * 16 + l) * 2 + s) * 8 + 4 + 3 * rank] = clock64();
+                    if (tr) p.trace[((tq * 16 + l) * 2 + s) * 8 + 4] = clock64();
                 }
+                sj += stash ? 1u : 0u;
             }
         }
         asm volatile("bar.sync 5, 512;" ::: "memory");
@@ -500,9 +515,10 @@ static inline int fill_stack_params(StackParams &p, const void *x, int K0, const
                                     float slope, int *smem_bytes)
 {
     if (!x || !layers || n_layers < 1 || n_layers > kStkMaxLayers) return PAPR_ERR_INVALID_ARGUMENT;
-    if (rows <= 0 || rows % kTileRows || K0 < 16 || K0 > 256 || K0 % 16) return PAPR_ERR_INVALID_ARGUMENT;
+    if (rows <= 0 || rows % kTileRows || rows / kTileRows >= (int64_t)1 << 22 || K0 < 16 || K0 > 256 || K0 % 16) return PAPR_ERR_INVALID_ARGUMENT;
     p.x = (const uint8_t *)x; p.n_tiles = rows / kTileRows; p.n_layers = n_layers; p.kblk0 = (K0 + 63) / 64; p.slope = slope;
     p.any_stash = 0;
+    p.any_bits_in = 0;
     { static int depth = -1; if (depth < 0) { const char *e = getenv("PAPR_STACK_STORE_DEPTH"); depth = e ? atoi(e) : 2; } p.store_depth = depth; }
     p.trace = nullptr;
     p.dbg_ring = 0;
@@ -524,6 +540,10 @@ static inline int fill_stack_params(StackParams &p, const void *x, int K0, const
         d.w = (const uint8_t *)h.w_image; d.bias = h.bias; d.out_blocked = (uint8_t *)h.out_blocked; d.out_f32 = h.out_f32;
         d.bits_out = h.sign_bits_out; d.bits_in = h.sign_bits_in; d.colsum = h.colsum; d.ld_f32 = h.ld_f32;
         d.N = h.N; d.kblk = (K + 63) / 64; d.k_steps = K / 16; d.act = h.act; d.ring = 0;
+        d.mode = (h.out_blocked ? kModeOutBlocked : 0) | (h.out_f32 ? kModeOutF32 : 0) | (h.sign_bits_out ? kModeBitsOut : 0) |
+                 (h.sign_bits_in ? kModeBitsIn : 0) | (h.colsum ? kModeColsum : 0) | (h.act ? kModeAct : 0) | (h.bias ? kModeBias : 0) |
+                 ((uint32_t)h.N << 16);
+        if (h.sign_bits_in) p.any_bits_in = 1;
         d.w_reps = h.w_replicas > 1 ? h.w_replicas : 1; d.w_rep_stride = h.w_replica_stride;
         if (h.out_blocked) p.any_stash = 1;
         K = h.N;

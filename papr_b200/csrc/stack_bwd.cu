@@ -253,7 +253,7 @@ extern "C" int papr_stack_bwd_fused(const void *dz, int K0, const papr_stack_lay
     p.sp.rg.slots = kRingSlots;
     for (int l = 0; l < n_layers; ++l) {
         if (dgrad_layers[l].out_f32 || dgrad_layers[l].bias || dgrad_layers[l].act) return PAPR_ERR_INVALID_ARGUMENT;
-        if (l < n_layers - 1) { p.sp.L[l].ring = 1; p.sp.L[l].out_blocked = p.sp.rg.base; }
+        if (l < n_layers - 1) { p.sp.L[l].ring = 1; p.sp.L[l].out_blocked = p.sp.rg.base; p.sp.L[l].mode |= kModeOutBlocked; }
         else if (!dgrad_layers[l].out_blocked) return PAPR_ERR_INVALID_ARGUMENT;
     }
     p.sp.any_stash = 1;
