@@ -130,24 +130,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
         : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-// 16 columns, for software-pipelined drains: the load is asynchronous until tmem_ld_wait16(v) -- which names the registers
-// as read-write operands, so the compiler can neither read nor move them between the load and the wait
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16])
-{
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait16(uint32_t (&v)[16])
-{
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
-                   "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
-                 :: "memory");
-}
 
 // ------------------------------------------------------------------ tcgen05.mma (bf16 x bf16 -> fp32, cta_group::1)
 // Shared-memory matrix descriptor, SWIZZLE_128B (layout type 2 at bits [61,64)), descriptor version 1 at [46,48).
@@ -324,27 +306,6 @@ __device__ __forceinline__ uint32_t bias_relu_pack32(const uint32_t (&v)[32], ui
     }
     return ~neg;
 }
-// the same for 16 columns (bits 0..15 of the result)
-template <bool BITS>
-__device__ __forceinline__ uint32_t bias_relu_pack16(const uint32_t (&v)[16], uint32_t bias_saddr, uint32_t (&w)[8])
-{
-    uint32_t neg = 0;
-#pragma unroll
-    for (int j4 = 3; j4 >= 0; --j4) {
-        const float4 q = lds_f4(bias_saddr + j4 * 16);
-        const float t0 = __uint_as_float(v[4 * j4]) + q.x, t1 = __uint_as_float(v[4 * j4 + 1]) + q.y;
-        const float t2 = __uint_as_float(v[4 * j4 + 2]) + q.z, t3 = __uint_as_float(v[4 * j4 + 3]) + q.w;
-        if (BITS) {
-            neg = __funnelshift_l(__float_as_uint(t3), neg, 1);
-            neg = __funnelshift_l(__float_as_uint(t2), neg, 1);
-            neg = __funnelshift_l(__float_as_uint(t1), neg, 1);
-            neg = __funnelshift_l(__float_as_uint(t0), neg, 1);
-        }
-        w[2 * j4] = pack_bf16_relu(t0, t1);
-        w[2 * j4 + 1] = pack_bf16_relu(t2, t3);
-    }
-    return (~neg) & 0xffffu;
-}
 __device__ __forceinline__ void sts_v4(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
 {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -359,22 +320,6 @@ __device__ __forceinline__ void mask_pack_relu32(const uint32_t (&v)[32], uint32
     for (int t = 0; t < 8; ++t) sh[t] = din << t;
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-        const int j0 = 2 * k, j1 = 2 * k + 1;
-        const int t0 = 7 - (j0 & 7), m0 = j0 >> 3, t1 = 7 - (j1 & 7), m1 = j1 >> 3;
-        const uint32_t sel = (uint32_t)((8 | m0) * 0x11) | ((uint32_t)((8 | (4 + m1)) * 0x11) << 8);
-        uint32_t mask;
-        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(mask) : "r"(sh[t0]), "r"(sh[t1]), "r"(sel));
-        w[k] = pack_bf16(__uint_as_float(v[j0]), __uint_as_float(v[j1])) & mask;
-    }
-}
-// the same for 16 columns (din: their 16 mask bits)
-__device__ __forceinline__ void mask_pack_relu16(const uint32_t (&v)[16], uint32_t din, uint32_t (&w)[8])
-{
-    uint32_t sh[8];
-#pragma unroll
-    for (int t = 0; t < 8; ++t) sh[t] = din << t;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
         const int j0 = 2 * k, j1 = 2 * k + 1;
         const int t0 = 7 - (j0 & 7), m0 = j0 >> 3, t1 = 7 - (j1 & 7), m1 = j1 >> 3;
         const uint32_t sel = (uint32_t)((8 | m0) * 0x11) | ((uint32_t)((8 | (4 + m1)) * 0x11) << 8);
