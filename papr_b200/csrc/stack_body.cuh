@@ -154,6 +154,11 @@ __device__ __forceinline__ void stack_body(const StackParams &p, const int64_t c
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (TRACE && p.trace && blockIdx.x == 0 && threadIdx.x == 0) {        // SM clock of the launch = cycles / nanoseconds
+        unsigned long long ns;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+        p.trace[4000] = clock64(); p.trace[4001] = (long long)ns;
+    }
 
     if (warp == 0) {
         if (lane == 0) {
@@ -506,6 +511,12 @@ __device__ __forceinline__ void stack_body(const StackParams &p, const int64_t c
 
     tc_fence_before();
     __syncthreads();
+    if (TRACE && p.trace && threadIdx.x == 0) {
+        unsigned long long ns;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+        if (blockIdx.x == 0) { p.trace[4002] = clock64(); p.trace[4003] = (long long)ns; }
+        if (rank == 0 && cluster_id < 80) p.trace[3900 + cluster_id] = (long long)ns;     // when each CTA pair ran out of work
+    }
     cluster_sync_all();
     if (warp == 2) tmem_dealloc2(tmem_base, 512);
 }

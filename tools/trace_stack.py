@@ -3,7 +3,7 @@ import ctypes, os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from papr_b200 import ops
 from papr_b200._lib import lib
-L = int(os.environ.get("LAYERS", 8)); rows = 128 * 4 * 74 * 6
+L = int(os.environ.get("LAYERS", 8)); rows = 128 * 4 * 74 * int(os.environ.get("QUADS", 6))
 torch.manual_seed(0)
 x = ops.Blocked.from_f32(torch.randn(rows, 256, device="cuda"))
 layers = []
@@ -20,6 +20,14 @@ e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 e0.record(); ops.stack_bf16(x, 256, layers); e1.record(); torch.cuda.synchronize()
 fn(None)
 ms = e0.elapsed_time(e1)
+clk = buf.cpu()[4000:4004]
+fin = [int(v) - int(clk[1]) for v in buf.cpu()[3900:3974] if int(v)]
+if fin:
+    fin.sort()
+    print(f"CTA pairs finish (ms after the start of pair 0): first {fin[0] / 1e6:.3f}, median {fin[len(fin) // 2] / 1e6:.3f}, last {fin[-1] / 1e6:.3f} "
+          f"-> the static tile assignment costs {100.0 * (fin[-1] - sum(fin) / len(fin)) / fin[-1]:.1f}% of the launch")
+if int(clk[3]) > int(clk[1]):
+    print(f"SM clock during the launch (CTA 0, clock64 / globaltimer): {(int(clk[2]) - int(clk[0])) / (int(clk[3]) - int(clk[1])):.3f} GHz over {(int(clk[3]) - int(clk[1])) / 1e6:.3f} ms")
 print(f"kernel {ms:.3f} ms for {rows // 128 * L} tile-layers -> {ms * 1e-3 * 1.9e9 / (rows // 128 * L / 148):.0f} cycles/tile-layer/SM (at 1.9 GHz)")
 t = buf.cpu()[:1024].reshape(4, 16, 2, 8); tw = buf.cpu()[2048:2048 + 256].reshape(4, 16, 2, 2); tc = buf.cpu()[3072:3072 + 128].reshape(4, 16, 2)
 t0 = int(t[0, 0, 0, 0])

@@ -1,1 +1,2 @@
-for i in 1 2 3; do for n in 0 1; do echo -n "bits_ilp=$n "; PAPR_STACK_BITS_ILP=$n timeout 100 python tools/ring_probe.py stack | grep -v "^$"; done; done
+export LAYERS=6 REPS=8
+for st in 0 1; do for qd in 85 340; do echo "stash=$st quads per cluster=$qd"; STASH=$st QUADS=$qd timeout 100 python tools/trace_stack.py | grep "SM clock\|CTA pairs\|^kernel"; done; done
