@@ -330,120 +330,9 @@ __device__ __forceinline__ void pe_fill(float x, int L, float *dst)
     }
 }
 
-__device__ __forceinline__ float half_sum(float v)      // sum over the 16 lanes of a half-warp
-{
-    v += __shfl_xor_sync(0xffffffffu, v, 8);
-    v += __shfl_xor_sync(0xffffffffu, v, 4);
-    v += __shfl_xor_sync(0xffffffffu, v, 2);
-    v += __shfl_xor_sync(0xffffffffu, v, 1);
-    return v;
-}
-
-// Each half-warp owns one (ray, candidate) row per iteration: 16 lanes x 8 columns cover the (<=128-wide) key input,
-// one 16-byte chunk per lane; the value input takes one or two chunks per lane.
-__global__ void __launch_bounds__(kRowThreads, 3) attn_prologue_fwd_fast_kernel(const PrologueParams p)
-{
-    __shared__ float pe_s[kRowWarps][2][kMaxDk];
-    __shared__ float geo_s[kRowWarps][32][9];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int hw = lane >> 4, hl = lane & 15;
-    const int S = 1 + 2 * p.L;
-    const int64_t M = p.R * p.K;
-    float *pe = pe_s[warp][hw];
-    const int dpe = 6 * S;
-
-    float a2[8], b2[8];                    // LayerNorm affine terms of this lane's key chunk (columns 8*hl .. 8*hl+7)
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        const int j = hl * 8 + e;
-        a2[e] = (j < p.dk) ? p.a2[j] : 0.f;
-        b2[e] = (j < p.dk) ? p.b2[j] : 0.f;
-    }
-
-    for (int64_t ray = (int64_t)blockIdx.x * kRowWarps + warp; ray < p.R; ray += (int64_t)gridDim.x * kRowWarps) {
-        const int64_t view = ray / p.rays_per_view;
-        int pidx = 0;
-        if (lane < p.K) {
-            float u[3], den;
-            pidx = p.idx[ray * p.K + lane];
-            const Geometry geo = ray_point_geometry(p.points + (size_t)pidx * 3, p.rays_o + view * 3, p.rays_d + ray * 3, p.eps, u, &den);
-#pragma unroll
-            for (int i = 0; i < 9; ++i) geo_s[warp][lane][i] = geo.g[i];
-        }
-        __syncwarp();
-        for (int k0 = 0; k0 < p.K; k0 += 2) {
-            const int k = k0 + hw;
-            const bool active = k < p.K;
-            const int kk = active ? k : k0;
-            const int64_t row = ray * p.K + kk;
-            const int pk = __shfl_sync(0xffffffffu, pidx, kk);
-            if (hl < 9) pe_fill(geo_s[warp][kk][hl], p.L, pe + hl * S);
-            __syncwarp();
-            float sum = 0.f, val[8];
-#pragma unroll
-            for (int m = 0; m < 8; ++m) {
-                const int j = hl + 16 * m;
-                val[m] = (j < p.dk) ? pe[j] : 0.f;
-                sum += val[m];
-            }
-            const float mean = half_sum(sum) / (float)p.dk;
-            float sq = 0.f;
-#pragma unroll
-            for (int m = 0; m < 8; ++m) { const float c = val[m] - mean; if (hl + 16 * m < p.dk) sq += c * c; }
-            const float rstd = 1.f / (sqrtf(half_sum(sq) / (float)(p.dk - 1)) + p.eps);
-            if (active && hl < p.nblk_k * 8) {
-                float f[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const int j = hl * 8 + e;
-                    f[e] = (j < p.dk) ? a2[e] * (pe[j] - mean) * rstd + b2[e] : 0.f;
-                }
-                *reinterpret_cast<uint4 *>(p.kin + blocked_chunk_offset(row, hl, p.nblk_k)) =
-                    make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
-            }
-#pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-                const int c = hl + 16 * cc;
-                if (active && c < p.nblk_v * 8) {
-                    float f[8];
-                    const int j0 = c * 8;
-                    if (j0 + 8 <= dpe) {
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) f[e] = pe[j0 + e + 3 * S];
-                    } else if (j0 >= dpe && j0 + 8 <= p.dv) {
-                        const float *src = p.feats + (size_t)pk * p.F + (j0 - dpe);
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) f[e] = __ldg(src + e);
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            const int j = j0 + e;
-                            float t = 0.f;
-                            if (j < dpe) t = pe[j + 3 * S];
-                            else if (j < p.dv) t = __ldg(p.feats + (size_t)pk * p.F + (j - dpe));
-                            f[e] = t;
-                        }
-                    }
-                    *reinterpret_cast<uint4 *>(p.vin + blocked_chunk_offset(row, c, p.nblk_v)) =
-                        make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
-                }
-            }
-            __syncwarp();
-        }
-    }
-    const int64_t M_pad = (M + 127) / 128 * 128;
-    const int per_row = (p.nblk_k + p.nblk_v) * 8;
-    for (int64_t i = (int64_t)blockIdx.x * kRowThreads + threadIdx.x; i < (M_pad - M) * per_row; i += (int64_t)gridDim.x * kRowThreads) {
-        const int64_t row = M + i / per_row;
-        const int c = (int)(i % per_row);
-        if (c < p.nblk_k * 8) *reinterpret_cast<uint4 *>(p.kin + blocked_chunk_offset(row, c, p.nblk_k)) = make_uint4(0, 0, 0, 0);
-        else *reinterpret_cast<uint4 *>(p.vin + blocked_chunk_offset(row, c - p.nblk_k * 8, p.nblk_v)) = make_uint4(0, 0, 0, 0);
-    }
-}
-
 // One (ray, candidate) row per LANE (the default shape L = 6, F = 64: 117-wide key input, 142-wide value input).  The
-// half-warp-per-row kernel above spends ~280 warp instructions per row because only 9 of 16 lanes build the positional
-// encoding and every column costs shuffles / shared-memory hops; here a lane carries its row in registers (9 sincos,
+// warp-per-ray kernel at the top of this file spends ~400 warp instructions per row (every column costs shuffles /
+// shared-memory hops); here a lane carries its row in registers (9 sincos,
 // double-angle recurrences, one statistics pass, one emitting pass with compile-time column indices): ~55 warp
 // instructions per row.  A warp stages its 32 rows -- 32 x 128 B per 64-column block, already in the tile-blocked
 // swizzle -- in shared memory and copies each 4 KB piece out with fully coalesced 16-byte stores.
@@ -597,137 +486,6 @@ __global__ void __launch_bounds__(kRowThreads, 2) attn_prologue_fwd_rows_kernel(
 #pragma unroll
         for (int c = (DV + 7) >> 3; c < NBV * 8; ++c) put_v(c);
         copy_out(p.vin, NBV);
-    }
-}
-
-__global__ void __launch_bounds__(kRowThreads, 3) attn_prologue_bwd_fast_kernel(const PrologueParams p)
-{
-    __shared__ float pe_s[kRowWarps][2][kMaxDk];      // pe values
-    __shared__ float dpe_s[kRowWarps][2][kMaxDk];     // d pe (LayerNorm backward + value-stack gradient)
-    __shared__ __align__(16) float gv_s[kRowWarps][2][kMaxDv];   // d vin
-    __shared__ float geo_s[kRowWarps][32][9];
-    __shared__ float dx_s[kRowWarps][32][6];          // per candidate: d proj (3), d D (3)
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int hw = lane >> 4, hl = lane & 15;
-    const int S = 1 + 2 * p.L;
-    float *pe = pe_s[warp][hw], *dpe = dpe_s[warp][hw], *gv = gv_s[warp][hw];
-    float *gk = dpe;    // d kin is staged in the d pe buffer: column j is read and then overwritten by the same lane
-    float a2c[8], acc_a2[8], acc_b2[8];
-#pragma unroll
-    for (int m = 0; m < 8; ++m) {
-        a2c[m] = (hl + 16 * m < p.dk) ? p.a2[hl + 16 * m] : 0.f;
-        acc_a2[m] = 0.f; acc_b2[m] = 0.f;
-    }
-    const bool vec_feats = (p.F % 4 == 0);
-
-    for (int64_t ray = (int64_t)blockIdx.x * kRowWarps + warp; ray < p.R; ray += (int64_t)gridDim.x * kRowWarps) {
-        const int64_t view = ray / p.rays_per_view;
-        float u[3] = {0, 0, 0}, den = 1.f;
-        int pidx = 0;
-        if (lane < p.K) {
-            pidx = p.idx[ray * p.K + lane];
-            const Geometry geo = ray_point_geometry(p.points + (size_t)pidx * 3, p.rays_o + view * 3, p.rays_d + ray * 3, p.eps, u, &den);
-#pragma unroll
-            for (int i = 0; i < 9; ++i) geo_s[warp][lane][i] = geo.g[i];
-        }
-        __syncwarp();
-        for (int k0 = 0; k0 < p.K; k0 += 2) {
-            const int k = k0 + hw;
-            const bool active = k < p.K;
-            const int kk = active ? k : k0;
-            const int64_t row = ray * p.K + kk;
-            const int pk = __shfl_sync(0xffffffffu, pidx, kk);
-            if (hl < 9) pe_fill(geo_s[warp][kk][hl], p.L, pe + hl * S);
-            if (hl < p.nblk_k * 8) {
-                float f[8];
-                unpack8(*reinterpret_cast<const uint4 *>(p.dkin + blocked_chunk_offset(row, hl, p.nblk_k)), f);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) gk[hl * 8 + e] = f[e];
-            }
-#pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-                const int c = hl + 16 * cc;
-                if (c < p.nblk_v * 8) {
-                    float f[8];
-                    unpack8(*reinterpret_cast<const uint4 *>(p.dvin + blocked_chunk_offset(row, c, p.nblk_v)), f);
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) gv[c * 8 + e] = f[e];
-                }
-            }
-            __syncwarp();
-            float val[8], sum = 0.f;
-#pragma unroll
-            for (int m = 0; m < 8; ++m) {
-                const int j = hl + 16 * m;
-                val[m] = (j < p.dk) ? pe[j] : 0.f;
-                sum += val[m];
-            }
-            const float mean = half_sum(sum) / (float)p.dk;
-            float sq = 0.f;
-#pragma unroll
-            for (int m = 0; m < 8; ++m) { const float c = val[m] - mean; if (hl + 16 * m < p.dk) sq += c * c; }
-            const float stdv = sqrtf(half_sum(sq) / (float)(p.dk - 1));
-            const float rstd = 1.f / (stdv + p.eps);
-            float z[8], gz[8], s1 = 0.f, s2 = 0.f;
-#pragma unroll
-            for (int m = 0; m < 8; ++m) {
-                const int j = hl + 16 * m;
-                z[m] = 0.f; gz[m] = 0.f;
-                if (j < p.dk) {
-                    z[m] = (val[m] - mean) * rstd;
-                    const float go = gk[j];
-                    if (active) { acc_a2[m] += go * z[m]; acc_b2[m] += go; }
-                    gz[m] = go * a2c[m];
-                    s1 += gz[m]; s2 += gz[m] * z[m];
-                }
-            }
-            s1 = half_sum(s1) / (float)p.dk;
-            s2 = half_sum(s2) / ((float)(p.dk - 1) * stdv);
-#pragma unroll
-            for (int m = 0; m < 8; ++m) {
-                const int j = hl + 16 * m;
-                if (j >= 3 * S && j < p.dk) dpe[j] = rstd * (gz[m] - s1) - z[m] * s2 + gv[j - 3 * S];
-            }
-            __syncwarp();
-            if (active && hl < 6) {
-                const float *pv = pe + (3 + hl) * S;
-                const float *dv = dpe + (3 + hl) * S;
-                float t = dv[0], scale = 1.f;
-                for (int i = 0; i < p.L; ++i) {
-                    t += scale * (dv[1 + 2 * i] * pv[2 + 2 * i] - dv[2 + 2 * i] * pv[1 + 2 * i]);
-                    scale *= 2.f;
-                }
-                dx_s[warp][k][hl] = t;
-            }
-            if (active) {
-                if (vec_feats) {
-                    for (int c = hl; c < p.F / 4; c += 16) {
-                        const float *g4 = gv + 6 * S + c * 4;
-                        red_add_v4(p.g_feats + (size_t)pk * p.F + c * 4, g4[0], g4[1], g4[2], g4[3]);
-                    }
-                } else {
-                    for (int c = hl; c < p.F; c += 16) atomicAdd(p.g_feats + (size_t)pk * p.F + c, gv[6 * S + c]);
-                }
-            }
-            __syncwarp();
-        }
-        if (lane < p.K) {
-            const float *dx = dx_s[warp][lane];
-            const float e0 = dx[0] - dx[3], e1 = dx[1] - dx[4], e2 = dx[2] - dx[5];
-            const float s = (e0 * u[0] + e1 * u[1] + e2 * u[2]) / den;
-            atomicAdd(p.g_points + (size_t)pidx * 3 + 0, dx[3] + u[0] * s);
-            atomicAdd(p.g_points + (size_t)pidx * 3 + 1, dx[4] + u[1] * s);
-            atomicAdd(p.g_points + (size_t)pidx * 3 + 2, dx[5] + u[2] * s);
-        }
-        __syncwarp();
-    }
-#pragma unroll
-    for (int m = 0; m < 8; ++m) {
-        const int j = hl + 16 * m;
-        // both half-warps hold partial sums for the same columns: fold them before the atomics
-        const float sa = acc_a2[m] + __shfl_xor_sync(0xffffffffu, acc_a2[m], 16);
-        const float sb = acc_b2[m] + __shfl_xor_sync(0xffffffffu, acc_b2[m], 16);
-        if (hw == 0 && j < p.dk) { atomicAdd(p.g_a2 + j, sa); atomicAdd(p.g_b2 + j, sb); }
     }
 }
 
@@ -1403,11 +1161,11 @@ extern "C" int papr_attn_prologue_fwd(const float *rays_o, const float *rays_d, 
     p.nblk_k = dk_pad / 64; p.nblk_v = dv_pad / 64; p.eps = eps;
     p.kin = (uint8_t *)kin; p.vin = (uint8_t *)vin; p.kin_f32 = kin_f32; p.vin_f32 = vin_f32;
     if (kin_f32 || vin_f32) attn_prologue_fwd_kernel<<<row_grid(R), kRowThreads, 0, (cudaStream_t)stream>>>(p);
-    else if (!getenv("PAPR_PROLOGUE_HALFWARP") && rows_shape(p, 6, 64)) return launch_prologue_fwd_rows<6, 64>(p, (cudaStream_t)stream);
-    else if (!getenv("PAPR_PROLOGUE_HALFWARP") && rows_shape(p, 4, 64)) return launch_prologue_fwd_rows<4, 64>(p, (cudaStream_t)stream);
-    else if (!getenv("PAPR_PROLOGUE_HALFWARP") && rows_shape(p, 6, 128)) return launch_prologue_fwd_rows<6, 128>(p, (cudaStream_t)stream);
-    else if (!getenv("PAPR_PROLOGUE_HALFWARP") && rows_shape(p, 4, 128)) return launch_prologue_fwd_rows<4, 128>(p, (cudaStream_t)stream);
-    else attn_prologue_fwd_fast_kernel<<<row_grid(R), kRowThreads, 0, (cudaStream_t)stream>>>(p);
+    else if (!getenv("PAPR_PROLOGUE_GENERIC") && rows_shape(p, 6, 64)) return launch_prologue_fwd_rows<6, 64>(p, (cudaStream_t)stream);
+    else if (!getenv("PAPR_PROLOGUE_GENERIC") && rows_shape(p, 4, 64)) return launch_prologue_fwd_rows<4, 64>(p, (cudaStream_t)stream);
+    else if (!getenv("PAPR_PROLOGUE_GENERIC") && rows_shape(p, 6, 128)) return launch_prologue_fwd_rows<6, 128>(p, (cudaStream_t)stream);
+    else if (!getenv("PAPR_PROLOGUE_GENERIC") && rows_shape(p, 4, 128)) return launch_prologue_fwd_rows<4, 128>(p, (cudaStream_t)stream);
+    else attn_prologue_fwd_kernel<<<row_grid(R), kRowThreads, 0, (cudaStream_t)stream>>>(p);      // any other PE order / feature width
     return check_launch();
 }
 
@@ -1428,11 +1186,11 @@ extern "C" int papr_attn_prologue_bwd(const float *rays_o, const float *rays_d, 
     p.dkin = (const uint8_t *)dkin; p.dvin = (const uint8_t *)dvin; p.dkin_f32 = dkin_f32; p.dvin_f32 = dvin_f32;
     p.g_points = g_points; p.g_feats = g_feats; p.g_a2 = g_ln_a; p.g_b2 = g_ln_b;
     if (dkin_f32 || dvin_f32) attn_prologue_bwd_kernel<<<row_grid(R), kRowThreads, 0, (cudaStream_t)stream>>>(p);
-    else if (!getenv("PAPR_PROLOGUE_HALFWARP") && rows_shape(p, 6, 64)) return launch_prologue_bwd_rows<6, 64>(p, (cudaStream_t)stream);
-    else if (!getenv("PAPR_PROLOGUE_HALFWARP") && rows_shape(p, 4, 64)) return launch_prologue_bwd_rows<4, 64>(p, (cudaStream_t)stream);
-    else if (!getenv("PAPR_PROLOGUE_HALFWARP") && rows_shape(p, 6, 128)) return launch_prologue_bwd_rows<6, 128>(p, (cudaStream_t)stream);
-    else if (!getenv("PAPR_PROLOGUE_HALFWARP") && rows_shape(p, 4, 128)) return launch_prologue_bwd_rows<4, 128>(p, (cudaStream_t)stream);
-    else attn_prologue_bwd_fast_kernel<<<row_grid(R), kRowThreads, 0, (cudaStream_t)stream>>>(p);
+    else if (!getenv("PAPR_PROLOGUE_GENERIC") && rows_shape(p, 6, 64)) return launch_prologue_bwd_rows<6, 64>(p, (cudaStream_t)stream);
+    else if (!getenv("PAPR_PROLOGUE_GENERIC") && rows_shape(p, 4, 64)) return launch_prologue_bwd_rows<4, 64>(p, (cudaStream_t)stream);
+    else if (!getenv("PAPR_PROLOGUE_GENERIC") && rows_shape(p, 6, 128)) return launch_prologue_bwd_rows<6, 128>(p, (cudaStream_t)stream);
+    else if (!getenv("PAPR_PROLOGUE_GENERIC") && rows_shape(p, 4, 128)) return launch_prologue_bwd_rows<4, 128>(p, (cudaStream_t)stream);
+    else attn_prologue_bwd_kernel<<<row_grid(R), kRowThreads, 0, (cudaStream_t)stream>>>(p);      // any other PE order / feature width
     return check_launch();
 }
 

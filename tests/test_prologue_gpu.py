@@ -1,4 +1,5 @@
-"""GPU: the three prologue kernel families agree -- exact fp32 (taps), half-warp-per-row bf16, row-per-lane bf16 -- forward
+"""GPU: the prologue kernels agree -- the warp-per-ray kernel with exact fp32 taps, the same kernel on bf16 only, and the
+row-per-lane bf16 kernels -- forward
 (key / value stack inputs: models/model.py:285-310, 396-437; utils.py:232-257; attn.py:39-42) and backward."""
 import os
 import types
@@ -34,11 +35,11 @@ def _case(R=301, K=20, P=700, views=1, seed=0, L=6, F=64):
 
 def _with_env(flag, fn):
     if flag:
-        os.environ["PAPR_PROLOGUE_HALFWARP"] = "1"
+        os.environ["PAPR_PROLOGUE_GENERIC"] = "1"
     try:
         return fn()
     finally:
-        os.environ.pop("PAPR_PROLOGUE_HALFWARP", None)
+        os.environ.pop("PAPR_PROLOGUE_GENERIC", None)
 
 
 @pytest.mark.parametrize("L,F", SHAPES)
@@ -47,7 +48,7 @@ def test_prologue_forward_families_agree(R, views, L, F):
     sh, rays_o, rays_d, points, feats, idx, ln_a, ln_b = _case(R=R, views=views, L=L, F=F)
     _, _, k32, v32 = A._prologue_fwd(sh, rays_o, rays_d, points, feats, idx, ln_a, ln_b, taps=True)
     outs = {}
-    for name, flag in (("halfwarp", True), ("rows", False)):
+    for name, flag in (("generic", True), ("rows", False)):
         kin, vin, _, _ = _with_env(flag, lambda: A._prologue_fwd(sh, rays_o, rays_d, points, feats, idx, ln_a, ln_b))
         outs[name] = (kin.to_f32(sh.M, sh.dk), vin.to_f32(sh.M, sh.dv), kin.to_f32(kin.rows_pad, kin.cols_pad),
                       vin.to_f32(vin.rows_pad, vin.cols_pad))
@@ -59,10 +60,10 @@ def test_prologue_forward_families_agree(R, views, L, F):
         assert float(kfull[sh.M:].abs().sum()) == 0.0 and float(vfull[sh.M:].abs().sum()) == 0.0, name
         assert float(kfull[:, sh.dk:].abs().sum()) == 0.0 and float(vfull[:, sh.dv:].abs().sum()) == 0.0, name
     # the two bf16 kernels differ only where a value sits on a rounding boundary
-    dk = (outs["rows"][0] - outs["halfwarp"][0]).abs()
-    assert float((dk > 0).float().mean()) < 0.02 and float((dk - 8e-3 * outs["rows"][0].abs()).max()) <= 1e-6
+    dk = (outs["rows"][0] - outs["generic"][0]).abs()
+    assert float((dk > 0).float().mean()) < 0.05 and float((dk - 8e-3 * outs["rows"][0].abs()).max()) <= 2e-5
     dpe = 6 * (1 + 2 * L)
-    assert torch.equal(outs["rows"][1][:, dpe:], outs["halfwarp"][1][:, dpe:])       # gathered point features: copies
+    assert torch.equal(outs["rows"][1][:, dpe:], outs["generic"][1][:, dpe:])       # gathered point features: copies
 
 
 @pytest.mark.parametrize("L,F", SHAPES)
@@ -77,7 +78,7 @@ def test_prologue_backward_families_agree(R, views, L, F):
     # reference: the exact fp32 kernel fed with the bf16-rounded gradients the other two read
     ref = A._prologue_bwd(sh, rays_o, rays_d, points, idx, ln_a, None, None,
                           dkin.to_f32(sh.M, sh.dk), dvin.to_f32(sh.M, sh.dv), points.shape[0])
-    for name, flag in (("halfwarp", True), ("rows", False)):
+    for name, flag in (("generic", True), ("rows", False)):
         got = _with_env(flag, lambda: A._prologue_bwd(sh, rays_o, rays_d, points, idx, ln_a, dkin, dvin, None, None, points.shape[0]))
         for what, a, b in zip(("g_points", "g_feats", "g_a2", "g_b2"), got, ref):
             scale = float(b.abs().max())
