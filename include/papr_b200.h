@@ -181,7 +181,8 @@ int papr_blend_bwd(const float *d_fused, const float *d_attn, const float *attn,
 /*
  * Backward of the folded LayerNorm + scaled dot: d_score (M) -> dh5 (M_pad,256) tile-blocked bf16 (+ optional fp32 tap),
  * zsum (R,256) = sum_k d_score * normalised h5 (= d ua), dssum (R) = sum_k d_score (= d cprime),
- * g_bias5 (256) += column sums of dh5.
+ * g_bias5 (256) += column sums of dh5; may be NULL (then papr_wgrad_bias_bf16 of the last key layer produces them and the
+ * bf16-only call walks the rows block by block, 512 contiguous bytes per warp instruction).
  */
 int papr_key_score_bwd(const float *d_score, const void *h5, const float *h5_f32, const float *stats,
                        const float *ua, int64_t R, int K, float eps, void *dh5_blocked, float *dh5_f32,

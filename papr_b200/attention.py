@@ -178,16 +178,18 @@ def _blend_bwd(sh, d_fused, d_attn, attn, sc, influ, idx, v, n_points):
     return dv, d_score, g_influ, g_bv
 
 
-def _key_score_bwd(sh, d_score, h5, h5_32, stats, ua, tap=False):
+def _key_score_bwd(sh, d_score, h5, h5_32, stats, ua, tap=False, want_bias=True):
+    """want_bias=False: g_b5 is left to the weight-gradient kernel of the last key layer (column sums of the dh5 tiles it
+    streams anyway), which lets the bf16 call use the block-major kernel."""
     dev = ua.device
     dh5 = ops.Blocked(sh.M, 256, dev)
     dh5_32 = torch.empty((sh.M, 256), device=dev) if tap else None
     zsum = torch.empty((sh.R, 256), device=dev)
     dssum = torch.empty((sh.R,), device=dev)
-    g_b5 = torch.zeros((256,), device=dev)
+    g_b5 = torch.zeros((256,), device=dev) if want_bias else None
     ops.call("papr_key_score_bwd",
         d_score.data_ptr(), _ptr(h5), _ptr(h5_32), stats.data_ptr(), ua.data_ptr(), sh.R, sh.K, sh.eps,
-        dh5.data_ptr(), _ptr(dh5_32), zsum.data_ptr(), dssum.data_ptr(), g_b5.data_ptr(),
+        dh5.data_ptr(), _ptr(dh5_32), zsum.data_ptr(), dssum.data_ptr(), _ptr(g_b5),
         nbytes=sh.M * (1024.0 + 12) + sh.R * 2048.0)
     return dh5, dh5_32, zsum, dssum, g_b5
 
@@ -374,12 +376,17 @@ def _stack_forward(x, weights, biases, slope, n_in0, save, last_f32=False, skip_
     return inputs, bits_list, out
 
 
-def _stack_backward(dz, inputs, bits_list, weights, slope, g_bias_last, in_valid, in_pad, skip_layers=(), images_t=None):
+def _stack_backward(dz, inputs, bits_list, weights, slope, g_bias_last, in_valid, in_pad, skip_layers=(), images_t=None,
+                    last_bias_from_wgrad=False):
     """Backward of _stack_forward.  dz: Blocked gradient of the last layer's output.  Returns (d_input Blocked,
     [gW], [gb])."""
     n_layers = len(weights)
     gWs, gbs = [None] * n_layers, [None] * n_layers
     gbs[-1] = g_bias_last
+    last_bias_here = last_bias_from_wgrad and g_bias_last is None     # the caller left the last layer's bias gradient to the
+    if last_bias_here:                                                # weight-gradient kernel (column sums of dz)
+        assert weights[-1].shape[0] >= 128, "a narrow last layer runs the weight gradient with swapped operands"
+        gbs[-1] = torch.zeros((weights[-1].shape[0],), device=weights[0].device)
     if FUSE_STACKS and not skip_layers and n_layers <= 8 and all(w.shape[0] == 256 for w in weights[:-1]):
         # dgrad of the whole stack in one launch per slice of rows; the per-layer dZ tiles it stashes feed the weight-gradient
         # launches of that slice.  The two are software-pipelined over the slices on two streams: the dgrad of slice s+1
@@ -390,7 +397,7 @@ def _stack_backward(dz, inputs, bits_list, weights, slope, g_bias_last, in_valid
         dev = weights[0].device
         rows_pad = dz.rows_pad
         # one launch for everything, dZ handed over through L2: no dZ stash, so no slicing either
-        fused_bwd = BWD_FUSED and n_layers >= 2 and not slope and all(w.shape[1] <= 256 for w in weights)
+        fused_bwd = BWD_FUSED and n_layers >= 2 and not slope and all(w.shape[1] <= 256 for w in weights) and not last_bias_here
         n_slices = 1 if fused_bwd else max(1, -(-rows_pad // BWD_SLICE_ROWS))
         per = -(-(rows_pad // 128) // n_slices) * 128
         n_slices = -(-rows_pad // per)
@@ -448,7 +455,7 @@ def _stack_backward(dz, inputs, bits_list, weights, slope, g_bias_last, in_valid
                     else:
                         # ... and the bias gradient of a hidden layer: the column sums of the dZ tiles streamed here
                         ops.wgrad_bf16(dzi, xi, gWs[i], n_out, n_in, max_ctas=cap,
-                                       a_colsum=gbs[i] if (WGRAD_BIAS and i < n_layers - 1) else None)
+                                       a_colsum=gbs[i] if ((WGRAD_BIAS and i < n_layers - 1) or (last_bias_here and i == n_layers - 1)) else None)
                 if overlap:
                     consumed[si % len(sets)] = torch.cuda.Event()
                     consumed[si % len(sets)].record(side)
@@ -466,7 +473,7 @@ def _stack_backward(dz, inputs, bits_list, weights, slope, g_bias_last, in_valid
         if n_out < 128:     # narrow output (value head): swap operands so that M = n_in
             ops.wgrad_bf16(x, dz, gW, n_in, n_out, transpose_out=True)
         else:
-            ops.wgrad_bf16(dz, x, gW, n_out, n_in)
+            ops.wgrad_bf16(dz, x, gW, n_out, n_in, a_colsum=gbs[i] if (last_bias_here and i == n_layers - 1) else None)
         Kd = (n_out + 15) // 16 * 16
         if i in skip_layers:
             ops.wgrad_bf16(dz, inputs[0], gW[:, n_in:], n_out, in_valid)
@@ -601,8 +608,9 @@ class RowAttentionFn(torch.autograd.Function):
         d_attn_c = d_attn.contiguous() if d_attn is not None else None
         dv, d_score, g_influ, g_bv = _blend_bwd(sh, d_fused.contiguous(), d_attn_c, attn, sc, infl, idx, v, P)
         d_vin, gvW, gvb = _stack_backward(dv, v_in, v_bits, vw, sh.v_slope, g_bv, sh.dv, sh.dv_pad, sh.v_skip, images_t=sh.v_images[1])
-        dh5, _, zsum, dssum, g_b5 = _key_score_bwd(sh, d_score, h5, None, stats, ua)
-        d_kin, gkW, gkb = _stack_backward(dh5, k_in, k_bits, kw, sh.k_slope, g_b5, sh.dk, sh.dk_pad, sh.k_skip, images_t=sh.k_images[1])
+        dh5, _, zsum, dssum, g_b5 = _key_score_bwd(sh, d_score, h5, None, stats, ua, want_bias=not WGRAD_BIAS)
+        d_kin, gkW, gkb = _stack_backward(dh5, k_in, k_bits, kw, sh.k_slope, g_b5, sh.dk, sh.dk_pad, sh.k_skip, images_t=sh.k_images[1],
+                                          last_bias_from_wgrad=g_b5 is None)
         g_points, g_feats, g_a, g_b = _prologue_bwd(sh, rays_o, rays_d, pts, idx, ln_a, d_kin, d_vin, None, None, P)
         return (None, None, None, None, g_points, g_feats, g_influ.reshape(-1, 1), zsum, dssum, g_a, g_b, None,
                 *gkW, *gkb, *gvW, *gvb)
