@@ -256,6 +256,19 @@ int papr_query_tail_fwd(const float *q5, const float *w_c, float c_const, float 
 int papr_query_tail_bwd(const float *q5, const float *stats, const float *w_c, const float *dz, int64_t ld_dz,
                         const float *dc, float eps, int64_t R, float *dq5, float *g_wc, float *g_cconst, void *stream);
 
+/*
+ * Query-side prologue: the input of the query stack for R rays (reference models/attn.py:148-176 `embed_q` input:
+ * utils.py:232-242 positional encoding of the ray direction, embed_type 1, then the in-norm of attn.py:30-42 with the
+ * unbiased std), replacing ~10 elementwise / reduction launches over an (R, 3(1+2L)) tensor by one.
+ *   fwd: rays_d (R,3) f32, a2 / b2 (3(1+2L)) -> q (R, 3(1+2L)) f32 = a2 * (pe - mean) / (std + eps) + b2
+ *   bwd: dq (R, 3(1+2L)) f32 -> g_a2 += sum_r dq * z, g_b2 += sum_r dq   (the ray direction is data: no gradient)
+ * L must be 4 or 6 (the PE orders of the shipped configs); PAPR_ERR_INVALID_ARGUMENT otherwise.
+ */
+int papr_query_prologue_fwd(const float *rays_d, const float *a2, const float *b2, int64_t R, int L, float eps, float *q,
+                            void *stream);
+int papr_query_prologue_bwd(const float *rays_d, const float *dq, int64_t R, int L, float eps, float *g_a2, float *g_b2,
+                            void *stream);
+
 
 /*
  * SURVEY section 8(f1) -- replaces the optimiser half of PAPR.step (reference models/model.py:439-446: one

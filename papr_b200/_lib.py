@@ -33,6 +33,8 @@ SIGNATURES = {
     "papr_stack_bf16_ex": [_ptr, _i32, _ptr, _i32, _i64, _f32, _i32, _ptr],
     "papr_query_tail_fwd": [_ptr, _ptr, _f32, _f32, _i64, _ptr, _ptr, _ptr, _ptr],
     "papr_query_tail_bwd": [_ptr, _ptr, _ptr, _ptr, _i64, _ptr, _f32, _i64, _ptr, _ptr, _ptr, _ptr],
+    "papr_query_prologue_fwd": [_ptr, _ptr, _ptr, _i64, _i32, _f32, _ptr, _ptr],
+    "papr_query_prologue_bwd": [_ptr, _ptr, _i64, _i32, _f32, _ptr, _ptr, _ptr],
     "papr_wgrad_bf16": [_ptr, _i32, _ptr, _i32, _ptr, _i64, _i32, _i32, _i32, _i64, _ptr],
     "papr_stack_bwd_workspace_bytes": [],
     "papr_stack_bwd_fused": [_ptr, _i32, _ptr, _ptr, _i32, _i64, _i32, _ptr, _i64, _ptr],

@@ -526,6 +526,34 @@ class _StackBf16Fn(torch.autograd.Function):
         return (dx.to_f32(ctx.rows, ctx.n_in), None, None, None, None, *gWs, *gbs)
 
 
+class _QueryPrologueFn(torch.autograd.Function):
+    """rays_d (R,3) -> the query stack's input a_2 * normalise(pe(rays_d)) + b_2 (R, 3(1+2L)) in one launch
+    (utils.py:232-242, attn.py:30-42); gradients for the affine pair only -- the ray direction is data."""
+
+    @staticmethod
+    def forward(ctx, rays_d, a2, b2, L, eps):
+        R = rays_d.shape[0]
+        rd = rays_d.detach().contiguous()
+        D = 3 * (1 + 2 * L)
+        q = torch.empty((R, D), device=rd.device)
+        ops.call("papr_query_prologue_fwd", rd.data_ptr(), a2.detach().contiguous().data_ptr(), b2.detach().contiguous().data_ptr(),
+                 R, L, float(eps), q.data_ptr(), nbytes=R * (12.0 + 4 * D))
+        ctx.save_for_backward(rd)
+        ctx.L, ctx.eps = L, eps
+        return q
+
+    @staticmethod
+    def backward(ctx, dq):
+        (rd,) = ctx.saved_tensors
+        R = rd.shape[0]
+        D = 3 * (1 + 2 * ctx.L)
+        dq = dq.contiguous()
+        g = torch.zeros((2, D), device=rd.device)
+        ops.call("papr_query_prologue_bwd", rd.data_ptr(), dq.data_ptr(), R, ctx.L, float(ctx.eps), g[0].data_ptr(),
+                 g[1].data_ptr(), nbytes=R * (12.0 + 4 * D))
+        return None, g[0], g[1], None, None
+
+
 class _QueryTailFn(torch.autograd.Function):
     """(q5, A, c0, w_c) -> (ua, w_c . z):  z = normalise(q5);  ua = z A^T + c0."""
 
@@ -657,6 +685,40 @@ class _ScoreBlendFp32Fn(torch.autograd.Function):
         return None, None, dh5, d_v, zsum, dssum, g_influ.reshape(-1, 1)
 
 
+class _ChunkFn(torch.autograd.Function):
+    """One checkpointed chunk of rays.  Forward runs the chunk WITHOUT autograd -- the inference form of every kernel: no
+    layer inputs, sign bits or row statistics are written, the MLP stacks run at their no-stash speed -- and keeps only the
+    chunk's inputs.  Backward runs the chunk again with the backward stash and back-propagates through it at once, so at
+    most one chunk's stash is alive.  (torch.utils.checkpoint would run the first pass in training form and throw the
+    stash away: a third of the first pass's HBM traffic for nothing.)  Gradients of the module's own parameters are
+    accumulated into their .grad by the inner backward, exactly as with a re-entrant torch checkpoint; the gradients of
+    the point cloud tensors are returned to the outer graph."""
+
+    @staticmethod
+    def forward(ctx, module, meta, rays_o, rd, idx, points, feats, influ):
+        ctx.module, ctx.meta = module, meta
+        ctx.save_for_backward(rays_o, rd, idx, points, feats, influ)
+        with torch.no_grad():
+            return module._rows(rays_o, rd, idx, points, feats, influ, *meta)
+
+    @staticmethod
+    def backward(ctx, d_fused, d_attn):
+        rays_o, rd, idx, points, feats, influ = ctx.saved_tensors
+        leaves = []
+        for t, need in zip((points, feats, influ), ctx.needs_input_grad[5:8]):
+            leaves.append(t.detach().requires_grad_(True) if (t is not None and need) else t)
+        with torch.enable_grad():
+            fused, attn = ctx.module._rows(rays_o, rd, idx, *leaves, *ctx.meta)
+            outs, grads = [], []
+            for o, g in ((fused, d_fused), (attn, d_attn)):
+                if g is not None and o.requires_grad:
+                    outs.append(o)
+                    grads.append(g)
+            if outs:
+                torch.autograd.backward(outs, grads)
+        return (None, None, None, None, None) + tuple(t.grad if (t is not None and t.requires_grad) else None for t in leaves)
+
+
 class ProximityAttention(nn.Module):
     """Owns the reference's attention parameters (same state_dict keys) and runs the B200 path."""
 
@@ -702,9 +764,12 @@ class ProximityAttention(nn.Module):
     # ------------------------------------------------------------------ per-ray query side (5% of the work)
     def query_terms(self, rays_d_flat, precision):
         """(R,3) -> ua (R,256), c' (R): the query stack, w_q and the fold of w_k / key outnorm (see module doc)."""
-        q = posenc(rays_d_flat, self.L)
         fq = self.embed.embed_q
-        q = fq.innorm(q)
+        if (precision != "fp32" and self.L in (4, 6) and hasattr(fq.innorm, "a_2") and rays_d_flat.is_cuda
+                and not os.environ.get("PAPR_QUERY_TORCH")):
+            q = _QueryPrologueFn.apply(rays_d_flat, fq.innorm.a_2, fq.innorm.b_2, self.L, fq.innorm.eps)
+        else:
+            q = fq.innorm(posenc(rays_d_flat, self.L))
         lins = fq.mlp.linears()
         if precision == "fp32":
             q = _mlp_fp32(fq.mlp, q)
@@ -800,16 +865,15 @@ class ProximityAttention(nn.Module):
                 self.weight_images.refresh()    # one launch: every weight image of the three stacks, both directions
             if not ray_chunk or (N == 1 and H * W <= ray_chunk) or (N * H * W <= ray_chunk):
                 return self._rows(rays_o, rd.reshape(-1, 3), idx.reshape(-1, K), points, feats, influ, precision, N, H * W)
-            from torch.utils.checkpoint import checkpoint
             fused, attn = [], []
             for v in range(N):
                 for r0 in range(0, H * W, ray_chunk):
                     r1 = min(r0 + ray_chunk, H * W)
-                    args = (rays_o[v:v + 1], rd[v, r0:r1], idx[v, r0:r1], points, feats, influ, precision, 1, r1 - r0)
+                    args = (rays_o[v:v + 1], rd[v, r0:r1], idx[v, r0:r1], points, feats, influ)
                     if grad:
-                        f, a = checkpoint(self._rows, *args, use_reentrant=False)
+                        f, a = _ChunkFn.apply(self, (precision, 1, r1 - r0), *args)
                     else:
-                        f, a = self._rows(*args)
+                        f, a = self._rows(*args, precision, 1, r1 - r0)
                     fused.append(f)
                     attn.append(a)
             return torch.cat(fused), torch.cat(attn)

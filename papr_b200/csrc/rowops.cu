@@ -716,7 +716,10 @@ __device__ __forceinline__ void load_row8(const ScoreParams &p, int64_t row, int
 // The warp-per-ray form spends three 5-stage shuffle reductions per row; here a lane owns its row's 256 columns (staged
 // through shared memory so the tile is read with coalesced 16-byte loads) and needs none.  Sums are taken about the row's
 // first element c0: mean = c0 + S/256, sum (h-mean)^2 = Q - S^2/256, ua.(h-mean) = T - (mean-c0) * sum(ua).
-__global__ void __launch_bounds__(kRowThreads, 1) score_rows_kernel(const ScoreParams p)
+// Twelve warps per CTA, one CTA per SM: a warp stages 16 KB, so they fill 192 KB of shared memory (with eight the kernel was
+// latency-bound -- ncu r02: 12.5% warps active, 52% of the DRAM roof; 12 warps: 2.95 -> 2.71 ms for score + blend at 800x800).
+constexpr int kScoreRowsWarps = 12;
+__global__ void __launch_bounds__(kScoreRowsWarps * 32, 1) score_rows_kernel(const ScoreParams p)
 {
     extern __shared__ __align__(16) uint8_t rows_stage[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -724,7 +727,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) score_rows_kernel(const ScoreP
     const uint32_t my = wst + (uint32_t)lane * 128u;
     const uint32_t sw = (uint32_t)lane & 7u;
     const int64_t M = p.R * p.K, M_pad = (M + 127) / 128 * 128;
-    for (int64_t row0 = ((int64_t)blockIdx.x * kRowWarps + warp) * 32; row0 < M_pad; row0 += (int64_t)gridDim.x * kRowWarps * 32) {
+    for (int64_t row0 = ((int64_t)blockIdx.x * kScoreRowsWarps + warp) * 32; row0 < M_pad; row0 += (int64_t)gridDim.x * kScoreRowsWarps * 32) {
         if (row0 >= M) break;                                  // warp-uniform: only padding rows left
         {
             const int64_t tile = row0 >> 7;
@@ -1185,6 +1188,97 @@ __global__ void __launch_bounds__(kRowThreads) query_tail_bwd_kernel(const Query
     if (lane == 0) atomicAdd(p.g_cc, acc_cc);
 }
 
+// ------------------------------------------------------------------------------------------------ query prologue
+// Per ray: the query stack's input q = a_2 * (pe - mean) / (std + eps) + b_2 with pe = [d_c, sin(2^i d_c), cos(2^i d_c)]
+// for the three components of the ray direction (models/utils.py:232-242 embed_type 1, attn.py:30-42 in-norm, unbiased
+// std).  One ray per thread, everything in registers; a CTA stages its 256 rows in shared memory so that the (R, 3S) fp32
+// output is written -- and, in the backward kernel, the incoming gradient read -- with coalesced accesses.  The ray
+// direction is an input of the scene, so the backward kernel produces only the gradients of the affine pair:
+// g_a2[j] += sum_r dq[r, j] * z[r, j],  g_b2[j] += sum_r dq[r, j].
+constexpr int kQpThreads = 256;
+
+template <int L>
+__device__ __forceinline__ void query_pe_normalised(const float *d, float eps, float *z)
+{
+    constexpr int S = 1 + 2 * L, D = 3 * S;
+    float sum = 0.f, sq = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        pe_fill(d[c], L, z + c * S);
+#pragma unroll
+        for (int j = 0; j < S; ++j) { sum += z[c * S + j]; sq = fmaf(z[c * S + j], z[c * S + j], sq); }
+    }
+    const float mean = sum * (1.f / D);
+    const float var = fmaxf(sq - (float)D * mean * mean, 0.f) * (1.f / (D - 1));
+    const float rstd = 1.f / (sqrtf(var) + eps);
+#pragma unroll
+    for (int j = 0; j < D; ++j) z[j] = (z[j] - mean) * rstd;
+}
+
+template <int L>
+__global__ void __launch_bounds__(kQpThreads) query_prologue_fwd_kernel(const float *__restrict__ rays_d, const float *__restrict__ a2,
+                                                                        const float *__restrict__ b2, int64_t R, float eps, float *__restrict__ q)
+{
+    constexpr int D = 3 * (1 + 2 * L);
+    __shared__ float stage[kQpThreads * D];
+    __shared__ float a_s[D], b_s[D];
+    if (threadIdx.x < D) { a_s[threadIdx.x] = a2[threadIdx.x]; b_s[threadIdx.x] = b2[threadIdx.x]; }
+    __syncthreads();
+    for (int64_t r0 = (int64_t)blockIdx.x * kQpThreads; r0 < R; r0 += (int64_t)gridDim.x * kQpThreads) {
+        const int64_t r = r0 + threadIdx.x;
+        if (r < R) {
+            const float d[3] = {rays_d[r * 3], rays_d[r * 3 + 1], rays_d[r * 3 + 2]};
+            float z[D];
+            query_pe_normalised<L>(d, eps, z);
+#pragma unroll
+            for (int j = 0; j < D; ++j) stage[threadIdx.x * D + j] = fmaf(a_s[j], z[j], b_s[j]);      // odd row stride: no bank conflicts
+        }
+        __syncthreads();
+        const int64_t n = (R - r0 < kQpThreads ? R - r0 : kQpThreads) * D;
+        for (int64_t i = threadIdx.x; i < n; i += kQpThreads) q[r0 * D + i] = stage[i];
+        __syncthreads();
+    }
+}
+
+template <int L>
+__global__ void __launch_bounds__(kQpThreads) query_prologue_bwd_kernel(const float *__restrict__ rays_d, const float *__restrict__ dq, int64_t R,
+                                                                        float eps, float *__restrict__ g_a2, float *__restrict__ g_b2)
+{
+    constexpr int D = 3 * (1 + 2 * L);
+    __shared__ float stage[kQpThreads * D];
+    __shared__ float red[2 * D];
+    if (threadIdx.x < 2 * D) red[threadIdx.x] = 0.f;
+    float acc_a[D], acc_b[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) { acc_a[j] = 0.f; acc_b[j] = 0.f; }
+    for (int64_t r0 = (int64_t)blockIdx.x * kQpThreads; r0 < R; r0 += (int64_t)gridDim.x * kQpThreads) {
+        const int64_t n = (R - r0 < kQpThreads ? R - r0 : kQpThreads) * D;
+        __syncthreads();
+        for (int64_t i = threadIdx.x; i < n; i += kQpThreads) stage[i] = dq[r0 * D + i];
+        __syncthreads();
+        const int64_t r = r0 + threadIdx.x;
+        if (r < R) {
+            const float d[3] = {rays_d[r * 3], rays_d[r * 3 + 1], rays_d[r * 3 + 2]};
+            float z[D];
+            query_pe_normalised<L>(d, eps, z);
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                const float g = stage[threadIdx.x * D + j];
+                acc_a[j] = fmaf(g, z[j], acc_a[j]);
+                acc_b[j] += g;
+            }
+        }
+    }
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+        const float sa = warp_sum(acc_a[j]), sb = warp_sum(acc_b[j]);
+        if (lane == 0) { atomicAdd(&red[j], sa); atomicAdd(&red[D + j], sb); }
+    }
+    __syncthreads();
+    if (threadIdx.x < D) { atomicAdd(g_a2 + threadIdx.x, red[threadIdx.x]); atomicAdd(g_b2 + threadIdx.x, red[D + threadIdx.x]); }
+}
+
 static int row_grid(int64_t R)
 {
     const int64_t blocks = (R + kRowWarps - 1) / kRowWarps;
@@ -1294,11 +1388,11 @@ extern "C" int papr_score_blend_fwd(const void *h5, const float *h5_f32, const f
     p.R = R; p.K = K; p.C = C; p.ldv = (int)ldv; p.score_relu = score_relu; p.normalize = normalize;
     p.bkg_score = bkg_score; p.eps = eps; p.fused = fused; p.attn = attn; p.sc = sc; p.stats = stats;
     if (h5 && !h5_f32 && K >= 16 && !getenv("PAPR_SCORE_WARP")) {
-        constexpr int smem = kRowWarps * 4 * 4096;
+        constexpr int smem = kScoreRowsWarps * 4 * 4096, threads = kScoreRowsWarps * 32;
         static SmemAttrOnce once;
         PAPR_CUDA_TRY(ensure_dyn_smem(once, score_rows_kernel, smem));
-        const int64_t groups = (R * K + kRowThreads - 1) / kRowThreads;
-        score_rows_kernel<<<(int)(groups < kNumSMs ? groups : kNumSMs), kRowThreads, smem, (cudaStream_t)stream>>>(p);
+        const int64_t groups = (R * K + threads - 1) / threads;
+        score_rows_kernel<<<(int)(groups < kNumSMs ? groups : kNumSMs), threads, smem, (cudaStream_t)stream>>>(p);
         PAPR_CUDA_TRY(cudaGetLastError());
         p.sc_ready = 1;
     }
@@ -1334,6 +1428,30 @@ extern "C" int papr_key_score_bwd(const float *d_score, const void *h5, const fl
         key_score_bwd_blocks_kernel<<<row_grid(R), kRowThreads, 0, (cudaStream_t)stream>>>(p);
     else
         key_score_bwd_kernel<<<row_grid(R), kRowThreads, 0, (cudaStream_t)stream>>>(p);
+    return check_launch();
+}
+
+extern "C" int papr_query_prologue_fwd(const float *rays_d, const float *a2, const float *b2, int64_t R, int L, float eps,
+                                       float *q, void *stream)
+{
+    if (!rays_d || !a2 || !b2 || !q || R <= 0) return PAPR_ERR_INVALID_ARGUMENT;
+    const int64_t groups = (R + kQpThreads - 1) / kQpThreads;
+    const int grid = (int)(groups < 4 * kNumSMs ? groups : 4 * kNumSMs);
+    if (L == 6) query_prologue_fwd_kernel<6><<<grid, kQpThreads, 0, (cudaStream_t)stream>>>(rays_d, a2, b2, R, eps, q);
+    else if (L == 4) query_prologue_fwd_kernel<4><<<grid, kQpThreads, 0, (cudaStream_t)stream>>>(rays_d, a2, b2, R, eps, q);
+    else return PAPR_ERR_INVALID_ARGUMENT;
+    return check_launch();
+}
+
+extern "C" int papr_query_prologue_bwd(const float *rays_d, const float *dq, int64_t R, int L, float eps, float *g_a2,
+                                       float *g_b2, void *stream)
+{
+    if (!rays_d || !dq || !g_a2 || !g_b2 || R <= 0) return PAPR_ERR_INVALID_ARGUMENT;
+    const int64_t groups = (R + kQpThreads - 1) / kQpThreads;
+    const int grid = (int)(groups < 2 * kNumSMs ? groups : 2 * kNumSMs);
+    if (L == 6) query_prologue_bwd_kernel<6><<<grid, kQpThreads, 0, (cudaStream_t)stream>>>(rays_d, dq, R, eps, g_a2, g_b2);
+    else if (L == 4) query_prologue_bwd_kernel<4><<<grid, kQpThreads, 0, (cudaStream_t)stream>>>(rays_d, dq, R, eps, g_a2, g_b2);
+    else return PAPR_ERR_INVALID_ARGUMENT;
     return check_launch();
 }
 

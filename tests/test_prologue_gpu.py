@@ -120,3 +120,38 @@ def test_score_rows_kernel_matches_warp_per_ray(R, K, relu):
         assert float((stats[:, 1].double() * (std[:, 0] + 1e-6) - 1).abs().max()) <= 1e-5, name
     assert float((new[0] - old[0]).abs().max()) <= 1e-4 * float(old[0].abs().max())
     assert float((new[1] - old[1]).abs().max()) <= 1e-5
+
+
+@pytest.mark.parametrize("L", [6, 4])
+@pytest.mark.parametrize("R", [1, 255, 257, 5000])
+def test_query_prologue_matches_torch_posenc_and_innorm(L, R):
+    """papr_query_prologue_fwd / _bwd against the torch formulation it replaces (utils.py:232-242 + attn.py:30-42)."""
+    from papr_b200.nn import LayerNorm
+    g = torch.Generator(device="cuda").manual_seed(R + L)
+    D = 3 * (1 + 2 * L)
+    rays_d = torch.nn.functional.normalize(torch.randn(R, 3, device="cuda", generator=g), dim=-1)
+    if R > 4:
+        rays_d[3] = torch.tensor([0.0, 0.0, 1.0], device="cuda")          # an axis-aligned direction
+    ln = LayerNorm(D, 1e-6).cuda()
+    with torch.no_grad():
+        ln.a_2.copy_(1 + 0.1 * torch.randn(D, device="cuda", generator=g))
+        ln.b_2.copy_(0.1 * torch.randn(D, device="cuda", generator=g))
+    want = ln(A.posenc(rays_d.double(), L).float())
+    got = A._QueryPrologueFn.apply(rays_d, ln.a_2, ln.b_2, L, ln.eps)
+    assert got.shape == want.shape
+    # the double-angle recurrence doubles the rounding error per octave: 2^L * 2^-24 on O(1) values, times 1/std
+    assert float((got - want).abs().max()) <= 2e-4
+    w = torch.randn(R, D, device="cuda", generator=g)
+    ga, gb = torch.autograd.grad((got * w).sum(), [ln.a_2, ln.b_2])
+    wa, wb = torch.autograd.grad((want * w).sum(), [ln.a_2, ln.b_2])
+    scale = max(1.0, float(wa.abs().max()), float(wb.abs().max()))
+    assert float((ga - wa).abs().max()) <= 2e-4 * scale * max(1.0, R ** 0.5)
+    assert float((gb - wb).abs().max()) <= 1e-5 * scale * max(1.0, R ** 0.5)
+
+
+def test_query_prologue_rejects_unsupported_orders():
+    from papr_b200._lib import PaprError
+    rays_d = torch.randn(8, 3, device="cuda")
+    a = torch.ones(3 * 11, device="cuda")
+    with pytest.raises(PaprError):
+        A._QueryPrologueFn.apply(rays_d, a, a, 5, 1e-6)

@@ -8,6 +8,9 @@ oracle (medium), max-abs errors of: attention weights, aggregated features (rela
   bf16+unet32   : bf16 stacks, the UNet evaluated in fp32 on the bf16 path's features  -> error owed to the stacks
   fp32+unetbf16 : parity-mode features, bf16 UNet                                      -> error owed to the UNet
   fp32          : parity mode (split-bf16 GEMMs on the library's kernels, fp32 UNet)
+  ref_autocast  : the oracle port of the REFERENCE's own path on the same GPU under torch.autocast(bfloat16) -- what the
+                  reference's `use_amp: True, amp_dtype: bfloat16` mode (models/attn.py:248, models/model.py:24-25) gives
+                  on these inputs through cuBLAS / cuDNN; the yardstick for a bf16 tolerance
 """
 import json
 import os
@@ -57,6 +60,16 @@ def errors(cfg, params, rays_o, rays_d, c2w, code, want):
                 bk = attn[..., K, :]
                 rgb = fg * (1 - bk) + m.bkg_feats.reshape(1, 1, 1, -1) * bk
                 out[name] = dict(rgb=float((rgb.cpu() - want["rgb"]).abs().max()))
+    # the reference's own mixed-precision mode on the same inputs (same candidate sets), stock PyTorch kernels
+    with torch.no_grad():
+        pc = {k: v.cuda() for k, v in params.items()}
+        idx = models["fp32"].select_k_ind.long()
+        r = O.forward(pc, cfg, rays_o, rays_d, shading_code=code, idx=idx, autocast_dtype=torch.bfloat16)
+        a = r["attn"].float().cpu()
+        out["ref_autocast"] = dict(attn=float((torch.sort(a[..., :K], -1).values - torch.sort(want["attn"][..., :K], -1).values).abs().max()),
+                                   bkg=float((a[..., K] - want["attn"][..., K]).abs().max()),
+                                   fused=rel_err(r["fused"].float().cpu(), want["fused"]),
+                                   rgb=float((r["rgb"].float().cpu() - want["rgb"]).abs().max()))
     return out
 
 
