@@ -520,9 +520,13 @@ class _StackBf16Fn(torch.autograd.Function):
         n_out = ws[-1].shape[0]
         g = gy.contiguous()
         dz = ops.Blocked.from_f32(g, cols_pad=max(ops.pad_cols(n_out), 128))
-        gb_last = g.sum(0)
+        # the last layer's bias gradient = column sums of dz: from the weight-gradient kernel's idle warps when it can
+        # (papr_wgrad_bias_bf16), not from a separate reduction over the (R, n_out) tensor
+        from_wgrad = n_out >= 128
+        gb_last = None if from_wgrad else g.sum(0)
         in_pad = ops.pad_cols(ctx.n_in)
-        dx, gWs, gbs = _stack_backward(dz, inputs, bits, ws, ctx.slope, gb_last, ctx.n_in, in_pad, images_t=ctx.img_t)
+        dx, gWs, gbs = _stack_backward(dz, inputs, bits, ws, ctx.slope, gb_last, ctx.n_in, in_pad, images_t=ctx.img_t,
+                                       last_bias_from_wgrad=from_wgrad)
         return (dx.to_f32(ctx.rows, ctx.n_in), None, None, None, None, *gWs, *gbs)
 
 
@@ -584,7 +588,8 @@ class _QueryTailFn(torch.autograd.Function):
         dub = ops.Blocked.from_f32(d_ua)
         _, dz, _ = ops.linear_bf16(dub, ops.pack_weight(A, 256, 256, transpose=True), 256, 256, out_blocked=False, out_f32=True)
         gA = torch.zeros((256, 256), device=dev)
-        ops.wgrad_bf16(dub, ctx.zb, gA, 256, 256)
+        g_c0 = torch.zeros(256, device=dev)
+        ops.wgrad_bf16(dub, ctx.zb, gA, 256, 256, a_colsum=g_c0)       # d c0 = column sums of d ua, from the same launch
         dq5 = torch.empty((R, 256), device=dev)
         g_wc = torch.zeros(256, device=dev)
         g_cc = torch.zeros(1, device=dev)
@@ -592,7 +597,7 @@ class _QueryTailFn(torch.autograd.Function):
                  d_c.data_ptr(), float(ctx.eps), R, dq5.data_ptr(), g_wc.data_ptr(), g_cc.data_ptr(),
                  nbytes=R * (3 * 1024.0 + 12))
         ctx.zb = None
-        return dq5, gA, d_ua.sum(0), g_wc, None
+        return dq5, gA, g_c0, g_wc, None
 
 
 class RowAttentionFn(torch.autograd.Function):

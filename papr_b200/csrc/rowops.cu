@@ -352,18 +352,27 @@ __global__ void __launch_bounds__(kRowThreads, 2) attn_prologue_fwd_rows_kernel(
     const uint32_t sw = (uint32_t)lane & 7u;
     const int64_t M = p.R * p.K, M_pad = (M + 127) / 128 * 128;
 
-    for (int64_t row0 = ((int64_t)blockIdx.x * kRowWarps + warp) * 32; row0 < M_pad; row0 += (int64_t)gridDim.x * kRowWarps * 32) {
+    // the candidate index of the NEXT group of rows is requested a whole iteration ahead: idx -> point is otherwise a chain of
+    // two dependent global loads at the top of every iteration
+    const int64_t row_step = (int64_t)gridDim.x * kRowWarps * 32;
+    int pidx_next = 0;
+    {
+        const int64_t first = ((int64_t)blockIdx.x * kRowWarps + warp) * 32 + lane;
+        if (first < M) pidx_next = p.idx[first];
+    }
+    for (int64_t row0 = ((int64_t)blockIdx.x * kRowWarps + warp) * 32; row0 < M_pad; row0 += row_step) {
         const int64_t row = row0 + lane;
         const bool live = row < M;
         float g[9];
-        int pidx = 0;
+        const int pidx = pidx_next;
+        pidx_next = 0;
+        if (row + row_step < M) pidx_next = p.idx[row + row_step];
 #pragma unroll
         for (int i = 0; i < 9; ++i) g[i] = 0.f;
         if (live) {
             const int64_t ray = row / p.K;
             const int64_t view = ray / p.rays_per_view;
             float u[3], den;
-            pidx = p.idx[row];
             const Geometry geo = ray_point_geometry(p.points + (size_t)pidx * 3, p.rays_o + view * 3, p.rays_d + ray * 3, p.eps, u, &den);
 #pragma unroll
             for (int i = 0; i < 9; ++i) g[i] = geo.g[i];
@@ -462,29 +471,41 @@ __global__ void __launch_bounds__(kRowThreads, 2) attn_prologue_fwd_rows_kernel(
                 if ((jv & 7) == 7) put_v(jv >> 3);
             }
         }
-        // point features follow the value-side encoding (model.py:396-437: cat(pe(geometry), pc_feats))
-        const float4 *fsrc = reinterpret_cast<const float4 *>(p.feats + (size_t)pidx * F);
+        // point features follow the value-side encoding (model.py:396-437: cat(pe(geometry), pc_feats)).
+        // A lane that fetched its own row's F floats would wait for one L2 round trip per 16-byte load (they are consumed one
+        // chunk at a time and there are no registers to hold them all); instead the WARP fetches every row together: for row r
+        // lane l loads features 2l, 2l+1 (+64), all 32 rows requested back to back, then each pair goes to its place in
+        // the staged row as one 32-bit store (DPE is even, so a pair never straddles a 16-byte chunk).
+        static_assert((DPE & 1) == 0 && (F == 64 || F == 128), "feature pairs must be 4-byte aligned in the row");
+        if (DPE & 7) {                                       // the chunk shared by the last PE columns and the first features
 #pragma unroll
-        for (int f = 0; f < F; f += 4) {
-            float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (live) q = __ldg(fsrc + (f >> 2));
-            const float qq[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int jv = DPE + f + e;
-                vb[jv & 7] = qq[e];
-                if ((jv & 7) == 7) put_v(jv >> 3);
-            }
-        }
-        if (DV & 7) {
-#pragma unroll
-            for (int e = DV & 7; e < 8; ++e) vb[e] = 0.f;
-            put_v(DV >> 3);
+            for (int e = DPE & 7; e < 8; ++e) vb[e] = 0.f;
+            put_v(DPE >> 3);
         }
 #pragma unroll
         for (int e = 0; e < 8; ++e) vb[e] = 0.f;
 #pragma unroll
-        for (int c = (DV + 7) >> 3; c < NBV * 8; ++c) put_v(c);
+        for (int c = (DPE + 7) >> 3; c < NBV * 8; ++c) put_v(c);
+        __syncwarp();
+        {
+            const uint32_t live_mask = __ballot_sync(0xffffffffu, live);
+#pragma unroll
+            for (int h = 0; h < F / 64; ++h) {
+                float2 q[32];
+#pragma unroll
+                for (int r = 0; r < 32; ++r) {
+                    const int pr = __shfl_sync(0xffffffffu, pidx, r);
+                    q[r] = make_float2(0.f, 0.f);
+                    if ((live_mask >> r) & 1u) q[r] = __ldg(reinterpret_cast<const float2 *>(p.feats + (size_t)pr * F + h * 64) + lane);
+                }
+                const int jv = DPE + h * 64 + 2 * lane;      // column of the pair in the value row
+                const uint32_t blk_off = (uint32_t)(jv >> 6) * 4096u, chunk = ((uint32_t)jv >> 3) & 7u, within = ((uint32_t)jv & 7u) * 2u;
+#pragma unroll
+                for (int r = 0; r < 32; ++r)
+                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(wst + blk_off + (uint32_t)r * 128u + ((chunk ^ ((uint32_t)r & 7u)) << 4) + within),
+                                 "r"(pack_bf16(q[r].x, q[r].y)) : "memory");
+            }
+        }
         copy_out(p.vin, NBV);
     }
 }
@@ -797,6 +818,20 @@ __global__ void __launch_bounds__(kRowThreads) score_blend_fwd_kernel(const Scor
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int64_t ray = (int64_t)blockIdx.x * kRowWarps + warp; ray < p.R; ray += (int64_t)gridDim.x * kRowWarps) {
+        // The value rows do not depend on the softmax: with C <= 32 (one column per lane) all K of them are requested
+        // before anything else, so their HBM latency overlaps the score / softmax chain (ncu r02: 17 warps stalled on
+        // long_scoreboard per issue when each row was loaded inside the accumulation loop, one at a time).
+        const bool v_ahead = p.C <= 32;
+        float vv[32];
+        if (v_ahead) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k)
+                vv[k] = (k < p.K && lane < p.C) ? __ldg(p.v + (ray * p.K + k) * p.ldv + lane) : 0.f;
+        }
+        float my_sc = 0.f;
+        if (p.sc_ready) {                    // raw scores and row statistics already written by score_rows_kernel
+            if (lane < p.K) my_sc = p.sc[ray * p.K + lane];
+        } else {
         float ua[8];
         {
             const float4 a = *reinterpret_cast<const float4 *>(p.ua + ray * 256 + lane * 8);
@@ -804,10 +839,6 @@ __global__ void __launch_bounds__(kRowThreads) score_blend_fwd_kernel(const Scor
             ua[0] = a.x; ua[1] = a.y; ua[2] = a.z; ua[3] = a.w; ua[4] = b.x; ua[5] = b.y; ua[6] = b.z; ua[7] = b.w;
         }
         const float cp = p.cprime[ray];
-        float my_sc = 0.f;
-        if (p.sc_ready) {                    // raw scores and row statistics already written by score_rows_kernel
-            if (lane < p.K) my_sc = p.sc[ray * p.K + lane];
-        } else {
         // bf16 rows are fetched one candidate ahead (4 registers) so the HBM latency overlaps the three warp reductions
         uint4 nxt = make_uint4(0, 0, 0, 0);
         if (!p.h5_f32) nxt = *reinterpret_cast<const uint4 *>(p.h5 + blocked_chunk_offset(ray * p.K, lane, 4));
@@ -850,6 +881,12 @@ __global__ void __launch_bounds__(kRowThreads) score_blend_fwd_kernel(const Scor
         if (lane == 0) p.attn[ray * (p.K + 1) + p.K] = eb / tot;
         const float topk = warp_sum(attn);
         const float w = p.normalize ? attn / topk : attn;
+        if (v_ahead) {
+            float acc = 0.f;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) acc = fmaf(__shfl_sync(0xffffffffu, w, k), vv[k], acc);    // lanes >= K carry w = 0
+            if (lane < p.C) p.fused[ray * p.C + lane] = acc;
+        } else
         for (int c0 = 0; c0 < p.C; c0 += 32) {
             const int c = c0 + lane;
             float acc = 0.f;
@@ -1153,39 +1190,76 @@ __global__ void __launch_bounds__(kRowThreads) query_tail_fwd_kernel(const Query
 
 __global__ void __launch_bounds__(kRowThreads) query_tail_bwd_kernel(const QueryTailParams p)
 {
+    // U rays per warp iteration: their loads are all in flight before the first of the two warp reductions per ray (with one
+    // ray at a time the kernel issued 10% of its slots and reached 25% of the DRAM roof, ncu r02)
+    constexpr int U = 4;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float wc[8], acc_wc[8], acc_cc = 0.f;
 #pragma unroll
     for (int e = 0; e < 8; ++e) { wc[e] = p.wc[lane * 8 + e]; acc_wc[e] = 0.f; }
-    for (int64_t ray = (int64_t)blockIdx.x * kRowWarps + warp; ray < p.R; ray += (int64_t)gridDim.x * kRowWarps) {
-        const float4 a = *reinterpret_cast<const float4 *>(p.q5 + ray * 256 + lane * 8);
-        const float4 b = *reinterpret_cast<const float4 *>(p.q5 + ray * 256 + lane * 8 + 4);
-        const float4 ga = *reinterpret_cast<const float4 *>(p.dz + ray * p.ld_dz + lane * 8);
-        const float4 gb = *reinterpret_cast<const float4 *>(p.dz + ray * p.ld_dz + lane * 8 + 4);
-        const float h[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-        float g[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
-        const float mean = p.stats[ray * 2], rstd = p.stats[ray * 2 + 1], dc = p.dc[ray];
-        float z[8], s1 = 0.f, s2 = 0.f;
+    const int64_t stride = (int64_t)gridDim.x * kRowWarps;
+    for (int64_t ray0 = (int64_t)blockIdx.x * kRowWarps + warp; ray0 < p.R; ray0 += stride * U) {
+        float h[U][8], g[U][8], mean[U], rstd[U], dc[U];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            z[e] = (h[e] - mean) * rstd;
-            acc_wc[e] += dc * z[e];
-            g[e] += dc * wc[e];                 // d z = (d ua) A + d c' * w_c
-            s1 += g[e]; s2 += g[e] * z[e];
+        for (int u = 0; u < U; ++u) {
+            const int64_t ray = ray0 + u * stride;
+            const bool on = ray < p.R;
+            const int64_t r = on ? ray : ray0;
+            const float4 a = *reinterpret_cast<const float4 *>(p.q5 + r * 256 + lane * 8);
+            const float4 b = *reinterpret_cast<const float4 *>(p.q5 + r * 256 + lane * 8 + 4);
+            const float4 ga = *reinterpret_cast<const float4 *>(p.dz + r * p.ld_dz + lane * 8);
+            const float4 gb = *reinterpret_cast<const float4 *>(p.dz + r * p.ld_dz + lane * 8 + 4);
+            h[u][0] = a.x; h[u][1] = a.y; h[u][2] = a.z; h[u][3] = a.w; h[u][4] = b.x; h[u][5] = b.y; h[u][6] = b.z; h[u][7] = b.w;
+            g[u][0] = ga.x; g[u][1] = ga.y; g[u][2] = ga.z; g[u][3] = ga.w; g[u][4] = gb.x; g[u][5] = gb.y; g[u][6] = gb.z; g[u][7] = gb.w;
+            mean[u] = p.stats[r * 2]; rstd[u] = p.stats[r * 2 + 1]; dc[u] = on ? p.dc[r] : 0.f;
         }
-        acc_cc += dc;
-        s1 = warp_sum(s1) * (1.f / 256.f);
-        const float sigma = 1.f / rstd - p.eps;
-        s2 = warp_sum(s2) / (255.f * sigma);
-        float o[8];
+        float s1[U], s2[U];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = rstd * (g[e] - s1) - z[e] * s2;
-        *reinterpret_cast<float4 *>(p.dq5 + ray * 256 + lane * 8) = make_float4(o[0], o[1], o[2], o[3]);
-        *reinterpret_cast<float4 *>(p.dq5 + ray * 256 + lane * 8 + 4) = make_float4(o[4], o[5], o[6], o[7]);
+        for (int u = 0; u < U; ++u) {
+            s1[u] = 0.f; s2[u] = 0.f;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                h[u][e] = (h[u][e] - mean[u]) * rstd[u];        // z
+                if (ray0 + u * stride < p.R) acc_wc[e] += dc[u] * h[u][e];
+                g[u][e] += dc[u] * wc[e];                       // d z = (d ua) A + d c' * w_c
+                s1[u] += g[u][e]; s2[u] += g[u][e] * h[u][e];
+            }
+            acc_cc += dc[u];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                s1[u] += __shfl_xor_sync(0xffffffffu, s1[u], o);
+                s2[u] += __shfl_xor_sync(0xffffffffu, s2[u], o);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t ray = ray0 + u * stride;
+            if (ray >= p.R) continue;
+            const float m1 = s1[u] * (1.f / 256.f);
+            const float sigma = 1.f / rstd[u] - p.eps;
+            const float m2 = s2[u] / (255.f * sigma);
+            float o8[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o8[e] = rstd[u] * (g[u][e] - m1) - h[u][e] * m2;
+            *reinterpret_cast<float4 *>(p.dq5 + ray * 256 + lane * 8) = make_float4(o8[0], o8[1], o8[2], o8[3]);
+            *reinterpret_cast<float4 *>(p.dq5 + ray * 256 + lane * 8 + 4) = make_float4(o8[4], o8[5], o8[6], o8[7]);
+        }
     }
+    // one set of 257 global atomics per CTA, not per warp (they all land on the same 257 addresses)
+    __shared__ float red_s[kRowWarps][257];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) atomicAdd(p.g_wc + lane * 8 + e, acc_wc[e]);
-    if (lane == 0) atomicAdd(p.g_cc, acc_cc);
+    for (int e = 0; e < 8; ++e) red_s[warp][lane * 8 + e] = acc_wc[e];
+    if (lane == 0) red_s[warp][256] = acc_cc;
+    __syncthreads();
+    for (int j = threadIdx.x; j < 257; j += kRowThreads) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < kRowWarps; ++w) t += red_s[w][j];
+        atomicAdd(j < 256 ? p.g_wc + j : p.g_cc, t);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ query prologue
@@ -1472,6 +1546,7 @@ extern "C" int papr_query_tail_bwd(const float *q5, const float *stats, const fl
     QueryTailParams p = {};
     p.q5 = q5; p.stats = const_cast<float *>(stats); p.wc = w_c; p.dz = dz; p.ld_dz = ld_dz; p.dc = dc; p.eps = eps; p.R = R;
     p.dq5 = dq5; p.g_wc = g_wc; p.g_cc = g_cconst;
-    query_tail_bwd_kernel<<<row_grid(R), kRowThreads, 0, (cudaStream_t)stream>>>(p);
+    const int grid_all = row_grid(R);           // 128 registers per thread: two CTAs per SM are resident
+    query_tail_bwd_kernel<<<grid_all < 2 * kNumSMs ? grid_all : 2 * kNumSMs, kRowThreads, 0, (cudaStream_t)stream>>>(p);
     return check_launch();
 }

@@ -67,23 +67,25 @@ __global__ void __launch_bounds__(256) nhwc_to_planes_kernel(const float *__rest
 // raster and its one-pixel (right: up to seven-pixel) frame, per shifted copy.  The interior -- all of it -- is written by
 // the kernel that produces the map, so a full memset of the buffer (0.25 ms for a 256-channel 800x800 map, 1 ms per
 // training step over all maps) is 97% redundant.
+// In raster order the frame is H + 1 contiguous runs of pixel rows per plane: [guard rows, line 0, left pad of line 1], then
+// for every line its right pad together with the left pad of the next line, and finally [right pad of line H, line H + 1,
+// guard rows].  One warp zeroes one run (a first version tested every 16-byte chunk of the buffer for "interior": two
+// 64-bit divisions per chunk, 0.1 ms per map and 1.1 ms per training step for 3% of the bytes).
 __global__ void __launch_bounds__(256) zero_border_kernel(uint8_t *__restrict__ planes, Raster g, int ncopies, int cbs, int64_t rows_total)
 {
-    const int64_t total = (int64_t)ncopies * cbs * rows_total * 8;
-    const int64_t raster_rows = (int64_t)(g.H + 2) * g.Wp;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int c = (int)(i & 7);
-        const int64_t r = (i >> 3) % rows_total;
-        const int64_t pc = (i >> 3) / rows_total;
-        const int cb = (int)(pc % cbs), d = (int)(pc / cbs);
-        // copy d of three holds pixel row p at p - (d - 1) (store_copies); a single copy is unshifted
-        const int64_t q = r + (ncopies == 3 ? d - 1 : 0) - g.row0;
-        bool interior = false;
-        if (q >= 0 && q < raster_rows) {
-            const int yy = (int)(q / g.Wp), xx = (int)(q % g.Wp);
-            interior = yy >= 1 && yy <= g.H && xx >= 1 && xx <= g.W;
-        }
-        if (!interior) *reinterpret_cast<uint4 *>(chunk_ptr(planes, g, d, cb, r, c)) = make_uint4(0, 0, 0, 0);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pc = blockIdx.y, cb = pc % cbs, d = pc / cbs;
+    // copy d of three holds pixel row p at p - (d - 1) (store_copies); a single copy is unshifted
+    const int64_t shift = g.row0 - (ncopies == 3 ? d - 1 : 0);          // raster index q lives in pixel row q + shift
+    uint8_t *plane = planes + (int64_t)d * g.copy_bytes + (int64_t)cb * g.plane_bytes;
+    for (int s = blockIdx.x * 8 + warp; s <= g.H; s += gridDim.x * 8) {
+        int64_t r0 = s == 0 ? 0 : (int64_t)s * g.Wp + g.W + 1 + shift;
+        int64_t r1 = s == g.H ? rows_total : (int64_t)(s + 1) * g.Wp + 1 + shift;
+        r0 = r0 < 0 ? 0 : r0;
+        r1 = r1 > rows_total ? rows_total : r1;
+        uint4 *dst = reinterpret_cast<uint4 *>(plane + r0 * 128);
+        const int64_t n = (r1 - r0) * 8;
+        for (int64_t i = lane; i < n; i += 32) dst[i] = make_uint4(0, 0, 0, 0);
     }
 }
 
@@ -335,11 +337,8 @@ extern "C" int papr_unet_zero_border(void *planes, const papr_raster *geom, int 
 {
     if (!planes || !raster_ok(geom) || cbs < 1 || (ncopies != 1 && ncopies != 3) || geom->plane_bytes % 128) return PAPR_ERR_INVALID_ARGUMENT;
     const int64_t rows_total = geom->plane_bytes / 128;
-    const int64_t total = (int64_t)ncopies * cbs * rows_total * 8;
-    int64_t blocks = (total + 255) / 256;
-    const int64_t cap = (int64_t)kNumSMs * 16;
-    if (blocks > cap) blocks = cap;
-    zero_border_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((uint8_t *)planes, make_raster(*geom), ncopies, cbs, rows_total);
+    const dim3 grid((unsigned)((geom->H + 1 + 7) / 8), (unsigned)(ncopies * cbs));
+    zero_border_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((uint8_t *)planes, make_raster(*geom), ncopies, cbs, rows_total);
     return check_launch();
 }
 
