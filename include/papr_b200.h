@@ -77,6 +77,21 @@ int papr_select_topk_grid(const float *rays_o, const float *rays_d, const void *
                           int G, int K, float eps, int32_t *idx_out, void *stream);
 
 /*
+ * Builds the inputs of papr_select_topk_grid on the device (six small launches, no host synchronisation): the camera frame
+ * around each view's mean ray direction, the grid placement over the gnomonic extent of the view's rays and of the points
+ * in front of the camera, the points binned and stored cell by cell (counting sort; the order inside a cell is
+ * unspecified and does not influence the selection), each cell's smallest |depth|.  Outputs as papr_select_topk_grid
+ * reads them: sorted_v (n_views*P, 4) f32, perm (n_views*P) i32, cells (n_views*G*G, 4) i32, view_params (n_views, 20)
+ * f32.  workspace: at least papr_select_grid_workspace_bytes(n_views, P, G) bytes of device memory (contents undefined).
+ * Rebuilt whenever the points or the cameras change, i.e. before every selection (model.py:258-283 has no such
+ * structure: it materialises all rays x points distances).
+ */
+int64_t papr_select_grid_workspace_bytes(int64_t n_views, int64_t P, int G);
+int papr_select_grid_build(const float *rays_o, const float *rays_d, const float *points, int64_t n_views, int64_t rays_per_view,
+                           int64_t P, int G, float eps, void *sorted_v, int32_t *perm, int32_t *cells, float *view_params,
+                           void *workspace, int64_t workspace_bytes, void *stream);
+
+/*
  * Tensor-core building blocks (stages a7/a8/a12).  Activations use the library's "tile-blocked" bf16 layout: a logical
  * [rows, cols] matrix (rows % 128 == 0, cols % 64 == 0) stored as [rows/128][cols/64] blocks of 16 KB, each block
  * 128 rows x 64 columns with the eight 16-byte chunks of a row XOR-swizzled by (row & 7) -- the shared-memory image

@@ -20,6 +20,8 @@ SIGNATURES = {
     "papr_select_topk": [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i32, _f32, _ptr, _ptr],
     "papr_select_topk_sorted": [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _i32, _f32, _ptr, _ptr, _ptr],
     "papr_select_topk_grid": [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i64, _i64, _i32, _i32, _f32, _ptr, _ptr],
+    "papr_select_grid_workspace_bytes": [_i64, _i64, _i32],
+    "papr_select_grid_build": [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i32, _f32, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _ptr],
     "papr_blocked_from_f32": [_ptr, _i64, _i32, _i64, _ptr, _i64, _i32, _ptr],
     "papr_blocked_to_f32": [_ptr, _i32, _ptr, _i64, _i32, _i64, _ptr],
     "papr_pack_weight": [_ptr, _i64, _i32, _i32, _i32, _i32, _i32, _f32, _ptr, _ptr],
@@ -55,7 +57,8 @@ SIGNATURES = {
     "papr_unet_convt_gather": [_ptr, _ptr, _i32, _i32, _ptr, _ptr, _i32, _i32, _ptr, _ptr],
     "papr_generate_rays": [_ptr, _i64, _i32, _i32, _f32, _f32, _i32, _i32, _i32, _i32, _f32, _ptr, _ptr, _ptr],
 }
-_RESTYPE = {"papr_status_string": _c.c_char_p, "papr_last_cuda_error": _c.c_char_p, "papr_stack_bwd_workspace_bytes": _i64}
+_RESTYPE = {"papr_status_string": _c.c_char_p, "papr_last_cuda_error": _c.c_char_p, "papr_stack_bwd_workspace_bytes": _i64,
+            "papr_select_grid_workspace_bytes": _i64}
 
 
 class StackLayer(ctypes.Structure):

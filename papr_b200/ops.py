@@ -114,16 +114,43 @@ def morton_groups(points):
 GRID_MIN_POINTS = 1024     # below this the plain scan is as fast as building the grid
 
 
+def grid_size(P):
+    """Cells per axis of the selection grid: about eight points per cell."""
+    return int(min(128, max(8, round((P / 8.0) ** 0.5))))
+
+
 def view_grids(rays_o, rays_d, points, eps, G=None):
-    """Host side of the screen-space grid selection (see select_grid_kernel in csrc/select.cu): per view, a camera frame
-    around the mean ray direction, the gnomonic extent of the view's rays, and the points binned on a G x G grid over that
-    extent, sorted by cell.  All torch ops on the device, batched over views, no host synchronisation.
+    """The acceleration structure of the screen-space grid selection (select_grid_kernel in csrc/select.cu), built by
+    papr_select_grid_build (csrc/select_grid_build.cu: six small launches, no host synchronisation): per view, a camera
+    frame around the mean ray direction, the gnomonic extent of the view's rays and of the points in front of the camera,
+    the points binned on a G x G grid over that extent and stored cell by cell.
     rays_o (N,3), rays_d (N,R,3), points (P,3) -> (sorted_v (N*P,4), perm (N*P,) i32, cells (N*G*G,4) i32, views (N,20), G)."""
     N, R, _ = rays_d.shape
     P = points.shape[0]
     dev = points.device
     if G is None:
-        G = int(min(128, max(8, round((P / 8.0) ** 0.5))))
+        G = grid_size(P)
+    sv = torch.empty((N * P, 4), device=dev)
+    perm = torch.empty((N * P,), dtype=torch.int32, device=dev)
+    cells = torch.empty((N * G * G, 4), dtype=torch.int32, device=dev)
+    views = torch.empty((N, 20), device=dev)
+    nbytes = int(lib().papr_select_grid_workspace_bytes(N, P, G))
+    ws = torch.empty((max(nbytes, 16),), dtype=torch.uint8, device=dev)
+    call("papr_select_grid_build", rays_o.data_ptr(), rays_d.data_ptr(), points.data_ptr(), N, R, P, G, float(eps), sv.data_ptr(),
+         perm.data_ptr(), cells.data_ptr(), views.data_ptr(), ws.data_ptr(), nbytes, kernels=6,
+         nbytes=12.0 * N * R * 2 + N * P * (12.0 * 3 + 4 * 2 + 20))
+    return sv, perm, cells, views, G
+
+
+def view_grids_torch(rays_o, rays_d, points, eps, G=None):
+    """The same structure from ~60 torch ops (stable sort by cell, searchsorted, scatter_reduce), batched over views: the
+    first implementation, kept as the A/B partner of papr_select_grid_build in tests/test_select_gpu.py (the two differ in
+    the last bits of the frame and in the order inside a cell; the selection they lead to is identical)."""
+    N, R, _ = rays_d.shape
+    P = points.shape[0]
+    dev = points.device
+    if G is None:
+        G = grid_size(P)
     # (no torch.tensor(python data, device=...) in here: a pageable host-to-device copy synchronises the stream and would
     # stop the host from running ahead of the GPU)
     dn = rays_d / rays_d.norm(dim=-1, keepdim=True).clamp_min(1e-30)
@@ -195,7 +222,8 @@ def select_topk(rays_o, rays_d, points, K, eps=1e-6, cull=None):
     """Stage a1 (reference models/model.py:258-283): int32 (N,H,W,K) nearest-point indices per ray,
     ordered by (distance, index).  rays_o (N,3), rays_d (N,H,W,3), points (P,3), all CUDA fp32.
     cull: None = automatic (the screen-space grid kernel for P >= GRID_MIN_POINTS, else the plain scan); "grid";
-    True / "morton" = the Morton-group kernel; False = plain scan.  All variants return the identical result."""
+    "grid_torch" = the grid kernel on a structure built by torch ops (A/B partner); True / "morton" = the Morton-group
+    kernel; False = plain scan.  All variants return the identical result."""
     N, H, W, _ = rays_d.shape
     P = points.shape[0]
     if not (1 <= K <= 32) or K >= P:
@@ -206,8 +234,9 @@ def select_topk(rays_o, rays_d, points, K, eps=1e-6, cull=None):
     work = dict(flops=17.0 * R * P, nbytes=12.0 * R + 12.0 * P + 4.0 * K * R)
     if cull is None:
         cull = "grid" if P >= GRID_MIN_POINTS else False
-    if cull == "grid":
-        sv, perm, cells, views, G = view_grids(ro, rd.reshape(N, H * W, 3), pts, float(eps))
+    if cull in ("grid", "grid_torch"):
+        build = view_grids if cull == "grid" else view_grids_torch
+        sv, perm, cells, views, G = build(ro, rd.reshape(N, H * W, 3), pts, float(eps))
         call("papr_select_topk_grid", ro.data_ptr(), rd.data_ptr(), sv.data_ptr(), perm.data_ptr(), cells.data_ptr(), views.data_ptr(),
              N, H * W, P, G, K, float(eps), idx.data_ptr(), **work)
     elif cull:

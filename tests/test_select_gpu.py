@@ -152,3 +152,52 @@ def test_grid_kernel_matches_plain_scan_on_a_dense_frame():
         a = ops.select_topk(rays_o.cuda(), rays_d.cuda(), params["points"].cuda(), K, eps, cull="grid")
         b = ops.select_topk(rays_o.cuda(), rays_d.cuda(), params["points"].cuda(), K, eps, cull=False)
         assert torch.equal(a, b), (P, K)
+
+
+@pytest.mark.parametrize("P,views,stripe", [(30000, 1, None), (5000, 3, None), (30000, 1, (700, 800)), (1031, 2, None)])
+def test_grid_build_kernels_structure_and_selection(P, views, stripe):
+    """papr_select_grid_build (csrc/select_grid_build.cu): the structure it leaves is a valid input of the grid kernel --
+    every point of every view stored exactly once, inside the range of the cell its own gnomonic image falls into, v and
+    eps|v|^2 as the plain scan stages them, each cell's depth no larger than that of any of its points -- and the selection
+    on it equals the selection on the torch-built structure and the plain scan, also for a stripe of the frame that misses
+    the object (all points beyond the rays' extent)."""
+    from papr_b200 import ops
+    cfg = make_config("chair")
+    params = O.init_params(cfg, P, seed=P, cloud="shell")
+    h0, h1 = stripe if stripe else (300, 364)
+    rays_o, rays_d, _ = O.synthetic_rays(800, 800, cfg.dataset.coord_scale, n_views=views, seed=3, h0=h0, h1=h1, w0=200, w1=328)
+    ro, rd, pts = rays_o.cuda(), rays_d.cuda().contiguous(), params["points"].cuda()
+    N, R, eps = views, rd.shape[1] * rd.shape[2], 1e-6
+    sv, perm, cells, vw, G = ops.view_grids(ro, rd.reshape(N, R, 3), pts, eps)
+    torch.cuda.synchronize()
+    perm_v = perm.view(N, P).long()
+    assert torch.equal(perm_v.sort(dim=1).values, torch.arange(P, device="cuda").expand(N, P))
+    v = pts[perm_v] - ro[:, None, :]
+    sv = sv.view(N, P, 4)
+    assert torch.equal(sv[..., :3], v)
+    vn2 = torch.addcmul(torch.addcmul(v[..., 0] * v[..., 0], v[..., 1], v[..., 1]), v[..., 2], v[..., 2])
+    torch.testing.assert_close(sv[..., 3], eps * vn2, rtol=1e-6, atol=0)
+    cells = cells.view(N, G * G, 4)
+    start, end = cells[..., 0].long(), cells[..., 1].long()
+    assert torch.equal(start[:, 1:], end[:, :-1]) and (start[:, 0] == 0).all() and (end[:, -1] == P).all()
+    # cell of every stored point, recomputed from the view parameters the kernel will read
+    cell_of_pos = torch.searchsorted(end.contiguous(), torch.arange(P, device="cuda").expand(N, P).contiguous(), right=True)
+    e1, e2, c = vw[:, 0:3], vw[:, 3:6], vw[:, 6:9]
+    w3 = (v * c[:, None]).sum(-1)
+    valid = w3.abs() > 1.01e-3 * vn2.sqrt()
+    gx = (v * e1[:, None]).sum(-1) / w3
+    gy = (v * e2[:, None]).sum(-1) / w3
+    fx = ((gx - vw[:, None, 9]) * vw[:, None, 13])
+    fy = ((gy - vw[:, None, 10]) * vw[:, None, 14])
+    cx, cy = cell_of_pos % G, cell_of_pos // G
+    tol = 1e-3                                              # cells: a point may sit on an edge up to rounding
+    inside = ((fx >= cx - tol) | (cx == 0)) & ((fx <= cx + 1 + tol) | (cx == G - 1)) & ((fy >= cy - tol) | (cy == 0)) & ((fy <= cy + 1 + tol) | (cy == G - 1))
+    assert bool((inside | ~valid).all())
+    zmin = cells[..., 2].contiguous().view(torch.float32)
+    depth_ok = zmin.gather(1, cell_of_pos) <= w3.abs() * (1 + 1e-5)
+    assert bool(depth_ok.all())
+    assert bool((vw[:, 15] <= zmin.amin(1)).all()) and bool((vw[:, 16] >= vn2.amax(1)).all())
+    a = ops.select_topk(ro, rd, pts, 20, eps, cull="grid")
+    b = ops.select_topk(ro, rd, pts, 20, eps, cull="grid_torch")
+    c_ = ops.select_topk(ro, rd, pts, 20, eps, cull=False)
+    assert torch.equal(a, c_) and torch.equal(b, c_)
