@@ -330,6 +330,15 @@ __device__ __forceinline__ void pe_fill(float x, int L, float *dst)
     }
 }
 
+// 16-byte asynchronous global -> shared copies (LDGSTS): a lane can have its whole share of a staged tile in flight at
+// once without holding it in registers (a register-staged copy of 40 x 16 bytes per lane is issued in batches of a few
+// loads, one DRAM latency after the other: ncu r02, 22% of the prologue backward's stall samples sat on those stores)
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
+
 // One (ray, candidate) row per LANE (the default shape L = 6, F = 64: 117-wide key input, 142-wide value input).  The
 // warp-per-ray kernel at the top of this file spends ~400 warp instructions per row (every column costs shuffles /
 // shared-memory hops); here a lane carries its row in registers (9 sincos,
@@ -564,13 +573,11 @@ __global__ void __launch_bounds__(128, 2) attn_prologue_bwd_rows_kernel(const Pr
             for (int b = 0; b < NBK + NBV; ++b) {
                 const uint8_t *src = (b < NBK ? p.dkin + ((size_t)tile * NBK + b) * kBlockBytes : p.dvin + ((size_t)tile * NBV + (b - NBK)) * kBlockBytes) + roff;
 #pragma unroll
-                for (int it = 0; it < 8; ++it) {
-                    const uint4 t = *reinterpret_cast<const uint4 *>(src + it * 512);
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(wst + (uint32_t)b * 4096u + (uint32_t)it * 512u + (uint32_t)lane * 16u),
-                                 "r"(t.x), "r"(t.y), "r"(t.z), "r"(t.w) : "memory");
-                }
+                for (int it = 0; it < 8; ++it)
+                    cp_async16(wst + (uint32_t)b * 4096u + (uint32_t)it * 512u + (uint32_t)lane * 16u, src + it * 512);
             }
         }
+        // (the tile lands while the lane works out its row's geometry and encoding, which need none of it)
         float g[9], u[3] = {0.f, 0.f, 0.f}, den = 1.f;
         int pidx = 0;
 #pragma unroll
@@ -603,6 +610,7 @@ __global__ void __launch_bounds__(128, 2) attn_prologue_bwd_rows_kernel(const Pr
         const float stdv = sqrtf(var);
         const float rstd = 1.f / (stdv + p.eps);
         const float lv = live ? 1.f : 0.f;
+        cp_async_wait_all();
         __syncwarp();
         column_sums(acc_b2, row0);                   // g_b2 += sum over rows of d kin
         __syncwarp();
@@ -756,11 +764,8 @@ __global__ void __launch_bounds__(kScoreRowsWarps * 32, 1) score_rows_kernel(con
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
 #pragma unroll
-                for (int it = 0; it < 8; ++it) {
-                    const uint4 t = *reinterpret_cast<const uint4 *>(src + (size_t)b * kBlockBytes + it * 512);
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(wst + (uint32_t)b * 4096u + (uint32_t)it * 512u + (uint32_t)lane * 16u),
-                                 "r"(t.x), "r"(t.y), "r"(t.z), "r"(t.w) : "memory");
-                }
+                for (int it = 0; it < 8; ++it)
+                    cp_async16(wst + (uint32_t)b * 4096u + (uint32_t)it * 512u + (uint32_t)lane * 16u, src + (size_t)b * kBlockBytes + it * 512);
             }
         }
         const int64_t row = row0 + lane;
@@ -781,6 +786,7 @@ __global__ void __launch_bounds__(kScoreRowsWarps * 32, 1) score_rows_kernel(con
             part = warp_sum(part);
             if (ray == rr) usum = part;
         }
+        cp_async_wait_all();
         __syncwarp();
         const float4 *uap = reinterpret_cast<const float4 *>(p.ua + ray * 256);
         float c0 = 0.f, S = 0.f, Q = 0.f, T = 0.f;
