@@ -122,6 +122,53 @@ def test_score_rows_kernel_matches_warp_per_ray(R, K, relu):
     assert float((new[1] - old[1]).abs().max()) <= 1e-5
 
 
+@pytest.mark.parametrize("R,K", [(301, 20), (5000, 20), (77, 16), (64, 13), (90, 24), (40, 31), (33, 5)])
+def test_key_score_bwd_kernel_families_agree(R, K):
+    """d h5 / zsum / dssum of the score backward (the chain through ua . LN(h5), attn.py:39-42): the block-major kernel and
+    the warp-per-row kernel against a float64 evaluation on the same bf16 h5.  (A third family that staged a ray's rows
+    through shared memory with cp.async one ray ahead, 8 warps per SM, was correct but slower: 4.1 vs 3.6 ms at 800x800.)"""
+    g = torch.Generator(device="cuda").manual_seed(R + K)
+    M = R * K
+    sh = types.SimpleNamespace(R=R, K=K, M=M, C=32, score_relu=True, normalize=True, bkg_score=5.0, eps=1e-6)
+    h32 = torch.randn(M, 256, device="cuda", generator=g) * 2 + 0.5
+    h5 = ops.Blocked.from_f32(h32)
+    hq = h5.to_f32(M, 256).double()
+    ua = torch.randn(R, 256, device="cuda", generator=g) * 0.2
+    cprime = torch.randn(R, device="cuda", generator=g)
+    influ = torch.rand(500, device="cuda", generator=g)
+    idx = torch.randint(0, 500, (R, K), device="cuda", generator=g, dtype=torch.int32)
+    v = torch.randn(ops.pad_rows(M), 32, device="cuda", generator=g)
+    stats = A._score_blend_fwd(sh, h5, None, ua, cprime, influ, idx, v)[3]
+    d_score = torch.randn(M, device="cuda", generator=g)
+    mean, std = hq.mean(-1, keepdim=True), hq.std(-1, keepdim=True)
+    z = (hq - mean) / (std + 1e-6)
+    uar, ds = ua.double().repeat_interleave(K, 0), d_score.double()[:, None]
+    dz = ds * uar                                            # score = ua . z + c'
+    m1 = dz.mean(-1, keepdim=True)
+    m2 = (dz * z).sum(-1, keepdim=True) / (255.0 * std)
+    want = (dz - m1) / (std + 1e-6) - z * m2                 # through z = (h - mean) / (std + eps), unbiased std
+    want_zsum = (ds * z).view(R, K, 256).sum(1)
+    outs = {}
+    for name, env in (("blocks", None), ("rows", "PAPR_KEY_SCORE_ROWWISE")):
+        if env:
+            os.environ[env] = "1"
+        try:
+            dh5, _, zsum, dssum, _ = A._key_score_bwd(sh, d_score, h5, None, stats, ua, want_bias=False)
+        finally:
+            if env:
+                os.environ.pop(env, None)
+        torch.cuda.synchronize()
+        got = dh5.to_f32(M, 256).double()
+        scale = float(want.abs().max())
+        assert float((got - want).abs().max()) <= 6e-3 * scale, (name, float((got - want).abs().max()), scale)      # bf16 output
+        assert float((zsum.double() - want_zsum).abs().max()) <= 2e-4 * max(1.0, float(want_zsum.abs().max())), name
+        assert float((dssum.double() - d_score.double().view(R, K).sum(1)).abs().max()) <= 1e-5, name
+        pad = dh5.to_f32(ops.pad_rows(M), 256)[M:]
+        assert not bool(pad.any()), name                     # padding rows of the tile-blocked gradient are zero
+        outs[name] = got
+    assert float((outs["rows"] - outs["blocks"]).abs().max()) <= 8e-3 * float(want.abs().max())       # one bf16 ulp at the top
+
+
 @pytest.mark.parametrize("L", [6, 4])
 @pytest.mark.parametrize("R", [1, 255, 257, 5000])
 def test_query_prologue_matches_torch_posenc_and_innorm(L, R):
