@@ -27,13 +27,19 @@ constexpr int kSelTile = 2048;   // points per shared-memory tile (32 KB as floa
 
 // ---------------------------------------------------------------------------------------------------------------
 // Two-phase exact selection (the product path).
-//   Phase 1 streams all points with a CHEAP key, a = |v x d|^2 + eps*|v|^2 (10 FP32 instructions per pair instead of
-//   22), and keeps the 32 smallest per ray -- the warp is 32 lanes wide, so 32 candidates cost the same as K.
+//   Phase 1 streams all points with a CHEAP key, a = |v x d|^2 + eps*(|v|^2 - (v.d)^2 / den) (15 FP32 instructions per
+//   pair instead of 22), and keeps the 32 smallest per ray -- the warp is 32 lanes wide, so 32 candidates cost the same
+//   as K.  In exact arithmetic a IS the reference's squared distance times den = |d|^2 + eps: with t = (v.d)/den,
+//   |v - t d|^2 den = |v x d|^2 + eps |v|^2 - eps (v.d)^2/den.  (Until the end of round 2 the last term was left out:
+//   the cheap key then exceeds the exact one by up to eps |v|^2 -- 0.016 at the Caterpillar scale, where neighbouring
+//   keys differ by 0.0005 -- which the 12 spare candidates of a 32-wide list absorbed in every test, but which the
+//   error bound below did not cover; the grid kernel's tighter threshold exposed it.)
 //   Phase 2 evaluates the reference-exact key (same rounding sequence as above) for those 32 candidates only and
 //   ranks them by (key, index).
 // The result is provably the reference's top-K whenever the K-th exact key, scaled by den, lies below
 // a32 - err(a32), where a32 is the largest cheap key kept and err() bounds |cheap - exact*den| for ANY pair
-// (derivation in DESIGN.md section 4: err(x) = 32 u V sqrt(x) + 128 u^2 V^2 + 8 u x, u = 2^-24, V = max|v| * |d|).
+// (err(x) = 32 u V sqrt(x) + 128 u^2 V^2 + 8 u x + 8 u eps max|v|^2, u = 2^-24, V = max|v| * |d|: the rounding of the
+// cross product, of the sums, and of the eps term).
 // Every point that was not kept has cheap key >= a32, hence exact key above the K-th one.  Rays that fail the test
 // (exact ties at the boundary, degenerate clouds) are rescanned with the exact key -- rare, and still bit-exact.
 // ---------------------------------------------------------------------------------------------------------------
@@ -78,7 +84,7 @@ select_topk2_kernel(const float *__restrict__ rays_o, const float *__restrict__ 
 
     const float ox = rays_o[3 * view + 0], oy = rays_o[3 * view + 1], oz = rays_o[3 * view + 2];
     const int64_t ray0 = (int64_t)blk * (kSelWarps * RPW) + warp * RPW;
-    float dx[RPW], dy[RPW], dz[RPW], thr[RPW], lk[RPW];
+    float dx[RPW], dy[RPW], dz[RPW], thr[RPW], lk[RPW], epd[RPW];
     int li[RPW];
 #pragma unroll
     for (int j = 0; j < RPW; ++j) {
@@ -87,6 +93,7 @@ select_topk2_kernel(const float *__restrict__ rays_o, const float *__restrict__ 
         const float *d = rays_d + ((int64_t)view * rays_per_view + r) * 3;
         dx[j] = d[0]; dy[j] = d[1]; dz[j] = d[2];
         thr[j] = INF; lk[j] = INF; li[j] = -1;
+        epd[j] = eps / (fmaf(dz[j], dz[j], fmaf(dy[j], dy[j], dx[j] * dx[j])) + eps);
     }
     float wmax = 0.f;                 // max |v|^2 over the points this thread staged (reduced over the block below)
 
@@ -114,7 +121,8 @@ select_topk2_kernel(const float *__restrict__ rays_o, const float *__restrict__ 
                 const float cx = fmaf(v.y, dz[j], -v.z * dy[j]);
                 const float cy = fmaf(v.z, dx[j], -v.x * dz[j]);
                 const float cz = fmaf(v.x, dy[j], -v.y * dx[j]);
-                const float a = fmaf(cx, cx, fmaf(cy, cy, fmaf(cz, cz, v.w)));
+                const float sd = fmaf(v.x, dx[j], fmaf(v.y, dy[j], v.z * dz[j]));
+                const float a = fmaf(-epd[j], sd * sd, fmaf(cx, cx, fmaf(cy, cy, fmaf(cz, cz, v.w))));
                 if (__any_sync(full, a < thr[j])) {
                     unsigned m = __ballot_sync(full, a < thr[j]);
                     while (m) {
@@ -167,7 +175,7 @@ select_topk2_kernel(const float *__restrict__ rays_o, const float *__restrict__ 
         const float a32 = thr[j];
         const float u = 5.9604645e-8f;
         const float V2 = wmax * den;                            // (max|v| * |d|)^2, den >= |d|^2
-        const float err = 32.f * u * sqrtf(V2 * a32) + 128.f * u * u * V2 + 8.f * u * a32;
+        const float err = 32.f * u * sqrtf(V2 * a32) + 128.f * u * u * V2 + 8.f * u * a32 + 8.f * u * eps * wmax;
         const bool safe = (a32 == INF) || (who != 0 && a32 > 1e-8f * fmaxf(V2, 1.f) && eK * den * (1.f + 4.f * u) < a32 - err);
         if (safe) {
             if (ci >= 0 && rank < K) idx_out[((int64_t)view * rays_per_view + r) * K + rank] = ci;
@@ -244,7 +252,7 @@ select_topk3_kernel(const float *__restrict__ rays_o, const float *__restrict__ 
 
     const float ox = rays_o[3 * view + 0], oy = rays_o[3 * view + 1], oz = rays_o[3 * view + 2];
     const int64_t ray0 = (int64_t)blk * (kSelWarps * RPW) + warp * RPW;
-    float dx[RPW], dy[RPW], dz[RPW], thr[RPW], lk[RPW];
+    float dx[RPW], dy[RPW], dz[RPW], thr[RPW], lk[RPW], epd[RPW];
     int li[RPW];
     float cxs = 0.f, cys = 0.f, czs = 0.f, dmin2 = INF;
 #pragma unroll
@@ -255,6 +263,7 @@ select_topk3_kernel(const float *__restrict__ rays_o, const float *__restrict__ 
         dx[j] = d[0]; dy[j] = d[1]; dz[j] = d[2];
         thr[j] = INF; lk[j] = INF; li[j] = -1;
         const float n2 = dx[j] * dx[j] + dy[j] * dy[j] + dz[j] * dz[j];
+        epd[j] = eps / (n2 + eps);
         const float rn = rsqrtf(fmaxf(n2, 1e-30f));
         cxs += dx[j] * rn; cys += dy[j] * rn; czs += dz[j] * rn;
         dmin2 = fminf(dmin2, n2);
@@ -326,7 +335,8 @@ select_topk3_kernel(const float *__restrict__ rays_o, const float *__restrict__ 
                 const float cx = fmaf(v.y, dz[j], -v.z * dy[j]);
                 const float cy = fmaf(v.z, dx[j], -v.x * dz[j]);
                 const float cz = fmaf(v.x, dy[j], -v.y * dx[j]);
-                const float a = fmaf(cx, cx, fmaf(cy, cy, fmaf(cz, cz, ew)));
+                const float sd = fmaf(v.x, dx[j], fmaf(v.y, dy[j], v.z * dz[j]));
+                const float a = fmaf(-epd[j], sd * sd, fmaf(cx, cx, fmaf(cy, cy, fmaf(cz, cz, ew))));
                 unsigned m = __ballot_sync(full, a < thr[j]);
                 while (m) {
                     const int src = __ffs(m) - 1;
@@ -371,7 +381,7 @@ select_topk3_kernel(const float *__restrict__ rays_o, const float *__restrict__ 
         const float a32 = thr[j];
         const float u = 5.9604645e-8f;
         const float V2 = wmax * den;
-        const float err = 32.f * u * sqrtf(V2 * a32) + 128.f * u * u * V2 + 8.f * u * a32;
+        const float err = 32.f * u * sqrtf(V2 * a32) + 128.f * u * u * V2 + 8.f * u * a32 + 8.f * u * eps * wmax;
         const bool finite32 = a32 < 1e30f;                      // padding points carry huge finite keys
         const bool safe = who != 0 && (!finite32 || (a32 > 1e-8f * fmaxf(V2, 1.f) && eK * den * (1.f + 4.f * u) < a32 - err));
         if (safe) {
@@ -430,7 +440,8 @@ select_grid_kernel(const float *__restrict__ rays_o, const float *__restrict__ r
                    const int32_t *__restrict__ perm /* (n_views*P) original point index */,
                    const int4 *__restrict__ cells /* (n_views*G*G): start, end, zmin bits, 0 */,
                    const float *__restrict__ views /* (n_views, kGridViewFloats) */,
-                   int64_t rays_per_view, int P, int G, int K, float eps, int32_t *__restrict__ idx_out, int blocks_per_view)
+                   int64_t rays_per_view, int P, int G, int K, float eps, int32_t *__restrict__ idx_out, int blocks_per_view,
+                   int last /* lane whose key is a ray's threshold: K - 1 .. 31 */)
 {
     const int view = blockIdx.x / blocks_per_view;
     const int blk = blockIdx.x - view * blocks_per_view;
@@ -447,7 +458,7 @@ select_grid_kernel(const float *__restrict__ rays_o, const float *__restrict__ r
 
     const int64_t ray0 = (int64_t)blk * (kSelWarps * RPW) + warp * RPW;
     if (ray0 >= rays_per_view) return;                          // warp-uniform; no block-wide barrier below
-    float dx[RPW], dy[RPW], dz[RPW], thr[RPW], lk[RPW];
+    float dx[RPW], dy[RPW], dz[RPW], thr[RPW], lk[RPW], epd[RPW];
     int li[RPW];
     float bx0 = INF, bx1 = -INF, by0 = INF, by1 = -INF, h2max = 0.f, dmin2 = INF, dmax2 = 0.f;
     bool can_cull = true;
@@ -459,6 +470,7 @@ select_grid_kernel(const float *__restrict__ rays_o, const float *__restrict__ r
         dx[j] = d[0]; dy[j] = d[1]; dz[j] = d[2];
         thr[j] = INF; lk[j] = INF; li[j] = -1;
         const float n2 = dx[j] * dx[j] + dy[j] * dy[j] + dz[j] * dz[j];
+        epd[j] = eps / (n2 + eps);
         const float w3 = dx[j] * ccx + dy[j] * ccy + dz[j] * ccz;
         can_cull = can_cull && (w3 * w3 > 0.04f * n2) && w3 > 0.f && n2 > 1e-30f && n2 < 1e30f;
         const float iw = 1.f / w3;
@@ -477,8 +489,14 @@ select_grid_kernel(const float *__restrict__ rays_o, const float *__restrict__ r
     // lower bound of the COMPUTED cheap key of any point at gnomonic distance >= dist of a cell with smallest depth z
     auto cell_bound = [&](float z, float dist2) -> float {
         const float b = z * z * dist2 * scale;
-        return b - (32.f * u * sqrtf(V2c * b) + 128.f * u * u * V2c + 8.f * u * b);
+        return b - (32.f * u * sqrtf(V2c * b) + 128.f * u * u * V2c + 8.f * u * b + 8.f * u * eps * wmax);
     };
+    // The threshold of a ray is the key in lane `last` -- by default the (K + 2)-nd smallest cheap key seen, not the 32nd: every point outside lanes 0..last of
+    // the list has a cheap key >= the final threshold (rejected points had key >= the threshold of their time, thresholds
+    // only fall, and an entry pushed beyond lane `last` is no smaller than lane `last`), which is all phase 2's safety test
+    // needs.  The tighter threshold means fewer insertions and an earlier end of the ring walk; the price is a smaller
+    // margin between the K-th exact key and the threshold -- one neighbour's gap instead of twelve at K = 20 -- i.e. an
+    // exact rescan where the (K+1)-st and (K+2)-nd neighbours tie with the K-th to 1e-6 (lattices, duplicates).
     int hcx = G >> 1, hcy = G >> 1;
     if (can_cull) {
         hcx = min(max((int)floorf((0.5f * (bx0 + bx1) - gminx) * icx), 0), G - 1);
@@ -540,14 +558,15 @@ select_grid_kernel(const float *__restrict__ rays_o, const float *__restrict__ r
                         const float kx = fmaf(v.y, dz[j], -v.z * dy[j]);
                         const float ky = fmaf(v.z, dx[j], -v.x * dz[j]);
                         const float kz = fmaf(v.x, dy[j], -v.y * dx[j]);
-                        const float a = fmaf(kx, kx, fmaf(ky, ky, fmaf(kz, kz, v.w)));
+                        const float sd = fmaf(v.x, dx[j], fmaf(v.y, dy[j], v.z * dz[j]));
+                        const float a = fmaf(-epd[j], sd * sd, fmaf(kx, kx, fmaf(ky, ky, fmaf(kz, kz, v.w))));
                         unsigned m = __ballot_sync(full, a < thr[j]);
                         while (m) {
                             const int s2 = __ffs(m) - 1;
                             m &= m - 1;
                             const float ck = __shfl_sync(full, a, s2);
                             const int ci = c + s2;
-                            if (ck < thr[j]) thr[j] = list_insert(lk[j], li[j], ck, ci, lane, 31);
+                            if (ck < thr[j]) thr[j] = list_insert(lk[j], li[j], ck, ci, lane, last);
                         }
                     }
                 }
@@ -586,7 +605,7 @@ select_grid_kernel(const float *__restrict__ rays_o, const float *__restrict__ r
         const float eK = __shfl_sync(full, ek, who ? __ffs(who) - 1 : 0);
         const float a32 = thr[j];
         const float V2 = wmax * den;
-        const float err = 32.f * u * sqrtf(V2 * a32) + 128.f * u * u * V2 + 8.f * u * a32;
+        const float err = 32.f * u * sqrtf(V2 * a32) + 128.f * u * u * V2 + 8.f * u * a32 + 8.f * u * eps * wmax;
         const bool safe = who != 0 && ((a32 == INF) || (a32 > 1e-8f * fmaxf(V2, 1.f) && eK * den * (1.f + 4.f * u) < a32 - err));
         if (safe) {
             if (ci >= 0 && rank < K) idx_out[((int64_t)view * rays_per_view + r) * K + rank] = ci;
@@ -675,9 +694,14 @@ extern "C" int papr_select_topk_grid(const float *rays_o, const float *rays_d, c
     const int64_t rays_per_block = kSelWarps * RPW;
     const int64_t blocks_per_view = (rays_per_view + rays_per_block - 1) / rays_per_block;
     if (blocks_per_view * n_views > INT32_MAX) return PAPR_ERR_INVALID_ARGUMENT;
+    // threshold lane: the (K+2)-nd candidate by default; PAPR_SELECT_LAST=31 restores the widest list (A/B switch)
+    int last = K + 1;
+    if (const char *e = getenv("PAPR_SELECT_LAST")) last = atoi(e);
+    last = last < K ? K : last;
+    last = last > 31 ? 31 : last;
     select_grid_kernel<RPW><<<(unsigned)(blocks_per_view * n_views), kSelThreads, 0, (cudaStream_t)stream>>>(
         rays_o, rays_d, (const float4 *)sorted_v, perm, (const int4 *)cells, view_params, rays_per_view, (int)P, G, K, eps, idx_out,
-        (int)blocks_per_view);
+        (int)blocks_per_view, last);
     return check_launch();
 }
 

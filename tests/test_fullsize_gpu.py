@@ -185,6 +185,17 @@ def test_caterpillar_shape_select_exact_and_chunked_training_equals_unchunked():
     pick = torch.randint(0, 1080 * 1920, (1500,), generator=torch.Generator().manual_seed(4))
     want, _ = O.select_topk(rays_o, rays_d.reshape(-1, 3)[pick].reshape(1, 1, -1, 3), params["points"], 20)
     assert torch.equal(idx.reshape(-1, 20)[pick.cuda()].cpu().long(), want.reshape(-1, 20))
+    # The same with the candidate list cut to K + 1 entries (one neighbour of margin) and at its full 32: at this scale
+    # eps |v|^2 = 0.016 is thirty times the gap between neighbouring keys, so a phase-1 key that is not the exact key
+    # times den up to rounding (the eps (v.d)^2 / den term) loses true neighbours here -- and did, until it was added.
+    import os
+    for last in ("20", "31"):
+        os.environ["PAPR_SELECT_LAST"] = last
+        try:
+            alt = ops.select_topk(rays_o.cuda(), rays_d.cuda(), params["points"].cuda(), 20)
+        finally:
+            os.environ.pop("PAPR_SELECT_LAST", None)
+        assert torch.equal(alt, idx), last
     model = PAPR(cfg, device="cuda", precision="bf16").cuda()
     model.load_my_state_dict({k: v.clone() for k, v in params.items()})
     assert model.proximity_attn.L == 4 and model.proximity_attn.dk == 81 and model.proximity_attn.dv == 118
