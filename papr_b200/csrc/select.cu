@@ -67,6 +67,32 @@ __device__ __forceinline__ float list_insert(float &lk, int &li, float ck, int c
     return __shfl_sync(full, lk, last);
 }
 
+// A whole batch at once: the 32 keys of a batch (one per lane, +inf where there is no point) are sorted across the warp
+// (bitonic network, 15 compare-exchange stages), laid against the list in reverse -- min(list[l], batch[31 - l]) is a
+// bitonic sequence holding the 32 smallest of the union -- and merged in 5 more stages.  ~150 instructions whatever the
+// number of newcomers, where the one-at-a-time insert costs ~14 instructions per newcomer on a chain of four dependent
+// warp-wide operations: the first batches of a ray (empty or loose list: most of their points enter) go this way.
+__device__ __forceinline__ void cmp_exchange(float &k, int &i, int stride, bool take_min)
+{
+    const float ok = __shfl_xor_sync(0xffffffffu, k, stride);
+    const int oi = __shfl_xor_sync(0xffffffffu, i, stride);
+    if (take_min ? (ok < k) : (ok > k)) { k = ok; i = oi; }
+}
+__device__ __forceinline__ void list_merge_batch(float &lk, int &li, float bk, int bi, int lane)
+{
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1) {
+        const bool up = (lane & size) == 0 || size == 32;
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) cmp_exchange(bk, bi, stride, ((lane & stride) == 0) == up);
+    }
+    const float rk = __shfl_sync(0xffffffffu, bk, 31 - lane);
+    const int ri = __shfl_sync(0xffffffffu, bi, 31 - lane);
+    if (rk < lk) { lk = rk; li = ri; }
+#pragma unroll
+    for (int stride = 16; stride > 0; stride >>= 1) cmp_exchange(lk, li, stride, (lane & stride) == 0);
+}
+
 template <int RPW>
 __global__ void __launch_bounds__(kSelThreads)
 select_topk2_kernel(const float *__restrict__ rays_o, const float *__restrict__ rays_d,
@@ -441,7 +467,7 @@ select_grid_kernel(const float *__restrict__ rays_o, const float *__restrict__ r
                    const int4 *__restrict__ cells /* (n_views*G*G): start, end, zmin bits, 0 */,
                    const float *__restrict__ views /* (n_views, kGridViewFloats) */,
                    int64_t rays_per_view, int P, int G, int K, float eps, int32_t *__restrict__ idx_out, int blocks_per_view,
-                   int last /* lane whose key is a ray's threshold: K - 1 .. 31 */)
+                   int last /* lane whose key is a ray's threshold: K .. 31 */, int merge_min /* newcomers per batch from which the batch is merged */)
 {
     const int view = blockIdx.x / blocks_per_view;
     const int blk = blockIdx.x - view * blocks_per_view;
@@ -561,6 +587,11 @@ select_grid_kernel(const float *__restrict__ rays_o, const float *__restrict__ r
                         const float sd = fmaf(v.x, dx[j], fmaf(v.y, dy[j], v.z * dz[j]));
                         const float a = fmaf(-epd[j], sd * sd, fmaf(kx, kx, fmaf(ky, ky, fmaf(kz, kz, v.w))));
                         unsigned m = __ballot_sync(full, a < thr[j]);
+                        if (__popc(m) >= merge_min) {                        // many newcomers: sort the batch and merge
+                            list_merge_batch(lk[j], li[j], a, pi < ce ? pi : -1, lane);
+                            thr[j] = __shfl_sync(full, lk[j], last);
+                            continue;
+                        }
                         while (m) {
                             const int s2 = __ffs(m) - 1;
                             m &= m - 1;
@@ -699,9 +730,11 @@ extern "C" int papr_select_topk_grid(const float *rays_o, const float *rays_d, c
     if (const char *e = getenv("PAPR_SELECT_LAST")) last = atoi(e);
     last = last < K ? K : last;
     last = last > 31 ? 31 : last;
+    int merge_min = 16;                                 // PAPR_SELECT_MERGE=33 switches the batch merge off (A/B switch)
+    if (const char *e = getenv("PAPR_SELECT_MERGE")) merge_min = atoi(e);
     select_grid_kernel<RPW><<<(unsigned)(blocks_per_view * n_views), kSelThreads, 0, (cudaStream_t)stream>>>(
         rays_o, rays_d, (const float4 *)sorted_v, perm, (const int4 *)cells, view_params, rays_per_view, (int)P, G, K, eps, idx_out,
-        (int)blocks_per_view, last);
+        (int)blocks_per_view, last, merge_min);
     return check_launch();
 }
 
