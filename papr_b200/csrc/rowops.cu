@@ -548,7 +548,7 @@ __global__ void __launch_bounds__(128, 2) attn_prologue_bwd_rows_kernel(const Pr
 #pragma unroll
     for (int e = 0; e < 8; ++e) { acc_a2[e] = 0.f; acc_b2[e] = 0.f; }
     auto column_sums = [&](float *acc, int64_t row0) {
-#pragma unroll 4
+#pragma unroll 8
         for (int r = half * 16; r < half * 16 + 16; ++r) {
             if (row0 + r < M) {
                 uint4 q;
@@ -562,7 +562,20 @@ __global__ void __launch_bounds__(128, 2) attn_prologue_bwd_rows_kernel(const Pr
         }
     };
 
-    for (int64_t row0 = ((int64_t)blockIdx.x * kWarps + warp) * 32; row0 < M_pad; row0 += (int64_t)gridDim.x * kWarps * 32) {
+    // The row's candidate index, and through it the point, are two dependent global loads ahead of everything else (ncu r02
+    // final: 14% of the stall samples on the first uses of the point and of the ray direction): the index is requested two
+    // iterations ahead, the point and the ray direction one iteration ahead.
+    const int64_t row_step = (int64_t)gridDim.x * kWarps * 32;
+    const int64_t row_first = ((int64_t)blockIdx.x * kWarps + warp) * 32 + lane;
+    int pidx_cur = 0, pidx_nxt = 0;
+    float pt_cur[3] = {0.f, 0.f, 0.f}, rd_cur[3] = {0.f, 0.f, 1.f};
+    if (row_first < M) {
+        pidx_cur = p.idx[row_first];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { pt_cur[i] = p.points[(size_t)pidx_cur * 3 + i]; rd_cur[i] = p.rays_d[(row_first / p.K) * 3 + i]; }
+    }
+    if (row_first + row_step < M) pidx_nxt = p.idx[row_first + row_step];
+    for (int64_t row0 = ((int64_t)blockIdx.x * kWarps + warp) * 32; row0 < M_pad; row0 += row_step) {
         const int64_t row = row0 + lane;
         const bool live = row < M;
         // stage the 32 rows: 4 KB contiguous per 64-column block
@@ -579,14 +592,23 @@ __global__ void __launch_bounds__(128, 2) attn_prologue_bwd_rows_kernel(const Pr
         }
         // (the tile lands while the lane works out its row's geometry and encoding, which need none of it)
         float g[9], u[3] = {0.f, 0.f, 0.f}, den = 1.f;
-        int pidx = 0;
+        const int pidx = pidx_cur;
+        const float pt[3] = {pt_cur[0], pt_cur[1], pt_cur[2]}, rd[3] = {rd_cur[0], rd_cur[1], rd_cur[2]};
+        {                                                       // requests for the next two iterations
+            const int64_t rn = row + row_step;
+            pidx_cur = pidx_nxt;
+            if (rn < M) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) { pt_cur[i] = p.points[(size_t)pidx_cur * 3 + i]; rd_cur[i] = p.rays_d[(rn / p.K) * 3 + i]; }
+            }
+            pidx_nxt = rn + row_step < M ? p.idx[rn + row_step] : 0;
+        }
 #pragma unroll
         for (int i = 0; i < 9; ++i) g[i] = 0.f;
         if (live) {
             const int64_t ray = row / p.K;
             const int64_t view = ray / p.rays_per_view;
-            pidx = p.idx[row];
-            const Geometry geo = ray_point_geometry(p.points + (size_t)pidx * 3, p.rays_o + view * 3, p.rays_d + ray * 3, p.eps, u, &den);
+            const Geometry geo = ray_point_geometry(pt, p.rays_o + view * 3, rd, p.eps, u, &den);
 #pragma unroll
             for (int i = 0; i < 9; ++i) g[i] = geo.g[i];
         }
